@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE ONLY - generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden
+The reference is imported read-only through oracle/ref_harness.py (stubs for gymnasium/pygame,
+per-game Philox stream in place of the global ``random``). The .npz files are the pins for the
+C oracle (tests/test_oracle_golden.py) and, through the oracle and directly, for the CUDA path
+(tests/test_gpu_parity.py). Nothing here runs on the GPU box.
+
+Fixture families
+  game_{A,B}_N*.npz      raw HexGame.make_move traces (random moves incl. occupied cells, played on
+                         past the win until the board is full): ret/board/regions/counter/cur/done/winner per ply
+  selfplay_N*_a*.npz     SelfPlayEnv (variant B) + BaseRandomPolicy rollouts with DummyVecEnv-style auto-reset;
+                         agent either sampled by BaseRandomPolicy from the same stream ("fused") or given
+                         externally (with some illegal moves)
+  envA_N*_of*.npz        variant-A HexEnv(opponent_policy=minihex.random_policy) rollouts, same two agent modes
+  kat.npz                the four hand-checked known-answer tests of SURVEY.md section 8c
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+from oracle.philox import GameStream, ListStream  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+NONE = -1
+
+
+def code(w):
+    return NONE if w is None else int(w)
+
+
+def snap_game(g):
+    return (np.array(g.board, dtype=np.int8).copy(), np.array(g.regions, dtype=np.uint8).copy(),
+            np.array(g.region_counter, dtype=np.int16).copy(), int(g.current_player_num), int(bool(g.done)), code(g.winner))
+
+
+def gen_raw_games(variant, N, n_games, seed):
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed)
+    C = N * N
+    T = C + C // 2 + 4
+    moves = np.zeros((n_games, T), np.int32)
+    ret = np.zeros((n_games, T), np.int8)
+    board = np.zeros((n_games, T, N, N), np.int8)
+    regions = np.zeros((n_games, T, 2, N + 2, N + 2), np.uint8)
+    counter = np.zeros((n_games, T, 2), np.int16)
+    cur = np.zeros((n_games, T), np.int8)
+    done = np.zeros((n_games, T), np.uint8)
+    winner = np.zeros((n_games, T), np.int8)
+    for gi in range(n_games):
+        if variant == "A":
+            g = A.HexGame(A.player.BLACK, A.player.EMPTY * np.ones((N, N)), A.player.BLACK)
+        else:
+            g = B.HexGame(0, np.zeros((N, N)))
+        # a random permutation with ~1/3 random repeats mixed in (=> some moves hit occupied cells)
+        perm = list(rs.permutation(C))
+        seq = []
+        while len(seq) < T:
+            if perm and rs.rand() > 0.3:
+                seq.append(perm.pop())
+            else:
+                seq.append(int(rs.randint(C)))
+        for t, a in enumerate(seq):
+            moves[gi, t] = a
+            ret[gi, t] = code(g.make_move(a))
+            b_, r_, c_, cu, dn, wn = snap_game(g)
+            board[gi, t], regions[gi, t], counter[gi, t], cur[gi, t], done[gi, t], winner[gi, t] = b_, r_, c_, cu, dn, wn
+    np.savez_compressed(os.path.join(OUT, "game_%s_N%d.npz" % (variant, N)), N=N, moves=moves, ret=ret, board=board,
+                        regions=regions, counter=counter, cur=cur, done=done, winner=winner)
+
+
+def rollout(kind, N, G, T, seed, agent_mode, fused, opponent_first=False, illegal_rate=0.05):
+    """kind 'B' = SelfPlayEnv, 'A' = variant-A HexEnv. One env object per game, own stream each."""
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed ^ 0x5EED)
+    C = N * N
+    out = dict(actions=np.zeros((T, G), np.int32), obs=np.zeros((T, G, N, N), np.int8), mask=np.zeros((T, G, C), np.uint8),
+               reward=np.zeros((T, G), np.float32), done=np.zeros((T, G), np.uint8), term_obs=np.zeros((T, G, N, N), np.int8),
+               regions=np.zeros((T, G, 2, N + 2, N + 2), np.uint8), counter=np.zeros((T, G, 2), np.int16),
+               sim_cur=np.zeros((T, G), np.int8), draws=np.zeros((T, G), np.uint32),
+               obs0=np.zeros((G, N, N), np.int8), mask0=np.zeros((G, C), np.uint8), agent=np.zeros(G, np.int8),
+               draws0=np.zeros(G, np.uint32))
+    for gi in range(G):
+        stream = GameStream(seed, gi)
+        rh.set_rng(stream)
+        if kind == "B":
+            env = S.selfplay_wrapper(B.HexEnv)(board_size=N, agent_player_num=None if agent_mode == 2 else agent_mode)
+            mask_fn = env.legal_actions
+            choose = lambda board: S.BaseRandomPolicy().choose_action(board)
+        else:
+            env = A.HexEnv(opponent_policy=minihex.random_policy, board_size=N,
+                           current_player_num=A.player.WHITE if opponent_first else A.player.BLACK)
+            mask_fn = env.get_action_mask
+            choose = lambda board: minihex.random_policy(board)
+        obs, _ = env.reset()
+        out["obs0"][gi] = obs
+        out["mask0"][gi] = mask_fn()
+        out["agent"][gi] = env.agent_player_num if kind == "B" else 0
+        out["draws0"][gi] = stream.idx
+        for t in range(T):
+            mask = mask_fn()
+            if fused:
+                a = int(choose(obs))
+            else:
+                legal = np.flatnonzero(mask)
+                a = int(rs.randint(C)) if rs.rand() < illegal_rate else int(legal[rs.randint(len(legal))])
+            obs, r, done, _, _ = env.step(a)
+            out["actions"][t, gi] = a
+            out["reward"][t, gi] = r
+            out["done"][t, gi] = done
+            if done:
+                out["term_obs"][t, gi] = obs
+                obs, _ = env.reset()
+            out["obs"][t, gi] = obs
+            out["mask"][t, gi] = mask_fn()
+            out["regions"][t, gi] = env.simulator.regions
+            out["counter"][t, gi] = env.simulator.region_counter
+            out["sim_cur"][t, gi] = env.simulator.current_player_num
+            out["draws"][t, gi] = stream.idx
+    return out
+
+
+def gen_kats():
+    """SURVEY.md section 8c KAT-1..4, re-derived from the reference here and stored verbatim."""
+    minihex, A, B, S = rh.load()
+    k = {}
+    g = A.HexGame(A.player.BLACK, A.player.EMPTY * np.ones((3, 3)), A.player.BLACK)
+    rets, empties = [], []
+    for m in [4, 0, 1, 3, 7]:
+        rets.append(code(g.make_move(m)))
+        empties.append(int(g.empty_fields))
+    k["kat1_ret"], k["kat1_empty_fields"] = np.array(rets), np.array(empties)
+    k["kat1_board"], k["kat1_regions"], k["kat1_counter"] = g.board.copy(), g.regions.copy(), g.region_counter.copy()
+    k["kat1_again"] = np.array([code(g.make_move(4)), g.current_player_num])
+
+    def selfplay(draws, agent, acts, name):
+        rh.set_rng(ListStream(draws))
+        env = S.selfplay_wrapper(B.HexEnv)(board_size=3, agent_player_num=agent)
+        obs, _ = env.reset()
+        seq_obs, seq_r, seq_d = [np.array(obs)], [], []
+        for a in acts:
+            obs, r, d, _, _ = env.step(a)
+            seq_obs.append(np.array(obs)); seq_r.append(r); seq_d.append(d)
+        k[name + "_obs"], k[name + "_r"], k[name + "_d"] = np.array(seq_obs), np.array(seq_r), np.array(seq_d)
+        k[name + "_regions"] = env.simulator.regions.copy()
+        k[name + "_envcur_simcur_winner"] = np.array([env.current_player_num, env.simulator.current_player_num, code(env.winner)])
+
+    selfplay([0.1, 0.2, 0.0, 0.3, 0.99], 0, [4, 1, 7], "kat2")
+    selfplay([0.1, 0.2, 0.5, 0.5, 0.5], 1, [0, 0], "kat3")
+    rh.set_rng(ListStream([0.5, 0.5, 0.5]))
+    env = A.HexEnv(opponent_policy=minihex.random_policy, board_size=3)
+    env.reset()
+    o1, r1, d1, _, i1 = env.step(4)
+    o1 = np.array(o1)
+    o2, r2, d2, _, i2 = env.step(4)
+    k["kat4_obs"] = np.array([o1, np.array(o2)])
+    k["kat4_r"], k["kat4_d"] = np.array([r1, r2]), np.array([d1, d2])
+    k["kat4_last_move_opponent"] = np.array([i1["last_move_opponent"]])
+    k["kat4_winner"] = np.array([code(i2["winner"])])
+    np.savez_compressed(os.path.join(OUT, "kat.npz"), **k)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    gen_kats()
+    for N, n in [(3, 12), (4, 8), (5, 8), (7, 4), (11, 3), (13, 1)]:
+        gen_raw_games("A", N, n, 100 + N)
+        gen_raw_games("B", N, n, 200 + N)
+    for N, G, T in [(3, 24, 24), (5, 16, 48), (6, 12, 48), (11, 8, 140)]:
+        for agent_mode in (0, 1, 2):
+            for fused in (1, 0):
+                o = rollout("B", N, G, T, seed=1000 + N, agent_mode=agent_mode, fused=bool(fused))
+                np.savez_compressed(os.path.join(OUT, "selfplay_N%d_a%d_f%d.npz" % (N, agent_mode, fused)), N=N, seed=1000 + N,
+                                    agent_mode=agent_mode, fused=fused, **o)
+    for N, G, T in [(3, 24, 24), (5, 16, 40), (7, 12, 60)]:
+        for of in (0, 1):
+            for fused in (1, 0):
+                o = rollout("A", N, G, T, seed=2000 + N, agent_mode=0, fused=bool(fused), opponent_first=bool(of))
+                np.savez_compressed(os.path.join(OUT, "envA_N%d_of%d_f%d.npz" % (N, of, fused)), N=N, seed=2000 + N,
+                                    opponent_first=of, fused=fused, **o)
+    total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print("golden fixtures: %d files, %.1f KiB" % (len(os.listdir(OUT)), total / 1024.0))
+
+
+if __name__ == "__main__":
+    main()
