@@ -1,0 +1,365 @@
+// hexb_core.cuh - per-game and per-word logic of the batched Hex simulator (sm_100a).
+//
+// Everything here is written against the REFERENCE SEMANTICS (MBPrdctns/hex_gym_env), cited as
+// file:line relative to the reference root, but in a representation chosen for the B200:
+//
+//   * one TAGGED LABEL BYTE per cell, [G][C] u8, in the AGENT'S PERSPECTIVE ("stored") coordinates:
+//       0 = empty, else (region label & 0x7f) | (player << 7), player 0 = "R" (connects stored row 0
+//       to row N-1; the agent), player 1 = "C" (connects stored col 0 to col N-1; the opponent).
+//     It replaces the reference's board f64[N,N] plus regions f64[2,N+2,N+2] (HexGame.py:23,38-45,
+//     HexSingleGame.py:27,42-49): the padded borders are implicit (near edge = label 1, far edge =
+//     label 2 until that player connects, then 1) and a cell belongs to at most one player, so one
+//     plane with a tag bit carries both region planes. Labels stay < 128 for N <= 19 (3 + the size
+//     of an independent set of the hex adjacency graph on the interior rows).
+//   * "stored" = true coordinates when the agent is BLACK, the transpose when the agent is WHITE
+//     (the hex neighbourhood is symmetric under transposition), so the agent's observation, mask and
+//     action index are the stored row-major order and never need a transpose on the hot path.
+//   * a small per-game record (SoA u32 words): occupancy bitboards in row-major and column-major
+//     order (the random opponent picks the k-th empty cell of ITS perspective = stored column-major
+//     order, SelfplayWrapper.py:17-22, minihex/__init__.py:8-12), counters, flags, RNG draw index.
+//
+// The same source compiles for the device (hexb_kernels.cu) and, with HEXB_HOST_EMU defined, for the
+// host-side emulator under tests/emu/ that replays the kernel phases serially. The emulator is test
+// infrastructure; the product has no CPU path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(HEXB_HOST_EMU)
+#define HEXB_HD __host__ __device__ __forceinline__
+#else
+#define HEXB_HD static inline
+#endif
+
+namespace hexb {
+
+// ----------------------------------------------------------------------------------------------
+// constants
+// ----------------------------------------------------------------------------------------------
+constexpr int kTile = 128;  // games per CTA tile == threads per CTA
+
+enum : int { VARIANT_A = 0, VARIANT_B = 1 };
+enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_PLY = 2 };
+
+// meta word
+constexpr uint32_t M_CTR_R_SHIFT = 0;   // bits 0-7   region_counter of R
+constexpr uint32_t M_CTR_C_SHIFT = 8;   // bits 8-15  region_counter of C
+constexpr uint32_t M_TOMOVE = 1u << 16;  // 1 = C to move (simulator.current_player_num in stored terms)
+constexpr uint32_t M_DONE = 1u << 17;
+constexpr uint32_t M_TRANSPOSED = 1u << 18;  // agent is true WHITE: stored = true^T, R = WHITE, C = BLACK
+constexpr uint32_t M_FAR_R1 = 1u << 19;      // R's far border label has become 1 (R connected)
+constexpr uint32_t M_FAR_C1 = 1u << 20;
+constexpr uint32_t M_WIN_SHIFT = 21;         // bits 21-22: simulator.winner 0 none, 1 R, 2 C
+constexpr uint32_t M_WIN_MASK = 3u << 21;
+constexpr uint32_t M_INVALID = 1u << 23;      // the episode ended on an illegal agent move (winner == 3)
+constexpr uint32_t M_COLOUR_SET = 1u << 24;   // SelfplayWrapper.py:72-73 ran (agent colour fixed for the env's lifetime)
+constexpr uint32_t M_LIVE = 1u << 25;         // reset() has been called at least once
+constexpr uint32_t M_AGENT_ENDED = 1u << 26;  // the agent's own ply ended the episode (terminal obs is the opponent's view)
+
+// per-game scratch words handed from the thread-per-game phases to the cooperative byte passes
+//   prm: bits 0-7 o1 (tagged), 8-15 o2 (tagged), 16-23 m (tagged), 24 need-relabel
+constexpr uint32_t P_NEED = 1u << 24;
+//   flg: bit 0 resetting, bit 1 output view is the opponent's (transposed+swapped), bit 2 has opening stone,
+//        bit 3 emit terminal obs, bit 4 terminal view is the opponent's; bits 8-15 opening byte, 16-31 opening cell
+constexpr uint32_t F_RESET = 1u << 0;
+constexpr uint32_t F_VIEW_OPP = 1u << 1;
+constexpr uint32_t F_OPEN = 1u << 2;
+constexpr uint32_t F_TERM = 1u << 3;
+constexpr uint32_t F_TERM_OPP = 1u << 4;
+
+template <int N>
+struct Geo {
+    static constexpr int C = N * N;
+    static constexpr int W = (C + 31) / 32;      // bitboard words
+    static constexpr int R = 2 * W + 3;          // record words: occ_rm[W], occ_cm[W], meta, draws, aux
+    static constexpr int TILE_BYTES = kTile * C;  // label bytes per tile (multiple of 16)
+    static constexpr int TILE_WORDS = TILE_BYTES / 4;
+    static constexpr uint32_t LAST_MASK = (C % 32) ? ((1u << (C % 32)) - 1u) : 0xffffffffu;
+};
+
+template <int N>
+struct Rec {
+    uint32_t occ_rm[Geo<N>::W];
+    uint32_t occ_cm[Geo<N>::W];
+    uint32_t meta, draws, aux;  // aux: bits 0-15 plies in the running episode
+};
+
+struct Params {
+    // packed state (owned by the handle)
+    uint8_t *labels;      // [Gpad][C]
+    uint32_t *rec;        // [R][Gpad]
+    long long *stats;     // [8]
+    long long G, Gpad, game_offset;
+    unsigned long long seed;
+    int variant, auto_reset, eval_state, opponent_first, agent_mode, mode;
+    int raw;  // 1: bare HexGame batch (hexb_ply): reset draws nothing and nobody opens
+    // borrowed I/O (device pointers, any may be null unless noted)
+    const int32_t *actions;    // [G]   null => sample the agent's move on device (one draw)
+    const double *opp_u;       // [G,2] null => Philox stream
+    const uint8_t *reset_mask;  // [G]   MODE_RESET: null => all
+    const double *open_u;      // [G]   MODE_RESET: injected opening draw
+    int8_t *obs;               // [G,N,N]
+    uint8_t *mask;             // [G,C]
+    float *reward;             // [G]
+    uint8_t *done;             // [G]
+    int8_t *term_obs;          // [G,N,N] written only for games that finished in this step
+    int32_t *actions_out;      // [G]   the agent action actually played
+    int8_t *ret;               // [G]   MODE_PLY: -1 none, 0 BLACK, 1 WHITE, 3 illegal
+};
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+HEXB_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+HEXB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+HEXB_HD uint32_t splat(uint32_t b) { return b * 0x01010101u; }
+
+// Philox4x32-10 (Random123); pinned by the Random123 known-answer vectors in tests/test_philox.py.
+HEXB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    o0 = c0;
+    o1 = c1;
+}
+
+// Draw idx of global game `game`: the double CPython's random.random() would build from two 32-bit outputs.
+HEXB_HD double draw01(unsigned long long seed, unsigned long long game, uint32_t idx) {
+    uint32_t a, b;
+    philox4x32_10(idx, (uint32_t)game, (uint32_t)(game >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// choice = int(random.random() * n)   (SelfplayWrapper.py:20, minihex/__init__.py:11): one fp64 multiply, truncation.
+HEXB_HD int choice_of(double u, int n) {
+#if defined(__CUDA_ARCH__)
+    int k = __double2int_rz(__dmul_rn(u, (double)n));
+#else
+    int k = (int)(u * (double)n);
+#endif
+    return k < 0 ? 0 : (k >= n ? n - 1 : k);
+}
+
+// index of the k-th (0-based) ZERO bit among the first C bits of a W-word bitboard
+template <int N>
+HEXB_HD int select_kth_zero(const uint32_t (&occ)[Geo<N>::W], int k) {
+    constexpr int W = Geo<N>::W;
+    uint32_t z = 0;
+    int base = 0;
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint32_t zw = ~occ[w];
+        if (w == W - 1) zw &= Geo<N>::LAST_MASK;
+        const int c = popc32(zw);
+        if (!found) {
+            if (k < c) { z = zw; base = 32 * w; found = true; }
+            else k -= c;
+        }
+    }
+    // k-th set bit of z by halving
+    int pos = 0, c;
+    c = popc32(z & 0xffffu); if (k >= c) { k -= c; pos += 16; z >>= 16; }
+    c = popc32(z & 0xffu);   if (k >= c) { k -= c; pos += 8;  z >>= 8; }
+    c = popc32(z & 0xfu);    if (k >= c) { k -= c; pos += 4;  z >>= 4; }
+    c = popc32(z & 0x3u);    if (k >= c) { k -= c; pos += 2;  z >>= 2; }
+    c = (int)(z & 1u);       if (k >= c) { pos += 1; }
+    return base + pos;
+}
+
+template <int N>
+HEXB_HD int count_empty(const uint32_t (&occ)[Geo<N>::W]) {
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) n += popc32(occ[w]);
+    return Geo<N>::C - n;
+}
+
+template <int N>
+HEXB_HD bool test_bit(const uint32_t (&bb)[Geo<N>::W], int i) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) v = (w == (i >> 5)) ? bb[w] : v;
+    return (v >> (i & 31)) & 1u;
+}
+template <int N>
+HEXB_HD void set_bit(uint32_t (&bb)[Geo<N>::W], int i) {
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) bb[w] |= (w == (i >> 5)) ? (1u << (i & 31)) : 0u;
+}
+
+template <int N>
+HEXB_HD int transpose_cell(int a) {
+    const int y = a / N;
+    return (a - y * N) * N + y;
+}
+
+// ----------------------------------------------------------------------------------------------
+// one stone: HexGame.fast_move (HexGame.py:85-111, HexSingleGame.py:88-122) + flood_fill
+// (HexGame.py:124-142, HexSingleGame.py:135-153) on the tagged label plane of ONE game.
+//   L      this game's C label bytes (shared memory on the device)
+//   p      0 = R, 1 = C      cell  stored row-major index, known to be empty
+// Writes the new cell's byte, updates occupancy/counters/far flags in `rec`, and returns the relabel
+// request for the cooperative byte pass (regions[regions == label] = new_region_label, :141-142 / :152-153):
+// at most two labels besides the minimum can be adjacent (the six neighbours form a cycle; own stones
+// that are adjacent on the cycle already share a label), so `prm` carries o1, o2 and m.
+// Returns true iff the mover's far border now carries label 1 (regions[-1,-1] == 1, :102 / :111).
+// ----------------------------------------------------------------------------------------------
+template <int N>
+HEXB_HD bool place_stone(uint8_t *L, Rec<N> &rec, int p, int cell, uint32_t &prm) {
+    const int y = cell / N, x = cell - y * N;
+    const uint32_t tag = (uint32_t)p << 7;
+    const bool up = y > 0, dn = y < N - 1, lf = x > 0, rt = x < N - 1;
+    // 3x3 window minus [0,0] and [2,2] (neighborhood[0,0] = neighborhood[2,2] = 0)
+    uint32_t v[8];
+    v[0] = up ? L[cell - N] : 0u;
+    v[1] = (up && rt) ? L[cell - N + 1] : 0u;
+    v[2] = lf ? L[cell - 1] : 0u;
+    v[3] = rt ? L[cell + 1] : 0u;
+    v[4] = (dn && lf) ? L[cell + N - 1] : 0u;
+    v[5] = dn ? L[cell + N] : 0u;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = (v[i] != 0u && (v[i] >> 7) == (uint32_t)p) ? (v[i] & 0x7fu) : 0xffu;
+    // implicit borders of the mover's padded plane
+    const uint32_t far1 = p ? (rec.meta & M_FAR_C1) : (rec.meta & M_FAR_R1);
+    const bool near_edge = p ? (x == 0) : (y == 0);
+    const bool far_edge = p ? (x == N - 1) : (y == N - 1);
+    v[6] = near_edge ? 1u : 0xffu;
+    v[7] = far_edge ? (far1 ? 1u : 2u) : 0xffu;
+    uint32_t m = 0xffu, o1 = 0xffu, o2 = 0xffu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m = v[i] < m ? v[i] : m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o1 = (v[i] > m && v[i] < o1) ? v[i] : o1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o2 = (v[i] > o1 && v[i] < o2) ? v[i] : o2;  // o1 == 0xff => nothing is > o1
+    const uint32_t cshift = p ? M_CTR_C_SHIFT : M_CTR_R_SHIFT;
+    uint32_t lab;
+    prm = 0;
+    if (m == 0xffu) {  // no adjacent region: new label = region_counter, counter += 1
+        lab = (rec.meta >> cshift) & 0xffu;
+        rec.meta += 1u << cshift;
+    } else {
+        lab = m;
+        if (o1 != 0xffu) {
+            const uint32_t o2e = (o2 != 0xffu) ? o2 : o1;
+            prm = (o1 | tag) | ((o2e | tag) << 8) | ((m | tag) << 16) | P_NEED;
+            // the relabel runs over the whole padded plane, borders included: 2 -> 1 moves the far border
+            if (m == 1u && !far1 && (o1 == 2u || o2 == 2u)) rec.meta |= p ? M_FAR_C1 : M_FAR_R1;
+        }
+    }
+    L[cell] = (uint8_t)(lab | tag);
+    set_bit<N>(rec.occ_rm, cell);
+    set_bit<N>(rec.occ_cm, x * N + y);
+    return (rec.meta & (p ? M_FAR_C1 : M_FAR_R1)) != 0u;
+}
+
+// ----------------------------------------------------------------------------------------------
+// byte-SIMD helpers for the cooperative passes (4 cells per 32-bit word)
+// ----------------------------------------------------------------------------------------------
+// 0x80 in every byte of x that is non-zero (exact, no cross-byte carries)
+HEXB_HD uint32_t nz_flags(uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
+// 0xff in every byte of x equal to the byte s
+HEXB_HD uint32_t eq_mask(uint32_t x, uint32_t s) {
+    const uint32_t z = (~nz_flags(x ^ splat(s))) & 0x80808080u;
+    return (z >> 7) * 0xffu;
+}
+HEXB_HD uint32_t relabel_word(uint32_t x, uint32_t prm) {
+    const uint32_t mk = eq_mask(x, prm & 0xffu) | eq_mask(x, (prm >> 8) & 0xffu);
+    return (x & ~mk) | (splat((prm >> 16) & 0xffu) & mk);
+}
+HEXB_HD uint32_t relabel_byte(uint32_t b, uint32_t prm) {
+    return ((prm & P_NEED) && (b == (prm & 0xffu) || b == ((prm >> 8) & 0xffu))) ? ((prm >> 16) & 0xffu) : b;
+}
+// observation / mask bytes in the STORED orientation (the agent's view)
+//   variant B (HexSingleGame.py:15-19, 265-271): own -1, opponent +1, empty 0; own = R
+//   variant A (HexGame.py:10-13): BLACK 0 (= R, the agent), WHITE 1, EMPTY 2
+HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) {
+    const uint32_t nz1 = nz_flags(x) >> 7;            // 0x01 per stone
+    const uint32_t c1 = (x >> 7) & 0x01010101u;       // 0x01 per C stone
+    msk = nz1 ^ 0x01010101u;                          // legal == empty
+    if (variant == VARIANT_B) obs = ((nz1 & ~c1) * 0xffu) | c1;
+    else obs = c1 | (msk << 1);
+}
+// one byte, optionally seen from the opponent's side (sign swap; the caller transposes the cell index)
+HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &msk) {
+    msk = (b == 0u);
+    if (variant == VARIANT_A) return b == 0u ? 2u : (b >> 7);
+    if (b == 0u) return 0u;
+    const bool own = ((b >> 7) != 0u) == opp_view;  // R is "own" in the agent's view, C in the opponent's
+    return own ? 0xffu : 0x01u;
+}
+
+// ----------------------------------------------------------------------------------------------
+// reset: HexGame.__init__ on an empty board (HexGame.py:21-68 / HexSingleGame.py:26-71) + HexEnv.reset
+// (HexGame.py:206-242 / HexSingleGame.py:208-231) + SelfPlayEnv.reset / setup_opponents / continue_game
+// (SelfplayWrapper.py:69-104,146-172). The label bytes themselves are cleared by the caller; this fills
+// `rec` and returns the opening stone (if the opponent moves first) through `flg`.
+// ----------------------------------------------------------------------------------------------
+template <int N>
+HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, const double *inj_u, uint32_t &flg) {
+    constexpr int C = Geo<N>::C;
+    uint32_t meta = rec.meta & (M_TRANSPOSED | M_COLOUR_SET);
+    meta |= M_LIVE | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
+    rec.aux = 0;
+    bool opp_opens;
+    if (P.raw) {
+        opp_opens = false;
+    } else if (P.variant == VARIANT_B) {
+        if (!(meta & M_COLOUR_SET)) {  // random.randint(0,1) once per env (SelfplayWrapper.py:72-73)
+            int colour = P.agent_mode;
+            if (P.agent_mode == 2) colour = (int)(draw01(P.seed, gid, rec.draws++) * 2.0);
+            meta |= M_COLOUR_SET | (colour ? M_TRANSPOSED : 0u);
+        }
+        if (!inj_u && !P.eval_state) {  // setup_opponents (:97-103): every pool entry is a random policy, only the draws count
+            const double rv = draw01(P.seed, gid, rec.draws++);
+            if (!(rv < 0.8)) rec.draws++;
+        }
+        opp_opens = (meta & M_TRANSPOSED) != 0u;  // agent WHITE: BLACK (the opponent) opens (:79-80)
+    } else {
+        opp_opens = P.opponent_first != 0;  // HexGame.py:224-230
+    }
+    if (opp_opens) {
+        double u;
+        if (inj_u) u = *inj_u;
+        else {
+            if (P.variant == VARIANT_B) rec.draws++;  // rv = random.uniform(0,1), unused (:159)
+            u = draw01(P.seed, gid, rec.draws++);
+        }
+        const int k = choice_of(u, C);         // k-th empty cell of the opponent's view of an empty board
+        const int x = k / N, y = k - x * N;    // stored column-major index -> stored (y, x)
+        uint32_t lab;
+        if (x == 0) lab = 1u;
+        else if (x == N - 1) lab = 2u;
+        else { lab = 3u; meta += 1u << M_CTR_C_SHIFT; }
+        set_bit<N>(rec.occ_rm, y * N + x);
+        set_bit<N>(rec.occ_cm, k);
+        rec.aux = 1;
+        flg |= F_OPEN | ((lab | 0x80u) << 8) | ((uint32_t)(y * N + x) << 16);
+    }
+    rec.meta = meta;  // R (the agent) to move
+    flg |= F_RESET;
+}
+
+}  // namespace hexb

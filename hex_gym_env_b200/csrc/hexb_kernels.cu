@@ -1,0 +1,455 @@
+// hexb_kernels.cu - sm_100a kernels and the C ABI (include/hexb.h) of the batched Hex simulator.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (see build.py).
+//
+// Kernel inventory:
+//   K1/K2/K3  hexb_tile_kernel<N>  one CTA per tile of 128 games; MODE_RESET / MODE_STEP / MODE_PLY
+//   K4        hexb_sample_kernel   standalone k-th-empty-cell sampler
+//   K5        hexb_encode_kernel   standalone observation + mask encoder (either view)
+//   K6        hexb_export_kernel / hexb_import_kernel   reference-layout dump / preset boards
+//   K7        statistics: warp __reduce_add_sync + one atomic per CTA inside the tile kernel; hexb_stats copies
+//
+// Data movement of the tile kernel: the tile's label bytes (128*C contiguous bytes) are brought into shared
+// memory by ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path, completion on an mbarrier) while the
+// threads fetch their record words with coalesced 32-bit loads ([word][game] layout); obs and mask leave as
+// coalesced 32-bit stores straight from registers; the label bytes return with one bulk store.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/hexb.h"
+#include "hexb_views.cuh"
+
+using namespace hexb;
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();  // never hang the GPU: a lost copy becomes a CUDA error
+    }
+}
+// global -> shared bulk copy (TMA 1-D), completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ tile kernel
+template <int N>
+struct SmemLayout {
+    static constexpr int LAB = 0;
+    static constexpr int PRM1 = Geo<N>::TILE_BYTES;
+    static constexpr int PRM2 = PRM1 + kTile * 4;
+    static constexpr int FLG = PRM2 + kTile * 4;
+    static constexpr int STATS = FLG + kTile * 4;
+    static constexpr int BAR = STATS + 8 * 4;
+    static constexpr int BYTES = BAR + 16;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kTile) hexb_tile_kernel(const Params P, const int use_bulk) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    using SL = SmemLayout<N>;
+    constexpr int TB = Geo<N>::TILE_BYTES;
+    Tile<N> T;
+    T.lab = smem + SL::LAB;
+    T.prm1 = reinterpret_cast<uint32_t *>(smem + SL::PRM1);
+    T.prm2 = reinterpret_cast<uint32_t *>(smem + SL::PRM2);
+    T.flg = reinterpret_cast<uint32_t *>(smem + SL::FLG);
+    int *sstats = reinterpret_cast<int *>(smem + SL::STATS);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SL::BAR);
+    const int tid = threadIdx.x;
+    T.g0 = (long long)blockIdx.x * kTile;
+    uint8_t *gl = P.labels + T.g0 * Geo<N>::C;
+
+    // ---- tile in
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, TB);
+            bulk_g2s(T.lab, gl, TB, bar);
+        }
+    } else {
+        const uint4 *s = reinterpret_cast<const uint4 *>(gl);
+        uint4 *d = reinterpret_cast<uint4 *>(T.lab);
+        for (int i = tid; i < TB / 16; i += kTile) d[i] = s[i];
+    }
+    if (tid < 8) sstats[tid] = 0;
+    Rec<N> rec;
+    load_rec<N>(P, T.g0 + tid, rec);
+    __syncthreads();  // barrier init / plain copy visible
+    if (use_bulk) mbar_wait(bar, 0);
+
+    // ---- phases
+    if (P.mode == MODE_STEP) {
+        Loc loc;
+        phase_agent<N>(T, P, tid, rec, loc);
+        __syncthreads();
+        pass_relabel<N>(T, T.prm1, tid);
+        __syncthreads();
+        phase_opponent<N>(T, P, tid, rec, loc);
+        // K7: episode statistics, warp reduction then one shared and one global atomic per counter
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int v = __reduce_add_sync(0xffffffffu, loc.st[i]);
+            if ((tid & 31) == 0 && v) atomicAdd(&sstats[i], v);
+        }
+        __syncthreads();
+        pass_encode<N>(T, P, tid);
+        __syncthreads();
+        phase_clear<N>(T, tid);
+        if (tid < 8 && sstats[tid]) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats) + tid, (unsigned long long)sstats[tid]);
+    } else if (P.mode == MODE_RESET) {
+        phase_reset<N>(T, P, tid, rec);
+        __syncthreads();
+        pass_encode<N>(T, P, tid);
+        __syncthreads();
+        phase_clear<N>(T, tid);
+    } else {
+        phase_ply<N>(T, P, tid, rec);
+        __syncthreads();
+        pass_relabel<N>(T, T.prm1, tid);
+    }
+
+    // ---- tile out
+    if (T.g0 + tid < P.G) store_rec<N>(P, T.g0 + tid, rec);
+    if (use_bulk) {
+        fence_async_smem();  // generic-proxy writes to smem -> visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(gl, T.lab, TB);
+            bulk_wait_read();
+        }
+    } else {
+        __syncthreads();
+        const uint4 *s = reinterpret_cast<const uint4 *>(T.lab);
+        uint4 *d = reinterpret_cast<uint4 *>(gl);
+        for (int i = tid; i < TB / 16; i += kTile) d[i] = s[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small kernels (hexb_views.cuh)
+__global__ void hexb_encode_kernel(View V, int view, int8_t *obs, uint8_t *mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V.G * V.N * V.N) encode_at(V, view, i, obs, mask);
+}
+template <int N>
+__global__ void hexb_sample_kernel(View V, int view, const double *u, int32_t *out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < V.G) sample_at<N>(V, view, g, u, out);
+}
+__global__ void hexb_export_kernel(View V, double *board, double *regions, double *counter, int8_t *cur, uint8_t *done,
+                                   int8_t *winner, int8_t *agent, uint32_t *draws) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V.G * 2 * (V.N + 2) * (V.N + 2)) export_at(V, i, board, regions, counter, cur, done, winner, agent, draws);
+}
+template <int N>
+__global__ void hexb_import_kernel(Params P, const int8_t *board_true, const int8_t *to_move) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < P.G) import_game<N>(P, g, board_true, to_move);
+}
+
+__global__ void hexb_stats_kernel(const long long *src, int64_t *dst) {
+    if (threadIdx.x < 8) dst[threadIdx.x] = (int64_t)src[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct hexb_env {
+    hexb_config cfg;
+    Params base;  // state pointers + config, I/O pointers null
+    int use_bulk;
+};
+
+static thread_local int g_last_cuda = 0;
+static int cuda_fail(cudaError_t e) {
+    g_last_cuda = (int)e;
+    return HEXB_ERR_CUDA;
+}
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) return cuda_fail(e_); \
+    } while (0)
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static bool cfg_ok(const hexb_config *c) {
+    if (!c) return false;
+    if (c->board_size < HEXB_MIN_BOARD || c->board_size > HEXB_MAX_BOARD) return false;
+    if (c->variant != HEXB_VARIANT_A && c->variant != HEXB_VARIANT_B) return false;
+    if (c->num_games < 1 || c->game_offset < 0) return false;
+    if (c->agent_mode < 0 || c->agent_mode > 2) return false;
+    if (c->variant == HEXB_VARIANT_A && c->agent_mode != HEXB_AGENT_BLACK) return false;
+    return true;
+}
+
+struct Layout {
+    long long Gpad;
+    size_t labels_off, rec_off, stats_off, total;
+};
+static Layout layout_of(const hexb_config *c) {
+    Layout L;
+    const long long C = (long long)c->board_size * c->board_size;
+    const long long W = (C + 31) / 32, R = 2 * W + 3;
+    L.Gpad = (c->num_games + kTile - 1) / kTile * kTile;
+    L.labels_off = 0;
+    L.rec_off = align256((size_t)(L.Gpad * C));
+    L.stats_off = L.rec_off + align256((size_t)(R * L.Gpad * 4));
+    L.total = L.stats_off + 256;
+    return L;
+}
+
+extern "C" {
+
+int32_t hexb_version(void) { return (1 << 16) | 0; }
+
+const char *hexb_strerror(int32_t code) {
+    switch (code) {
+        case HEXB_OK: return "ok";
+        case HEXB_ERR_ARG: return "bad argument or unsupported configuration";
+        case HEXB_ERR_CUDA: return "CUDA call failed";
+        case HEXB_ERR_STATE: return "state buffer too small or misaligned";
+        case HEXB_ERR_NOGPU: return "no usable CUDA device";
+        default: return "unknown error";
+    }
+}
+
+int32_t hexb_last_cuda_error(void) { return g_last_cuda; }
+
+size_t hexb_state_bytes(const hexb_config *cfg) { return cfg_ok(cfg) ? layout_of(cfg).total : 0; }
+
+int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, void *stream, hexb_env **out) {
+    if (!cfg_ok(cfg) || !out) return HEXB_ERR_ARG;
+    const Layout L = layout_of(cfg);
+    if (!state || state_bytes < L.total || ((uintptr_t)state & 255)) return HEXB_ERR_STATE;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) return HEXB_ERR_NOGPU;
+    CK(cudaSetDevice(cfg->device));
+    CK(cudaMemsetAsync(state, 0, L.total, (cudaStream_t)stream));
+    hexb_env *e = (hexb_env *)calloc(1, sizeof(hexb_env));
+    if (!e) return HEXB_ERR_ARG;
+    e->cfg = *cfg;
+    Params &P = e->base;
+    P.labels = (uint8_t *)state + L.labels_off;
+    P.rec = (uint32_t *)((uint8_t *)state + L.rec_off);
+    P.stats = (long long *)((uint8_t *)state + L.stats_off);
+    P.G = cfg->num_games;
+    P.Gpad = L.Gpad;
+    P.game_offset = cfg->game_offset;
+    P.seed = cfg->seed;
+    P.variant = cfg->variant;
+    P.auto_reset = cfg->auto_reset;
+    P.eval_state = cfg->eval_state;
+    P.opponent_first = cfg->opponent_first;
+    P.agent_mode = cfg->agent_mode;
+    P.raw = cfg->raw;
+    const char *b = getenv("HEXB_BULK");
+    e->use_bulk = (b && b[0] == '0') ? 0 : 1;
+    *out = e;
+    return HEXB_OK;
+}
+
+int32_t hexb_destroy(hexb_env *env) {
+    if (!env) return HEXB_ERR_ARG;
+    free(env);
+    return HEXB_OK;
+}
+
+}  // extern "C"
+
+template <int N>
+static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
+    constexpr int smem = SmemLayout<N>::BYTES;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(hexb_tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    const unsigned grid = (unsigned)(P.Gpad / kTile);
+    hexb_tile_kernel<N><<<grid, kTile, smem, s>>>(P, e->use_bulk);
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+#define HEXB_FOR_N(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19)
+
+static int dispatch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
+    switch (e->cfg.board_size) {
+#define X(n) \
+    case n: return launch_tile<n>(e, P, s);
+        HEXB_FOR_N(X)
+#undef X
+    }
+    return HEXB_ERR_ARG;
+}
+
+static View view_of(const hexb_env *e) {
+    View V;
+    V.labels = e->base.labels;
+    V.rec = e->base.rec;
+    V.G = e->base.G;
+    V.Gpad = e->base.Gpad;
+    V.N = e->cfg.board_size;
+    V.variant = e->cfg.variant;
+    V.raw = e->cfg.raw;
+    return V;
+}
+
+extern "C" {
+
+int32_t hexb_reset(hexb_env *env, const uint8_t *reset_mask, const double *open_u, int8_t *obs, uint8_t *mask, void *stream) {
+    if (!env) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    Params P = env->base;
+    P.mode = MODE_RESET;
+    P.reset_mask = reset_mask;
+    P.open_u = open_u;
+    P.obs = obs;
+    P.mask = mask;
+    return dispatch_tile(env, P, (cudaStream_t)stream);
+}
+
+int32_t hexb_step(hexb_env *env, const int32_t *actions, const double *opp_u, int8_t *obs, uint8_t *mask, float *reward,
+                  uint8_t *done, int8_t *term_obs, int32_t *actions_out, void *stream) {
+    if (!env || env->cfg.raw) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    Params P = env->base;
+    P.mode = MODE_STEP;
+    P.actions = actions;
+    P.opp_u = opp_u;
+    P.obs = obs;
+    P.mask = mask;
+    P.reward = reward;
+    P.done = done;
+    P.term_obs = term_obs;
+    P.actions_out = actions_out;
+    return dispatch_tile(env, P, (cudaStream_t)stream);
+}
+
+size_t hexb_host_workspace_bytes(const hexb_config *cfg) {
+    if (!cfg_ok(cfg)) return 0;
+    const size_t G = (size_t)cfg->num_games, C = (size_t)cfg->board_size * cfg->board_size;
+    return align256(G * 4) + 2 * align256(G * C) + align256(G * 4) + align256(G);
+}
+
+int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_host, int8_t *obs_host, uint8_t *mask_host,
+                       float *reward_host, uint8_t *done_host, void *stream) {
+    if (!env || !workspace || env->cfg.raw) return HEXB_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t G = (size_t)env->cfg.num_games, C = (size_t)env->cfg.board_size * env->cfg.board_size;
+    uint8_t *w = (uint8_t *)workspace;
+    int32_t *d_act = (int32_t *)w;            w += align256(G * 4);
+    int8_t *d_obs = (int8_t *)w;              w += align256(G * C);
+    uint8_t *d_mask = w;                      w += align256(G * C);
+    float *d_rew = (float *)w;                w += align256(G * 4);
+    uint8_t *d_done = w;
+    CK(cudaSetDevice(env->cfg.device));
+    if (actions_host) CK(cudaMemcpyAsync(d_act, actions_host, G * 4, cudaMemcpyHostToDevice, s));
+    const int rc = hexb_step(env, actions_host ? d_act : nullptr, nullptr, obs_host ? d_obs : nullptr, mask_host ? d_mask : nullptr,
+                             reward_host ? d_rew : nullptr, done_host ? d_done : nullptr, nullptr, nullptr, stream);
+    if (rc != HEXB_OK) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, d_obs, G * C, cudaMemcpyDeviceToHost, s));
+    if (mask_host) CK(cudaMemcpyAsync(mask_host, d_mask, G * C, cudaMemcpyDeviceToHost, s));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, d_rew, G * 4, cudaMemcpyDeviceToHost, s));
+    if (done_host) CK(cudaMemcpyAsync(done_host, d_done, G, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return HEXB_OK;
+}
+
+int32_t hexb_ply(hexb_env *env, const int32_t *actions, int8_t *ret, void *stream) {
+    if (!env || !actions || !env->cfg.raw) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    Params P = env->base;
+    P.mode = MODE_PLY;
+    P.actions = actions;
+    P.ret = ret;
+    return dispatch_tile(env, P, (cudaStream_t)stream);
+}
+
+int32_t hexb_encode(hexb_env *env, int32_t view, int8_t *obs, uint8_t *mask, void *stream) {
+    if (!env || (view != 0 && view != 1)) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    const View V = view_of(env);
+    const long long n = V.G * V.N * V.N;
+    hexb_encode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(V, view, obs, mask);
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+int32_t hexb_sample_actions(hexb_env *env, int32_t view, const double *u, int32_t *actions_out, void *stream) {
+    if (!env || !u || !actions_out || (view != 0 && view != 1)) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    const View V = view_of(env);
+    const unsigned grid = (unsigned)((V.G + 127) / 128);
+    switch (V.N) {
+#define X(n) \
+    case n: hexb_sample_kernel<n><<<grid, 128, 0, (cudaStream_t)stream>>>(V, view, u, actions_out); break;
+        HEXB_FOR_N(X)
+#undef X
+    }
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+int32_t hexb_export_state(hexb_env *env, double *board, double *regions, double *region_counter, int8_t *cur, uint8_t *done,
+                          int8_t *winner, int8_t *agent, uint32_t *draws, void *stream) {
+    if (!env) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    const View V = view_of(env);
+    const long long n = V.G * 2 * (V.N + 2) * (V.N + 2);
+    hexb_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(V, board, regions, region_counter, cur, done, winner,
+                                                                                       agent, draws);
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, void *stream) {
+    if (!env || !board_true || !env->cfg.raw) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    const Params P = env->base;
+    const unsigned grid = (unsigned)((P.G + 127) / 128);
+    switch (env->cfg.board_size) {
+#define X(n) \
+    case n: hexb_import_kernel<n><<<grid, 128, 0, (cudaStream_t)stream>>>(P, board_true, to_move); break;
+        HEXB_FOR_N(X)
+#undef X
+    }
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream) {
+    if (!env || !out8) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    hexb_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->base.stats, out8);
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+}  // extern "C"

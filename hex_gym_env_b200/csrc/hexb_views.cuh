@@ -1,0 +1,131 @@
+// hexb_views.cuh - state views that are not on the timed path: standalone observation/mask encoder (K5),
+// k-th-empty sampler (K4), reference-layout export and preset-board import (K6). Written per element so the
+// kernels in hexb_kernels.cu are one-line wrappers and the host emulator (tests/emu) can loop over the same code.
+#pragma once
+#include "hexb_phases.cuh"
+
+namespace hexb {
+
+struct View {
+    const uint8_t *labels;
+    const uint32_t *rec;
+    long long G, Gpad;
+    int N, variant, raw;
+};
+HEXB_HD uint32_t view_meta(const View &V, long long g) {
+    const int W = (V.N * V.N + 31) / 32;
+    return V.rec[(long long)(2 * W) * V.Gpad + g];
+}
+
+// K5: obs + mask of the current state. view 0: the agent's (stored orientation, or the opponent's for an episode the
+// agent's own ply ended - what step() returned); view 1: the side to move's (variant-B one-ply HexEnv).
+HEXB_HD void encode_at(const View &V, int view, long long i, int8_t *obs, uint8_t *mask) {
+    const int C = V.N * V.N;
+    const long long g = i / C;
+    const int c = (int)(i - g * C);
+    const uint32_t meta = view_meta(V, g);
+    bool opp = false;
+    if (V.variant == VARIANT_B) {
+        if (view == 1 || V.raw) opp = (meta & M_TOMOVE) != 0u;
+        else opp = (meta & M_DONE) && (meta & M_AGENT_ENDED);
+    }
+    const int y = c / V.N, x = c - y * V.N;
+    const uint32_t b = V.labels[g * C + (opp ? x * V.N + y : c)];
+    uint32_t mk;
+    const uint32_t ob = encode_byte(b, V.variant, opp, mk);
+    if (obs) obs[i] = (int8_t)ob;
+    if (mask) mask[i] = (uint8_t)mk;
+}
+
+// K4: int(u * n_empty)-th empty cell in row-major order of the chosen view.
+template <int N>
+HEXB_HD void sample_at(const View &V, int view, long long g, const double *u, int32_t *out) {
+    constexpr int W = Geo<N>::W;
+    const uint32_t meta = V.rec[(long long)(2 * W) * V.Gpad + g];
+    const bool opp = V.variant == VARIANT_B && (view == 1 || V.raw) && (meta & M_TOMOVE);
+    uint32_t occ[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) occ[w] = V.rec[(long long)((opp ? W : 0) + w) * V.Gpad + g];
+    const int n = count_empty<N>(occ);
+    out[g] = n > 0 ? select_kth_zero<N>(occ, choice_of(u[g], n)) : -1;
+}
+
+// K6: reference-layout dump. Element i = (game, plane, padded cell); board / scalars ride on the first elements.
+HEXB_HD void export_at(const View &V, long long i, double *board, double *regions, double *counter, int8_t *cur, uint8_t *done,
+                       int8_t *winner, int8_t *agent, uint32_t *draws) {
+    const int N = V.N, C = N * N, Pd = N + 2, P2 = Pd * Pd;
+    const int W = (C + 31) / 32;
+    const long long g = i / (2 * P2);
+    const int r = (int)(i - g * 2 * P2);
+    const int pl = r / P2, pc = r - pl * P2;
+    const int Y = pc / Pd, X = pc - Y * Pd;
+    const uint32_t meta = view_meta(V, g);
+    const int tr = (meta & M_TRANSPOSED) ? 1 : 0;
+    const int sp = pl ^ tr;  // stored player that is true colour `pl`
+    const uint8_t *L = V.labels + g * C;
+    if (regions) {
+        const uint32_t far = (meta & (sp ? M_FAR_C1 : M_FAR_R1)) ? 1u : 2u;
+        uint32_t v = 0;
+        if (Y >= 1 && Y <= N && X >= 1 && X <= N) {
+            const int y = Y - 1, x = X - 1;
+            const uint32_t b = L[tr ? x * N + y : y * N + x];
+            v = (b != 0u && (int)(b >> 7) == sp) ? (b & 0x7fu) : 0u;
+        } else if (pl == 0) {  // BLACK plane: rows 0 and N+1 (HexGame.py:43,45 / HexSingleGame.py:47,49)
+            v = (Y == 0) ? 1u : (Y == N + 1 ? far : 0u);
+        } else {               // WHITE plane: cols 0 and N+1 (HexGame.py:42,44 / HexSingleGame.py:46,48)
+            v = (X == 0) ? 1u : (X == N + 1 ? far : 0u);
+        }
+        regions[i] = (double)v;
+    }
+    if (pl == 0 && pc < C && board) {
+        const int c = pc, y = c / N, x = c - y * N;
+        bool opp = false;
+        if (V.variant == VARIANT_B) opp = V.raw ? ((meta & M_TOMOVE) != 0u) : ((meta & M_DONE) && (meta & M_AGENT_ENDED));
+        const uint32_t b = L[opp ? x * N + y : c];
+        uint32_t mk;
+        const uint32_t ob = encode_byte(b, V.variant, opp, mk);
+        board[g * C + c] = (double)(int8_t)ob;
+    }
+    if (r == 0) {
+        if (counter) {
+            const uint32_t cr = (meta >> M_CTR_R_SHIFT) & 0xffu, cc = (meta >> M_CTR_C_SHIFT) & 0xffu;
+            counter[2 * g + 0] = (double)(tr ? cc : cr);
+            counter[2 * g + 1] = (double)(tr ? cr : cc);
+        }
+        if (cur) cur[g] = (int8_t)(((meta & M_TOMOVE) ? 1 : 0) ^ tr);
+        if (done) done[g] = (meta & M_DONE) ? 1 : 0;
+        if (winner) {
+            const uint32_t w = (meta & M_WIN_MASK) >> M_WIN_SHIFT;
+            winner[g] = (int8_t)(w == 0u ? -1 : (int)((w - 1u) ^ (uint32_t)tr));
+        }
+        if (agent) agent[g] = (int8_t)tr;
+        if (draws) draws[g] = V.rec[(long long)(2 * W + 1) * V.Gpad + g];
+    }
+}
+
+// K6b: HexGame.__init__ with a preset board: raster-order flood_fill rebuild (HexGame.py:53-61, HexSingleGame.py:57-65).
+template <int N>
+HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true, const int8_t *to_move) {
+    constexpr int C = Geo<N>::C;
+    uint8_t *L = P.labels + g * C;
+    Rec<N> rec;
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
+    rec.meta = M_LIVE | M_COLOUR_SET | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
+    rec.draws = 0;
+    rec.aux = 0;
+    for (int c = 0; c < C; ++c) L[c] = 0;
+    for (int c = 0; c < C; ++c) {
+        const int v = board_true[g * C + c];
+        if (v != 0 && v != 1) continue;
+        uint32_t prm;
+        place_stone<N>(L, rec, v, c, prm);
+        rec.aux++;
+        if (prm & P_NEED)
+            for (int k = 0; k < C; ++k) L[k] = (uint8_t)relabel_byte(L[k], prm);
+    }
+    if (to_move && to_move[g]) rec.meta |= M_TOMOVE;
+    store_rec<N>(P, g, rec);
+}
+
+}  // namespace hexb

@@ -1,0 +1,142 @@
+/* hexb.h - C ABI of the B200-native batched Hex simulator (libhexb.so).
+ *
+ * This is the drop-in boundary for the hot path of MBPrdctns/hex_gym_env. The reference has no FFI: its
+ * boundary is the Python class API (HexGame / HexEnv / SelfPlayEnv), consumed by stable-baselines3 through
+ * gymnasium. Each entry point below names the reference call(s) it replaces (file:line relative to the
+ * reference root); the Python classes in hex_gym_env_b200/ bind these symbols with ctypes and keep the
+ * reference's names, arguments and return conventions.
+ *
+ * Conventions
+ *   - Plain C, no C++/torch types. Every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - All calls are asynchronous on `stream` (a cudaStream_t passed as void*), except the *_host call and
+ *     hexb_create/hexb_destroy. No hidden synchronisation, no host reads of device data.
+ *   - Return value: 0 = HEXB_OK, negative = error (hexb_strerror). Illegal GAME moves are data (ret 3 /
+ *     done), never errors. Nothing throws across this boundary.
+ *   - The caller owns every buffer, including the packed state (hexb_state_bytes tells its size); the
+ *     handle only remembers pointers. One handle per device, not re-entrant.
+ *   - G games = one shard. Game i of the shard is global game game_offset + i; the random stream of a
+ *     game depends only on (seed, global index), so results do not depend on how games are sharded.
+ */
+#ifndef HEXB_H
+#define HEXB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEXB_OK 0
+#define HEXB_ERR_ARG (-1)     /* bad argument / unsupported configuration */
+#define HEXB_ERR_CUDA (-2)    /* a CUDA call failed; hexb_last_cuda_error() has the code */
+#define HEXB_ERR_STATE (-3)   /* state buffer too small or misaligned */
+#define HEXB_ERR_NOGPU (-4)   /* no usable CUDA device */
+
+#define HEXB_VARIANT_A 0 /* minihex/HexGame.py: board 0/1/2 in true coordinates, opponent inside step() */
+#define HEXB_VARIANT_B 1 /* minihex/HexSingleGame.py + SelfplayWrapper.py: board -1/+1/0 in the mover's view */
+
+#define HEXB_AGENT_BLACK 0
+#define HEXB_AGENT_WHITE 1
+#define HEXB_AGENT_RANDOM 2 /* agent_player_num=None: random.randint(0,1) once per game (SelfplayWrapper.py:72-73) */
+
+#define HEXB_MIN_BOARD 3
+#define HEXB_MAX_BOARD 19
+
+typedef struct hexb_env hexb_env;
+
+typedef struct hexb_config {
+    int32_t board_size;     /* N, 3..19 */
+    int32_t variant;        /* HEXB_VARIANT_A | HEXB_VARIANT_B */
+    int64_t num_games;      /* G, games in this shard */
+    int64_t game_offset;    /* global index of game 0 of this shard */
+    uint64_t seed;          /* key of the per-game Philox4x32-10 streams */
+    int32_t agent_mode;     /* variant B: HEXB_AGENT_*; variant A: must be HEXB_AGENT_BLACK (player_color=WHITE is
+                               corrupt in the reference, HexGame.py:245-248, and is rejected) */
+    int32_t opponent_first; /* variant A: ctor current_player_num=WHITE, the opponent opens (HexGame.py:224-230) */
+    int32_t auto_reset;     /* 1: finished games restart inside step (DummyVecEnv semantics) */
+    int32_t eval_state;     /* variant B: SelfPlayEnv.set_eval(True): setup_opponents draws nothing (SelfplayWrapper.py:92-96) */
+    int32_t raw;            /* 1: bare HexGame batch for hexb_ply (no opponent, no draws) */
+    int32_t device;         /* CUDA device ordinal */
+} hexb_config;
+
+/* Library / ABI version (major << 16 | minor). */
+int32_t hexb_version(void);
+const char *hexb_strerror(int32_t code);
+int32_t hexb_last_cuda_error(void);
+
+/* Bytes of packed device state for `cfg` (0 on a bad config). Layout: label bytes [Gpad][N*N] u8, then the
+ * per-game record words [R][Gpad] u32 (occupancy bitboards, counters, flags, draw index), then int64[8] stats. */
+size_t hexb_state_bytes(const hexb_config *cfg);
+
+/* Create a handle over caller-allocated, 256-byte-aligned device memory and zero it on `stream`.
+ * Replaces HexEnv.__init__ (HexGame.py:152-197, HexSingleGame.py:163-196) and SelfPlayEnv.__init__
+ * (SelfplayWrapper.py:39-67). Games are not playable until hexb_reset. */
+int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, void *stream, hexb_env **out);
+int32_t hexb_destroy(hexb_env *env);
+
+/* reset(): HexGame.__init__ on an empty board (HexGame.py:21-68, HexSingleGame.py:26-71), HexEnv.reset
+ * (HexGame.py:206-242, HexSingleGame.py:208-231), SelfPlayEnv.reset + setup_opponents + opening continue_game
+ * (SelfplayWrapper.py:69-104). reset_mask u8[G] (null = all games); open_u f64[G] (null = per-game stream)
+ * replaces the opponent's opening draw. Emits obs i8[G,N,N] and mask u8[G,N*N] (either may be null). */
+int32_t hexb_reset(hexb_env *env, const uint8_t *reset_mask, const double *open_u, int8_t *obs, uint8_t *mask, void *stream);
+
+/* step(): one env step for every game = agent ply + random-opponent reply, fused with the win check, reward,
+ * done, auto-reset, observation and legal-action mask.
+ *   variant B: SelfPlayEnv.step (SelfplayWrapper.py:174-199) -> HexEnv.step (HexSingleGame.py:233-263) ->
+ *              fast_move / flood_fill (:88-153), continue_game + BaseRandomPolicy.choose_action (:146-172, :17-22),
+ *              legal_actions (:205-206), invert_board (:265-271)
+ *   variant A: HexEnv.step (HexGame.py:244-295), opponent_move (:332-349), random_policy (minihex/__init__.py:8-12),
+ *              fast_move / flood_fill (:85-142), get_action_mask (:203-204)
+ * actions i32[G] in the agent's view (null: the agent is the random policy too and draws from the game's stream);
+ * opp_u f64[G,2] (null: stream) = [reply draw, opening draw after an auto-reset];
+ * outputs (each may be null): obs i8[G,N,N], mask u8[G,N*N], reward f32[G], done u8[G],
+ * term_obs i8[G,N,N] (written only for games that finished in this call: the observation step() returned before
+ * the auto-reset, i.e. SB3's info["terminal_observation"]), actions_out i32[G] (the agent action played). */
+int32_t hexb_step(hexb_env *env, const int32_t *actions, const double *opp_u, int8_t *obs, uint8_t *mask, float *reward,
+                  uint8_t *done, int8_t *term_obs, int32_t *actions_out, void *stream);
+
+/* The same step with HOST buffers (pinned memory recommended): copies actions_host to the device, steps, copies
+ * obs/mask/reward/done back and waits for them. This is the call a host-side (CPU policy) user of the reference
+ * API makes; it needs hexb_host_workspace_bytes(cfg) bytes of device scratch passed at every call. */
+size_t hexb_host_workspace_bytes(const hexb_config *cfg);
+int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_host, int8_t *obs_host, uint8_t *mask_host,
+                       float *reward_host, uint8_t *done_host, void *stream);
+
+/* Batched HexGame.make_move (fast_move: HexGame.py:85-111, HexSingleGame.py:88-122) on a raw=1 handle.
+ * actions i32[G]: variant A true row-major cell, variant B the mover's-view cell as HexEnv.step passes it.
+ * ret i8[G]: -1 = None, 0 = BLACK won, 1 = WHITE won, 3 = illegal (state untouched). */
+int32_t hexb_ply(hexb_env *env, const int32_t *actions, int8_t *ret, void *stream);
+
+/* Observation + mask of the current state without stepping (get_action_mask HexGame.py:203-204, legal_actions
+ * HexSingleGame.py:205-206, the live simulator.board). view 0 = the agent's (what step/reset return), view 1 = the
+ * side to move's (variant-B HexEnv one-ply loop: board after invert_board, HexSingleGame.py:259-262). */
+int32_t hexb_encode(hexb_env *env, int32_t view, int8_t *obs, uint8_t *mask, void *stream);
+
+/* k-th-empty-cell sampler, standalone (BaseRandomPolicy.choose_action SelfplayWrapper.py:17-22; random_policy
+ * minihex/__init__.py:8-12): actions_out[g] = int(u[g] * n_empty)-th empty cell of game g in row-major order of the
+ * chosen view (see hexb_encode). u f64[G] must be given. */
+int32_t hexb_sample_actions(hexb_env *env, int32_t view, const double *u, int32_t *actions_out, void *stream);
+
+/* Reference-layout dump for parity checks and checkpoints (attribute reads .board/.regions/.region_counter/...):
+ * board f64[G,N,N] (live simulator.board), regions f64[G,2,N+2,N+2] incl. borders, region_counter f64[G,2],
+ * cur i8[G] (simulator.current_player_num), done u8[G], winner i8[G] (-1 none), agent i8[G] (true colour),
+ * draws u32[G] (stream position). Any pointer may be null. */
+int32_t hexb_export_state(hexb_env *env, double *board, double *regions, double *region_counter, int8_t *cur, uint8_t *done,
+                          int8_t *winner, int8_t *agent, uint32_t *draws, void *stream);
+
+/* HexGame.__init__ with a preset board and connected_stones=None (HexGame.py:53-61, HexSingleGame.py:57-65): stones are
+ * inserted in raster order through flood_fill. board_true i8[G,N,N] in {0 BLACK, 1 WHITE, 2 EMPTY}, true coordinates;
+ * to_move i8[G] (0/1). Only on raw=1 handles. */
+int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, void *stream);
+
+/* Episode statistics accumulated by hexb_step since creation, int64[8] on the device:
+ * [0] episodes finished, [1] BLACK wins, [2] WHITE wins, [3] agent wins, [4] plies of finished episodes,
+ * [5] episodes ended by an illegal agent move, [6] env steps, [7] plies. Copies them to out8 (device). The multi-GPU
+ * layer all-reduces this vector with NCCL; nothing else ever crosses GPUs. */
+int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEXB_H */

@@ -372,7 +372,11 @@ void hexref_batch_reset(void *h, const uint8_t *reset_mask, const double *open_u
     const int C = b->N * b->N;
     for (int64_t i = 0; i < b->G; ++i) {
         env_t *e = &b->envs[i];
-        if (!reset_mask || reset_mask[i]) env_reset(e, open_u ? &open_u[i] : NULL);
+        if (!reset_mask || reset_mask[i]) {
+            int64_t plies = e->st[7]; /* st[7] counts plies played inside step() (incl. auto-reset openings) only */
+            env_reset(e, open_u ? &open_u[i] : NULL);
+            e->st[7] = plies;
+        }
         emit_obs_mask(e, obs ? obs + i * C : NULL, mask ? mask + i * C : NULL);
     }
 }

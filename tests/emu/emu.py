@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE ONLY - ctypes wrapper of the host emulator of the CUDA tile kernel (tests/emu/hexb_emu.cpp).
+
+Same method surface as oracle.hexref.RefBatch so that tests/parity.py can drive either side."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libhexb_emu.so")
+    srcs = [os.path.join(_HERE, "hexb_emu.cpp")] + [os.path.join(_ROOT, "hex_gym_env_b200", "csrc", f)
+                                                     for f in ("hexb_core.cuh", "hexb_phases.cuh", "hexb_views.cuh")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-Wall", "-Wno-unknown-pragmas",
+                               "-o", so, srcs[0]])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
+        L.emu_create.restype = vp
+        L.emu_create.argtypes = [i32, i32, i64, i64, u64, i32, i32, i32, i32, i32]
+        L.emu_destroy.argtypes = [vp]
+        L.emu_reset.argtypes = [vp] * 5
+        L.emu_step.argtypes = [vp] * 9
+        L.emu_ply.argtypes = [vp] * 3
+        L.emu_encode.argtypes = [vp, i32, vp, vp]
+        L.emu_sample_actions.argtypes = [vp, i32, vp, vp]
+        L.emu_export_state.argtypes = [vp] * 9
+        L.emu_import_boards.argtypes = [vp] * 3
+        L.emu_stats.argtypes = [vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class EmuBatch(object):
+    def __init__(self, variant, board_size, num_games, seed=0, game_offset=0, agent_mode=0, opponent_first=False,
+                 auto_reset=True, eval_state=False, raw=False):
+        self.N, self.G, self.C = board_size, num_games, board_size * board_size
+        self._h = lib().emu_create(board_size, variant, num_games, game_offset, seed, agent_mode, int(opponent_first),
+                                   int(auto_reset), int(eval_state), int(raw))
+        if not self._h:
+            raise ValueError("bad emulator config")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().emu_destroy(self._h)
+            self._h = None
+
+    def reset(self, reset_mask=None, open_u=None):
+        obs = np.empty((self.G, self.N, self.N), np.int8)
+        mask = np.empty((self.G, self.C), np.uint8)
+        rm = None if reset_mask is None else np.ascontiguousarray(reset_mask, np.uint8)
+        ou = None if open_u is None else np.ascontiguousarray(open_u, np.float64)
+        lib().emu_reset(self._h, _p(rm), _p(ou), _p(obs), _p(mask))
+        return obs, mask
+
+    def step(self, actions=None, opp_u=None, want_term=False):
+        obs = np.empty((self.G, self.N, self.N), np.int8)
+        mask = np.empty((self.G, self.C), np.uint8)
+        reward = np.empty(self.G, np.float32)
+        done = np.empty(self.G, np.uint8)
+        term = np.zeros((self.G, self.N, self.N), np.int8) if want_term else None
+        aout = np.empty(self.G, np.int32)
+        a = None if actions is None else np.ascontiguousarray(actions, np.int32)
+        u = None if opp_u is None else np.ascontiguousarray(opp_u, np.float64)
+        lib().emu_step(self._h, _p(a), _p(u), _p(obs), _p(mask), _p(reward), _p(done), _p(term), _p(aout))
+        out = dict(obs=obs, mask=mask, reward=reward, done=done, actions=aout)
+        if want_term:
+            out["term_obs"] = term
+        return out
+
+    def ply(self, actions):
+        ret = np.empty(self.G, np.int8)
+        a = np.ascontiguousarray(actions, np.int32)
+        lib().emu_ply(self._h, _p(a), _p(ret))
+        return ret
+
+    def encode(self, view=0):
+        obs = np.empty((self.G, self.N, self.N), np.int8)
+        mask = np.empty((self.G, self.C), np.uint8)
+        lib().emu_encode(self._h, view, _p(obs), _p(mask))
+        return obs, mask
+
+    def sample_actions(self, u, view=0):
+        out = np.empty(self.G, np.int32)
+        uu = np.ascontiguousarray(u, np.float64)
+        lib().emu_sample_actions(self._h, view, _p(uu), _p(out))
+        return out
+
+    def import_boards(self, board_true, to_move=None):
+        b = np.ascontiguousarray(board_true, np.int8)
+        tm = None if to_move is None else np.ascontiguousarray(to_move, np.int8)
+        lib().emu_import_boards(self._h, _p(b), _p(tm))
+
+    def export(self):
+        N, G = self.N, self.G
+        out = dict(board=np.empty((G, N, N), np.float64), regions=np.empty((G, 2, N + 2, N + 2), np.float64),
+                   region_counter=np.empty((G, 2), np.float64), cur=np.empty(G, np.int8), done=np.empty(G, np.uint8),
+                   winner=np.empty(G, np.int8), agent=np.empty(G, np.int8), draws=np.empty(G, np.uint32))
+        lib().emu_export_state(self._h, *[_p(out[k]) for k in
+                                          ("board", "regions", "region_counter", "cur", "done", "winner", "agent", "draws")])
+        return out
+
+    def stats(self):
+        out = np.zeros(8, np.int64)
+        lib().emu_stats(self._h, _p(out))
+        return out

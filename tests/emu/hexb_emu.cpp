@@ -1,0 +1,169 @@
+// TEST INFRASTRUCTURE ONLY - host-side emulator of the CUDA tile kernel.
+//
+// Compiles the SAME phase code the device runs (hex_gym_env_b200/csrc/hexb_phases.cuh, hexb_views.cuh) with
+// HEXB_HOST_EMU and replays one CTA at a time: every phase is run for all 128 "threads" before the next one,
+// which is what the __syncthreads() between phases guarantees on the GPU. It lets the CPU test-suite check the
+// device logic against the oracle in a container without a GPU. It is not a CPU fallback: the product package
+// never loads it, and it is far too slow to be one.
+#define HEXB_HOST_EMU 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../hex_gym_env_b200/csrc/hexb_views.cuh"
+
+using namespace hexb;
+
+struct emu_env {
+    int N;
+    Params base;
+    std::vector<uint8_t> state;
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+template <int N>
+static void run_tiles(Params P) {
+    constexpr int C = Geo<N>::C;
+    std::vector<uint8_t> smem(Geo<N>::TILE_BYTES);
+    std::vector<uint32_t> prm1(kTile), prm2(kTile), flg(kTile);
+    std::vector<Rec<N>> recs(kTile);
+    std::vector<Loc> locs(kTile);
+    for (long long g0 = 0; g0 < P.Gpad; g0 += kTile) {
+        Tile<N> T;
+        T.lab = smem.data();
+        T.prm1 = prm1.data();
+        T.prm2 = prm2.data();
+        T.flg = flg.data();
+        T.g0 = g0;
+        memcpy(T.lab, P.labels + g0 * C, Geo<N>::TILE_BYTES);
+        for (int t = 0; t < kTile; ++t) load_rec<N>(P, g0 + t, recs[t]);
+        if (P.mode == MODE_STEP) {
+            for (int t = 0; t < kTile; ++t) phase_agent<N>(T, P, t, recs[t], locs[t]);
+            for (int t = 0; t < kTile; ++t) pass_relabel<N>(T, T.prm1, t);
+            for (int t = 0; t < kTile; ++t) phase_opponent<N>(T, P, t, recs[t], locs[t]);
+            for (int t = 0; t < kTile; ++t)
+                for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
+            for (int t = 0; t < kTile; ++t) pass_encode<N>(T, P, t);
+            for (int t = 0; t < kTile; ++t) phase_clear<N>(T, t);
+        } else if (P.mode == MODE_RESET) {
+            for (int t = 0; t < kTile; ++t) phase_reset<N>(T, P, t, recs[t]);
+            for (int t = 0; t < kTile; ++t) pass_encode<N>(T, P, t);
+            for (int t = 0; t < kTile; ++t) phase_clear<N>(T, t);
+        } else {
+            for (int t = 0; t < kTile; ++t) phase_ply<N>(T, P, t, recs[t]);
+            for (int t = 0; t < kTile; ++t) pass_relabel<N>(T, T.prm1, t);
+        }
+        for (int t = 0; t < kTile; ++t)
+            if (g0 + t < P.G) store_rec<N>(P, g0 + t, recs[t]);
+        memcpy(P.labels + g0 * C, T.lab, Geo<N>::TILE_BYTES);
+    }
+}
+
+#define HEXB_FOR_N(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) X(17) X(18) X(19)
+
+static void dispatch(const emu_env *e, const Params &P) {
+    switch (e->N) {
+#define X(n) \
+    case n: run_tiles<n>(P); break;
+        HEXB_FOR_N(X)
+#undef X
+    }
+}
+
+static View view_of(const emu_env *e) {
+    View V;
+    V.labels = e->base.labels;
+    V.rec = e->base.rec;
+    V.G = e->base.G;
+    V.Gpad = e->base.Gpad;
+    V.N = e->N;
+    V.variant = e->base.variant;
+    V.raw = e->base.raw;
+    return V;
+}
+
+extern "C" {
+
+void *emu_create(int N, int variant, long long G, long long game_offset, unsigned long long seed, int agent_mode, int opponent_first,
+                 int auto_reset, int eval_state, int raw) {
+    if (N < 3 || N > 19 || G < 1) return nullptr;
+    emu_env *e = new emu_env();
+    e->N = N;
+    const long long C = (long long)N * N, W = (C + 31) / 32, R = 2 * W + 3;
+    const long long Gpad = (G + kTile - 1) / kTile * kTile;
+    const size_t rec_off = align256((size_t)(Gpad * C)), stats_off = rec_off + align256((size_t)(R * Gpad * 4));
+    e->state.assign(stats_off + 256 + 256, 0);
+    uint8_t *base = e->state.data();
+    base += (256 - ((uintptr_t)base & 255)) & 255;
+    Params &P = e->base;
+    memset(&P, 0, sizeof(P));
+    P.labels = base;
+    P.rec = (uint32_t *)(base + rec_off);
+    P.stats = (long long *)(base + stats_off);
+    P.G = G; P.Gpad = Gpad; P.game_offset = game_offset; P.seed = seed;
+    P.variant = variant; P.auto_reset = auto_reset; P.eval_state = eval_state; P.opponent_first = opponent_first;
+    P.agent_mode = agent_mode; P.raw = raw;
+    return e;
+}
+void emu_destroy(void *h) { delete (emu_env *)h; }
+
+void emu_reset(void *h, const uint8_t *reset_mask, const double *open_u, int8_t *obs, uint8_t *mask) {
+    emu_env *e = (emu_env *)h;
+    Params P = e->base;
+    P.mode = MODE_RESET; P.reset_mask = reset_mask; P.open_u = open_u; P.obs = obs; P.mask = mask;
+    dispatch(e, P);
+}
+void emu_step(void *h, const int32_t *actions, const double *opp_u, int8_t *obs, uint8_t *mask, float *reward, uint8_t *done,
+              int8_t *term_obs, int32_t *actions_out) {
+    emu_env *e = (emu_env *)h;
+    Params P = e->base;
+    P.mode = MODE_STEP; P.actions = actions; P.opp_u = opp_u; P.obs = obs; P.mask = mask; P.reward = reward; P.done = done;
+    P.term_obs = term_obs; P.actions_out = actions_out;
+    dispatch(e, P);
+}
+void emu_ply(void *h, const int32_t *actions, int8_t *ret) {
+    emu_env *e = (emu_env *)h;
+    Params P = e->base;
+    P.mode = MODE_PLY; P.actions = actions; P.ret = ret;
+    dispatch(e, P);
+}
+void emu_encode(void *h, int view, int8_t *obs, uint8_t *mask) {
+    emu_env *e = (emu_env *)h;
+    const View V = view_of(e);
+    for (long long i = 0; i < V.G * V.N * V.N; ++i) encode_at(V, view, i, obs, mask);
+}
+void emu_sample_actions(void *h, int view, const double *u, int32_t *out) {
+    emu_env *e = (emu_env *)h;
+    const View V = view_of(e);
+    for (long long g = 0; g < V.G; ++g) switch (V.N) {
+#define X(n) \
+    case n: sample_at<n>(V, view, g, u, out); break;
+            HEXB_FOR_N(X)
+#undef X
+        }
+}
+void emu_export_state(void *h, double *board, double *regions, double *counter, int8_t *cur, uint8_t *done, int8_t *winner,
+                      int8_t *agent, uint32_t *draws) {
+    emu_env *e = (emu_env *)h;
+    const View V = view_of(e);
+    const long long n = V.G * 2 * (V.N + 2) * (V.N + 2);
+    for (long long i = 0; i < n; ++i) export_at(V, i, board, regions, counter, cur, done, winner, agent, draws);
+}
+void emu_import_boards(void *h, const int8_t *board_true, const int8_t *to_move) {
+    emu_env *e = (emu_env *)h;
+    for (long long g = 0; g < e->base.G; ++g) switch (e->N) {
+#define X(n) \
+    case n: import_game<n>(e->base, g, board_true, to_move); break;
+            HEXB_FOR_N(X)
+#undef X
+        }
+}
+void emu_stats(void *h, int64_t *out8) {
+    emu_env *e = (emu_env *)h;
+    for (int i = 0; i < 8; ++i) out8[i] = e->base.stats[i];
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+"""Shared parity drivers: run an implementation of the batched simulator next to the golden vectors and the oracle.
+
+`make(kind, N, G, **kw)` must return an object with the RefBatch method surface (reset / step / ply / export / stats,
+numpy in and out). tests/test_emu_parity.py passes the host emulator of the kernel phases (CPU); tests/test_gpu_parity.py
+passes the CUDA library through its C ABI (GPU). Every comparison is bit-exact (integer / byte work; rewards are small
+integers in f32)."""
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+from oracle import hexref
+
+STATE_KEYS = ("board", "regions", "region_counter", "cur", "done", "winner", "agent", "draws")
+
+
+def eq(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape or not np.array_equal(a, b):
+        bad = np.argwhere(a != b) if a.shape == b.shape else None
+        raise AssertionError("%s differs%s" % (what, "" if bad is None else " at %s (first of %d)" % (bad[0], len(bad))))
+
+
+def golden_raw_game(make, name):
+    z = np.load(os.path.join(GOLDEN, name))
+    N = int(z["N"])
+    moves = z["moves"]
+    n_games, T = moves.shape
+    env = make(hexref.KIND_GAME_A, N, n_games)
+    env.reset()
+    for t in range(T):
+        ret = env.ply(moves[:, t])
+        e = env.export()
+        eq(ret, z["ret"][:, t], "%s ret t=%d" % (name, t))
+        eq(e["board"], z["board"][:, t].astype(np.float64), "%s board t=%d" % (name, t))
+        eq(e["regions"], z["regions"][:, t].astype(np.float64), "%s regions t=%d" % (name, t))
+        eq(e["region_counter"], z["counter"][:, t].astype(np.float64), "%s counter t=%d" % (name, t))
+        eq(e["cur"], z["cur"][:, t], "%s cur t=%d" % (name, t))
+        eq(e["done"], z["done"][:, t], "%s done t=%d" % (name, t))
+        eq(e["winner"], z["winner"][:, t], "%s winner t=%d" % (name, t))
+
+
+def golden_rollout(make, name):
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, fused = int(z["N"]), int(z["seed"]), int(z["fused"])
+    T, G = z["actions"].shape
+    if name.startswith("selfplay"):
+        env = make(hexref.KIND_SELFPLAY_B, N, G, seed=seed, agent_mode=int(z["agent_mode"]))
+    else:
+        env = make(hexref.KIND_ENV_A, N, G, seed=seed, opponent_first=bool(int(z["opponent_first"])))
+    obs0, mask0 = env.reset()
+    eq(obs0, z["obs0"], name + " obs0")
+    eq(mask0, z["mask0"], name + " mask0")
+    e = env.export()
+    eq(e["agent"], z["agent"], name + " agent")
+    eq(e["draws"], z["draws0"], name + " draws0")
+    for t in range(T):
+        o = env.step(None if fused else z["actions"][t], want_term=True)
+        w = "%s t=%d " % (name, t)
+        eq(o["actions"], z["actions"][t], w + "actions")
+        eq(o["reward"], z["reward"][t], w + "reward")
+        eq(o["done"], z["done"][t], w + "done")
+        eq(o["obs"], z["obs"][t], w + "obs")
+        eq(o["mask"], z["mask"][t], w + "mask")
+        d = z["done"][t].astype(bool)
+        eq(o["term_obs"][d], z["term_obs"][t][d], w + "term_obs")
+        e = env.export()
+        eq(e["regions"], z["regions"][t].astype(np.float64), w + "regions")
+        eq(e["region_counter"], z["counter"][t].astype(np.float64), w + "counter")
+        eq(e["cur"], z["sim_cur"][t], w + "cur")
+        eq(e["draws"], z["draws"][t], w + "draws")
+
+
+def versus_oracle(make, kind, N, G, T, seed=0, game_offset=0, fused=True, auto_reset=True, illegal_rate=0.03,
+                  check_state_every=1, **kw):
+    """Side-by-side rollout of `make(...)` and the oracle on the same seeded inputs."""
+    ref = hexref.RefBatch(kind, N, G, seed=seed, game_offset=game_offset, **kw)
+    env = make(kind, N, G, seed=seed, game_offset=game_offset, auto_reset=auto_reset, **kw)
+    rs = np.random.RandomState(seed + 17)
+    ro, rm = ref.reset()
+    o, m = env.reset()
+    eq(o, ro, "reset obs")
+    eq(m, rm, "reset mask")
+    C = N * N
+    for t in range(T):
+        if fused:
+            acts = None
+        else:
+            # uniformly random legal action from the oracle's mask, sometimes an arbitrary (possibly illegal) cell
+            u = rs.rand(G)
+            cnt = rm.sum(1).astype(np.int64)
+            k = np.minimum((u * cnt).astype(np.int64), np.maximum(cnt - 1, 0))
+            order = np.argsort(-rm.astype(np.int8), axis=1, kind="stable")
+            acts = order[np.arange(G), k].astype(np.int32)
+            bad = rs.rand(G) < illegal_rate
+            acts[bad] = rs.randint(-2, C + 2, size=int(bad.sum()))
+        r = ref.step(acts, auto_reset=auto_reset, want_term=True)
+        o = env.step(acts, want_term=True)
+        w = "N=%d t=%d " % (N, t)
+        for key in ("actions", "reward", "done", "obs", "mask"):
+            if key == "actions" and not fused:
+                continue
+            eq(o[key], r[key], w + key)
+        d = r["done"].astype(bool)
+        if auto_reset or t == 0 or True:
+            newly = d if auto_reset else d
+            eq(o["term_obs"][newly] if auto_reset else o["obs"][newly], r["term_obs"][newly], w + "term_obs")
+        rm = r["mask"]
+        if check_state_every and t % check_state_every == 0:
+            re_, e = ref.export(), env.export()
+            for key in STATE_KEYS:
+                eq(e[key], re_[key], w + key)
+    eq(env.stats(), ref.stats(), "stats")
+    return ref, env

@@ -1,0 +1,54 @@
+"""CPU: the kernel's phase code (hex_gym_env_b200/csrc/hexb_phases.cuh), replayed serially by the host emulator
+(tests/emu), against the golden vectors of the unmodified reference and against the oracle. This is a check of the
+device LOGIC in a container without a GPU; the -m gpu tests repeat the same drivers through libhexb.so on the B200."""
+import numpy as np
+import pytest
+
+import parity
+from conftest import golden_files
+from oracle import hexref
+from emu.emu import EmuBatch
+
+
+def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False):
+    if kind == hexref.KIND_GAME_A:
+        return EmuBatch(0, N, G, raw=True)
+    variant = 0 if kind == hexref.KIND_ENV_A else 1
+    return EmuBatch(variant, N, G, seed=seed, game_offset=game_offset, agent_mode=agent_mode, opponent_first=opponent_first,
+                    auto_reset=auto_reset, eval_state=eval_state)
+
+
+@pytest.mark.parametrize("name", golden_files("game_A"))
+def test_golden_raw_games(name):
+    parity.golden_raw_game(make, name)
+
+
+@pytest.mark.parametrize("name", golden_files("selfplay_") + golden_files("envA_"))
+def test_golden_rollouts(name):
+    parity.golden_rollout(make, name)
+
+
+@pytest.mark.parametrize("N", [3, 4, 5, 6, 7, 8, 9, 11, 13, 19])
+@pytest.mark.parametrize("agent_mode", [0, 1, 2])
+def test_selfplay_vs_oracle(N, agent_mode):
+    G = 300 if N <= 11 else 140   # not a multiple of the 128-game tile: exercises the ragged last tile
+    T = 2 * N * N // 3 + 10
+    parity.versus_oracle(make, hexref.KIND_SELFPLAY_B, N, G, T, seed=N * 10 + agent_mode, game_offset=12345678901 * agent_mode,
+                         fused=(agent_mode != 1), agent_mode=agent_mode)
+
+
+@pytest.mark.parametrize("N", [3, 5, 7, 10])
+@pytest.mark.parametrize("opponent_first", [False, True])
+def test_envA_vs_oracle(N, opponent_first):
+    parity.versus_oracle(make, hexref.KIND_ENV_A, N, 200, N * N, seed=5 + N, fused=not opponent_first, opponent_first=opponent_first)
+
+
+@pytest.mark.parametrize("kind", [hexref.KIND_SELFPLAY_B, hexref.KIND_ENV_A])
+def test_no_auto_reset(kind):
+    """Finished games stay finished: terminal observation (incl. the opponent's view after an agent win), stale rewards."""
+    kw = dict(agent_mode=2) if kind == hexref.KIND_SELFPLAY_B else {}
+    parity.versus_oracle(make, kind, 4, 200, 30, seed=3, fused=False, auto_reset=False, illegal_rate=0.1, **kw)
+
+
+def test_eval_state_draws():
+    parity.versus_oracle(make, hexref.KIND_SELFPLAY_B, 5, 130, 40, seed=9, agent_mode=2, eval_state=True)
