@@ -1,0 +1,233 @@
+"""HexBatch - G independent Hex games living on one B200, advanced in lockstep by the kernels of libhexb.so.
+
+This is the thin host object over the C ABI of include/hexb.h. torch is used for device memory, streams and
+(in multi_gpu.py) torch.distributed only; every operation on game state is a call through the C ABI into the
+hand-written sm_100a kernels (hex_gym_env_b200/csrc). There is no CPU path: constructing a HexBatch without the
+CUDA library or without a GPU raises.
+
+What each method replaces in the reference (MBPrdctns/hex_gym_env, paths relative to its root):
+  reset()            HexEnv.reset (minihex/HexGame.py:206-242, minihex/HexSingleGame.py:208-231), SelfPlayEnv.reset
+                     (minihex/SelfplayWrapper.py:69-89) for all games or a masked subset
+  step()             SelfPlayEnv.step (SelfplayWrapper.py:174-199) / variant-A HexEnv.step (HexGame.py:244-295) incl. the
+                     random opponent, reward/done, DummyVecEnv-style auto-reset, observation and legal-action mask
+  ply()              HexGame.make_move / fast_move (HexGame.py:85-111, HexSingleGame.py:88-122)
+  encode()           get_action_mask (HexGame.py:203-204) / legal_actions (HexSingleGame.py:205-206) + the live board
+  sample_actions()   BaseRandomPolicy.choose_action (SelfplayWrapper.py:17-22) / random_policy (minihex/__init__.py:8-12)
+  export_state()     attribute reads .board / .regions / .region_counter / .current_player_num / .done / .winner
+  import_boards()    HexGame.__init__ with a preset board (HexGame.py:53-61, HexSingleGame.py:57-65)
+"""
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import HexbConfig, check
+
+VARIANT_A = 0  # minihex/HexGame.py
+VARIANT_B = 1  # minihex/HexSingleGame.py + minihex/SelfplayWrapper.py
+AGENT_BLACK, AGENT_WHITE, AGENT_RANDOM = 0, 1, 2
+
+STAT_NAMES = ("episodes", "black_wins", "white_wins", "agent_wins", "episode_plies", "invalid_ends", "env_steps", "plies")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class HexBatch(object):
+    def __init__(self, board_size, num_games, variant=VARIANT_B, device=None, seed=0, game_offset=0,
+                 agent_mode=AGENT_BLACK, opponent_first=False, auto_reset=True, eval_state=False, raw=False):
+        self._h = None
+        self._lib = _native.lib()  # raises if libhexb.so cannot be built / loaded
+        if not torch.cuda.is_available():
+            raise RuntimeError("hex_gym_env_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.N, self.G, self.C = int(board_size), int(num_games), int(board_size) * int(board_size)
+        self.variant, self.raw, self.auto_reset = int(variant), bool(raw), bool(auto_reset)
+        self.cfg = HexbConfig(board_size=self.N, variant=self.variant, num_games=self.G, game_offset=int(game_offset),
+                              seed=int(seed) & 0xFFFFFFFFFFFFFFFF, agent_mode=int(agent_mode), opponent_first=int(bool(opponent_first)),
+                              auto_reset=int(bool(auto_reset)), eval_state=int(bool(eval_state)), raw=int(bool(raw)),
+                              device=self.device.index)
+        nbytes = self._lib.hexb_state_bytes(ctypes.byref(self.cfg))
+        if nbytes == 0:
+            raise ValueError("unsupported configuration: board_size=%r num_games=%r variant=%r agent_mode=%r"
+                             % (board_size, num_games, variant, agent_mode))
+        self.state_bytes = int(nbytes)
+        with torch.cuda.device(self.device):
+            self._state = torch.empty(self.state_bytes + 256, dtype=torch.uint8, device=self.device)
+            off = (-self._state.data_ptr()) % 256
+            self._state_ptr = self._state.data_ptr() + off
+            h = ctypes.c_void_p()
+            check(self._lib.hexb_create(ctypes.byref(self.cfg), ctypes.c_void_p(self._state_ptr), self.state_bytes,
+                                        self._stream(), ctypes.byref(h)))
+        self._h = h
+        self._out = {}
+        self._ws = None
+        self._pinned = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hexb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _buf(self, name, shape, dtype):
+        t = self._out.get(name)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._out[name] = t
+        return t
+
+    def _chk(self, t, shape, dtype, name):
+        if t is None:
+            return None
+        if not (t.is_cuda and t.device == self.device and t.dtype == dtype and t.is_contiguous() and tuple(t.shape) == tuple(shape)):
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s" % (name, dtype, tuple(shape), self.device))
+        return t
+
+    def _in(self, x, shape, dtype, name):
+        if x is None:
+            return None
+        t = torch.as_tensor(x)
+        if t.dtype != dtype or not t.is_cuda or t.device != self.device:
+            t = t.to(device=self.device, dtype=dtype)
+        t = t.contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+        return t
+
+    # ------------------------------------------------------------------ the hot path
+    def reset(self, reset_mask=None, open_u=None, obs=None, mask=None):
+        """Reset all games (or those with reset_mask != 0). Returns (obs i8[G,N,N], mask u8[G,C]) device tensors."""
+        G, N, C = self.G, self.N, self.C
+        rm = self._in(reset_mask, (G,), torch.uint8, "reset_mask")
+        ou = self._in(open_u, (G,), torch.float64, "open_u")
+        obs = self._chk(obs, (G, N, N), torch.int8, "obs") if obs is not None else self._buf("obs", (G, N, N), torch.int8)
+        mask = self._chk(mask, (G, C), torch.uint8, "mask") if mask is not None else self._buf("mask", (G, C), torch.uint8)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_reset(self._h, _ptr(rm), _ptr(ou), _ptr(obs), _ptr(mask), self._stream()))
+        return obs, mask
+
+    def step(self, actions=None, opp_u=None, obs=None, mask=None, reward=None, done=None, term_obs=None, actions_out=None,
+             want_term=False, want_actions=False, outputs=True):
+        """One env step for every game. actions=None: the agent is the random policy as well (fused sampling).
+
+        Returns a dict of device tensors (obs, mask, reward, done [, term_obs, actions]). The default output tensors
+        are owned by this object and overwritten by the next call (like the reference, whose observation is the live
+        board array); pass your own tensors (e.g. rollout-buffer slices) to keep them. outputs=False steps without
+        writing any observation (pure simulation)."""
+        G, N, C = self.G, self.N, self.C
+        a = self._in(actions, (G,), torch.int32, "actions")
+        u = self._in(opp_u, (G, 2), torch.float64, "opp_u")
+        if outputs:
+            obs = self._chk(obs, (G, N, N), torch.int8, "obs") if obs is not None else self._buf("obs", (G, N, N), torch.int8)
+            mask = self._chk(mask, (G, C), torch.uint8, "mask") if mask is not None else self._buf("mask", (G, C), torch.uint8)
+            reward = self._chk(reward, (G,), torch.float32, "reward") if reward is not None else self._buf("reward", (G,), torch.float32)
+            done = self._chk(done, (G,), torch.uint8, "done") if done is not None else self._buf("done", (G,), torch.uint8)
+        if term_obs is not None:
+            term_obs = self._chk(term_obs, (G, N, N), torch.int8, "term_obs")
+        elif want_term:
+            term_obs = self._buf("term_obs", (G, N, N), torch.int8)
+        if actions_out is not None:
+            actions_out = self._chk(actions_out, (G,), torch.int32, "actions_out")
+        elif want_actions:
+            actions_out = self._buf("actions", (G,), torch.int32)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_step(self._h, _ptr(a), _ptr(u), _ptr(obs), _ptr(mask), _ptr(reward), _ptr(done), _ptr(term_obs),
+                                      _ptr(actions_out), self._stream()))
+        out = dict(obs=obs, mask=mask, reward=reward, done=done)
+        if term_obs is not None:
+            out["term_obs"] = term_obs
+        if actions_out is not None:
+            out["actions"] = actions_out
+        return out
+
+    def pinned_io(self):
+        """Pinned host buffers for step_host: dict(actions i32[G], obs i8[G,N,N], mask u8[G,C], reward f32[G], done u8[G])."""
+        if self._pinned is None:
+            G, N, C = self.G, self.N, self.C
+            self._pinned = dict(actions=torch.empty(G, dtype=torch.int32).pin_memory(),
+                                obs=torch.empty((G, N, N), dtype=torch.int8).pin_memory(),
+                                mask=torch.empty((G, C), dtype=torch.uint8).pin_memory(),
+                                reward=torch.empty(G, dtype=torch.float32).pin_memory(),
+                                done=torch.empty(G, dtype=torch.uint8).pin_memory())
+        return self._pinned
+
+    def step_host(self, actions_host=None, io=None, want_obs=True, want_mask=True):
+        """The step as a host-side user of the reference API makes it: HOST actions in, HOST obs/mask/reward/done out
+        (one call, copies inside, returns when the results are in host memory). `io` = pinned_io() or compatible CPU
+        tensors. actions_host=None: fused agent sampling on the device (no H2D)."""
+        io = io or self.pinned_io()
+        if self._ws is None:
+            n = self._lib.hexb_host_workspace_bytes(ctypes.byref(self.cfg))
+            self._ws = torch.empty(int(n) + 256, dtype=torch.uint8, device=self.device)
+        ws = self._ws.data_ptr() + ((-self._ws.data_ptr()) % 256)
+        if actions_host is not None and actions_host is not io["actions"]:
+            io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_step_host(self._h, ctypes.c_void_p(ws), _ptr(io["actions"]) if actions_host is not None else None,
+                                           _ptr(io["obs"]) if want_obs else None, _ptr(io["mask"]) if want_mask else None,
+                                           _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
+        return io
+
+    # ------------------------------------------------------------------ the pieces on their own
+    def ply(self, actions, ret=None):
+        a = self._in(actions, (self.G,), torch.int32, "actions")
+        ret = self._chk(ret, (self.G,), torch.int8, "ret") if ret is not None else self._buf("ret", (self.G,), torch.int8)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_ply(self._h, _ptr(a), _ptr(ret), self._stream()))
+        return ret
+
+    def encode(self, view=0, obs=None, mask=None):
+        G, N, C = self.G, self.N, self.C
+        obs = self._chk(obs, (G, N, N), torch.int8, "obs") if obs is not None else self._buf("obs", (G, N, N), torch.int8)
+        mask = self._chk(mask, (G, C), torch.uint8, "mask") if mask is not None else self._buf("mask", (G, C), torch.uint8)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_encode(self._h, int(view), _ptr(obs), _ptr(mask), self._stream()))
+        return obs, mask
+
+    def sample_actions(self, u, view=0, out=None):
+        uu = self._in(u, (self.G,), torch.float64, "u")
+        out = self._chk(out, (self.G,), torch.int32, "out") if out is not None else self._buf("sampled", (self.G,), torch.int32)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_sample_actions(self._h, int(view), _ptr(uu), _ptr(out), self._stream()))
+        return out
+
+    def export_state(self):
+        """Reference-layout dump (float64 like the reference's numpy arrays). New tensors every call."""
+        G, N = self.G, self.N
+        dev = self.device
+        out = dict(board=torch.empty((G, N, N), dtype=torch.float64, device=dev),
+                   regions=torch.empty((G, 2, N + 2, N + 2), dtype=torch.float64, device=dev),
+                   region_counter=torch.empty((G, 2), dtype=torch.float64, device=dev),
+                   cur=torch.empty(G, dtype=torch.int8, device=dev), done=torch.empty(G, dtype=torch.uint8, device=dev),
+                   winner=torch.empty(G, dtype=torch.int8, device=dev), agent=torch.empty(G, dtype=torch.int8, device=dev),
+                   draws=torch.empty(G, dtype=torch.int32, device=dev))
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_export_state(self._h, *[_ptr(out[k]) for k in ("board", "regions", "region_counter", "cur", "done",
+                                                                                 "winner", "agent", "draws")], self._stream()))
+        return out
+
+    def import_boards(self, board_true, to_move=None):
+        b = self._in(board_true, (self.G, self.N, self.N), torch.int8, "board_true")
+        tm = self._in(to_move, (self.G,), torch.int8, "to_move")
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_import_boards(self._h, _ptr(b), _ptr(tm), self._stream()))
+
+    def stats(self, out=None):
+        """Episode statistics since creation as a device int64[8] tensor (see STAT_NAMES)."""
+        out = self._chk(out, (8,), torch.int64, "out") if out is not None else torch.empty(8, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_stats(self._h, _ptr(out), self._stream()))
+        return out

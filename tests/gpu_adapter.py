@@ -1,0 +1,56 @@
+"""Adapter giving hex_gym_env_b200.HexBatch (CUDA, through the C ABI) the numpy method surface of oracle.hexref.RefBatch
+so that tests/parity.py can drive it. Used only by the -m gpu tests."""
+import numpy as np
+import torch
+
+from hex_gym_env_b200 import HexBatch
+from oracle import hexref
+
+
+class GpuBatch(object):
+    def __init__(self, variant, N, G, **kw):
+        self.b = HexBatch(N, G, variant=variant, device=0, **kw)
+        self.N, self.G = N, G
+
+    @staticmethod
+    def _np(t):
+        return t.cpu().numpy()
+
+    def reset(self, reset_mask=None, open_u=None):
+        obs, mask = self.b.reset(reset_mask, open_u)
+        return self._np(obs), self._np(mask)
+
+    def step(self, actions=None, opp_u=None, want_term=False):
+        if want_term:
+            self.b._buf("term_obs", (self.G, self.N, self.N), torch.int8).zero_()
+        o = self.b.step(actions, opp_u, want_term=want_term, want_actions=True)
+        return {k: self._np(v) for k, v in o.items()}
+
+    def ply(self, actions):
+        return self._np(self.b.ply(actions))
+
+    def encode(self, view=0):
+        obs, mask = self.b.encode(view)
+        return self._np(obs), self._np(mask)
+
+    def sample_actions(self, u, view=0):
+        return self._np(self.b.sample_actions(u, view))
+
+    def import_boards(self, board_true, to_move=None):
+        self.b.import_boards(board_true, to_move)
+
+    def export(self):
+        e = {k: self._np(v) for k, v in self.b.export_state().items()}
+        e["draws"] = e["draws"].astype(np.uint32)
+        return e
+
+    def stats(self):
+        return self._np(self.b.stats())
+
+
+def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False):
+    if kind == hexref.KIND_GAME_A:
+        return GpuBatch(0, N, G, raw=True)
+    variant = 0 if kind == hexref.KIND_ENV_A else 1
+    return GpuBatch(variant, N, G, seed=seed, game_offset=game_offset, agent_mode=agent_mode, opponent_first=opponent_first,
+                    auto_reset=auto_reset, eval_state=eval_state)
