@@ -251,7 +251,7 @@ def run_gpu(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "hexb_tile_kernel<%d> MODE_STEP" % N, "kernel_ms": kern_ms,
+                "kernel": "hexb_step_kernel<%d> MODE_STEP" % N, "kernel_ms": kern_ms,
                 "bytes_per_env_step_contract": B, "bytes_per_env_step_moved": moved_bytes(N),
                 "achieved_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
@@ -321,7 +321,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--board", type=int, default=BOARD)

@@ -35,7 +35,7 @@ namespace hexb {
 // ----------------------------------------------------------------------------------------------
 // constants
 // ----------------------------------------------------------------------------------------------
-constexpr int kTile = 128;  // games per CTA tile == threads per CTA
+constexpr int kTile = 128;  // games per CTA == threads per CTA (4 warps, each owning a chunk of 32 games)
 
 enum : int { VARIANT_A = 0, VARIANT_B = 1 };
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_PLY = 2 };
@@ -59,12 +59,15 @@ constexpr uint32_t M_AGENT_ENDED = 1u << 26;  // the agent's own ply ended the e
 //   prm: bits 0-7 o1 (tagged), 8-15 o2 (tagged), 16-23 m (tagged), 24 need-relabel
 constexpr uint32_t P_NEED = 1u << 24;
 //   flg: bit 0 resetting, bit 1 output view is the opponent's (transposed+swapped), bit 2 has opening stone,
-//        bit 3 emit terminal obs, bit 4 terminal view is the opponent's; bits 8-15 opening byte, 16-31 opening cell
+//        bit 3 emit terminal obs, bit 4 terminal view is the opponent's, bit 5 row needs the relabel sweep;
+//        bits 8-15 opening byte, 16-31 opening cell
 constexpr uint32_t F_RESET = 1u << 0;
 constexpr uint32_t F_VIEW_OPP = 1u << 1;
 constexpr uint32_t F_OPEN = 1u << 2;
 constexpr uint32_t F_TERM = 1u << 3;
 constexpr uint32_t F_TERM_OPP = 1u << 4;
+constexpr uint32_t F_RELABEL = 1u << 5;
+constexpr uint32_t F_ROWJOB = F_RESET | F_TERM | F_RELABEL;  // anything the warp has to sweep the row for
 
 template <int N>
 struct Geo {
@@ -87,7 +90,7 @@ struct Params {
     // packed state (owned by the handle)
     uint8_t *labels;      // [Gpad][C]
     uint32_t *rec;        // [R][Gpad]
-    long long *stats;     // [8]
+    long long *stats;     // [kStatStripes][8]
     long long G, Gpad, game_offset;
     unsigned long long seed;
     int variant, auto_reset, eval_state, opponent_first, agent_mode, mode;

@@ -3,16 +3,11 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (see build.py).
 //
 // Kernel inventory:
-//   K1/K2/K3  hexb_tile_kernel<N>  one CTA per tile of 128 games; MODE_RESET / MODE_STEP / MODE_PLY
+//   K1/K2/K3  hexb_step_kernel<N>  one warp per chunk of 32 games, 4 warps per CTA; MODE_RESET / MODE_STEP / MODE_PLY
 //   K4        hexb_sample_kernel   standalone k-th-empty-cell sampler
 //   K5        hexb_encode_kernel   standalone observation + mask encoder (either view)
 //   K6        hexb_export_kernel / hexb_import_kernel   reference-layout dump / preset boards
-//   K7        statistics: warp __reduce_add_sync + one atomic per CTA inside the tile kernel; hexb_stats copies
-//
-// Data movement of the tile kernel: the tile's label bytes (128*C contiguous bytes) are brought into shared
-// memory by ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA path, completion on an mbarrier) while the
-// threads fetch their record words with coalesced 32-bit loads ([word][game] layout); obs and mask leave as
-// coalesced 32-bit stores straight from registers; the label bytes return with one bulk store.
+//   K7        statistics: warp __reduce_add_sync + one atomic per warp and counter (striped); hexb_stats sums the stripes
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -60,97 +55,122 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ------------------------------------------------------------------------------------------------ tile kernel
+// ------------------------------------------------------------------------------------------------ step kernel
+// One warp = one chunk of 32 games; a CTA is 4 independent warps (no __syncthreads anywhere). Per warp:
+//   lane 0 starts ONE bulk asynchronous copy (cp.async.bulk = the 1-D TMA path, completion on the warp's own mbarrier)
+//   of the chunk's 32*C label bytes into shared memory; meanwhile every lane loads its game's record words (coalesced,
+//   [word][game] layout) and runs the Philox rounds of the step's two draws; then the thread-per-game plies, the
+//   warp-per-game row jobs, the elementwise obs/mask encode with 16-byte coalesced stores, the record stores and one
+//   bulk copy of the chunk back to global memory.
+constexpr int kWarpsPerCta = kTile / kWarp;
+
 template <int N>
 struct SmemLayout {
-    static constexpr int LAB = 0;
-    static constexpr int PRM1 = Geo<N>::TILE_BYTES;
-    static constexpr int PRM2 = PRM1 + kTile * 4;
-    static constexpr int FLG = PRM2 + kTile * 4;
-    static constexpr int STATS = FLG + kTile * 4;
-    static constexpr int BAR = STATS + 8 * 4;
-    static constexpr int BYTES = BAR + 16;
+    static constexpr int CHUNK = Chunk<N>::BYTES;
+    static constexpr int BAR = kWarpsPerCta * CHUNK;   // multiple of 16
+    static constexpr int BYTES = BAR + kWarpsPerCta * 8;
 };
 
 template <int N>
-__global__ void __launch_bounds__(kTile) hexb_tile_kernel(const Params P, const int use_bulk) {
+__device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params &P, long long g0, int lane) {
+    constexpr int C = Geo<N>::C;
+    const long long out0 = g0 * C;        // byte offset of the chunk in obs / mask (multiple of 16)
+    const long long limit = P.G * C;      // bytes that exist in the caller's buffers
+    const uint4 *src = reinterpret_cast<const uint4 *>(chunk);
+    uint8_t *obs = reinterpret_cast<uint8_t *>(P.obs);
+    const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)P.mask)) & 15) == 0;
+#pragma unroll 2
+    for (int i = lane; i < Chunk<N>::VECS; i += kWarp) {
+        const uint4 x = src[i];
+        Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
+        encode_vec<N>(in, P.variant, o, m);
+        const long long off = out0 + 16ll * i;
+        if (vec_ok && off + 16 <= limit) {
+            if (obs) __stcs(reinterpret_cast<uint4 *>(obs + off), make_uint4(o.x, o.y, o.z, o.w));
+            if (P.mask) __stcs(reinterpret_cast<uint4 *>(P.mask + off), make_uint4(m.x, m.y, m.z, m.w));
+        } else {
+            if (obs) store_tail(obs, off, limit, o);
+            if (P.mask) store_tail(P.mask, off, limit, m);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kTile) hexb_step_kernel(const Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using SL = SmemLayout<N>;
-    constexpr int TB = Geo<N>::TILE_BYTES;
-    Tile<N> T;
-    T.lab = smem + SL::LAB;
-    T.prm1 = reinterpret_cast<uint32_t *>(smem + SL::PRM1);
-    T.prm2 = reinterpret_cast<uint32_t *>(smem + SL::PRM2);
-    T.flg = reinterpret_cast<uint32_t *>(smem + SL::FLG);
-    int *sstats = reinterpret_cast<int *>(smem + SL::STATS);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SL::BAR);
-    const int tid = threadIdx.x;
-    T.g0 = (long long)blockIdx.x * kTile;
-    uint8_t *gl = P.labels + T.g0 * Geo<N>::C;
+    constexpr int C = Geo<N>::C;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint8_t *chunk = smem + wid * SL::CHUNK;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + SL::BAR) + wid;
+    const long long wglobal = (long long)blockIdx.x * kWarpsPerCta + wid;
+    const long long g0 = wglobal * kWarp;   // first game of the chunk
+    const long long g = g0 + lane;          // this lane's game
+    uint8_t *gl = P.labels + g0 * C;
 
-    // ---- tile in
-    if (use_bulk) {
-        if (tid == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, TB);
-            bulk_g2s(T.lab, gl, TB, bar);
-        }
-    } else {
-        const uint4 *s = reinterpret_cast<const uint4 *>(gl);
-        uint4 *d = reinterpret_cast<uint4 *>(T.lab);
-        for (int i = tid; i < TB / 16; i += kTile) d[i] = s[i];
+    // ---- chunk in (asynchronous), record in, draws
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, SL::CHUNK);
+        bulk_g2s(chunk, gl, SL::CHUNK, bar);
     }
-    if (tid < 8) sstats[tid] = 0;
     Rec<N> rec;
-    load_rec<N>(P, T.g0 + tid, rec);
-    __syncthreads();  // barrier init / plain copy visible
-    if (use_bulk) mbar_wait(bar, 0);
+    load_rec<N>(P, g, rec);
+    double u_agent = 0.0, u_opp = 0.0;
+    if (P.mode == MODE_STEP && g < P.G) pre_draws<N>(P, rec, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+    __syncwarp();  // the barrier's initialisation is visible to the other lanes
+    mbar_wait(bar, 0);
 
-    // ---- phases
+    // ---- thread-per-game phase
+    uint32_t prmA = 0, prmB = 0, flg = 0;
+    uint8_t *L = chunk + lane * C;
     if (P.mode == MODE_STEP) {
         Loc loc;
-        phase_agent<N>(T, P, tid, rec, loc);
-        __syncthreads();
-        pass_relabel<N>(T, T.prm1, tid);
-        __syncthreads();
-        phase_opponent<N>(T, P, tid, rec, loc);
-        // K7: episode statistics, warp reduction then one shared and one global atomic per counter
+        game_step<N>(L, P, g, rec, u_agent, u_opp, loc, prmA, prmB, flg);
+        // K7: episode statistics - warp reduction, then one atomic per non-zero counter into this warp's stripe
+        unsigned long long *stripe = reinterpret_cast<unsigned long long *>(P.stats) + 8 * (wglobal & (kStatStripes - 1));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int v = __reduce_add_sync(0xffffffffu, loc.st[i]);
-            if ((tid & 31) == 0 && v) atomicAdd(&sstats[i], v);
+            const int v = __reduce_add_sync(FULL, loc.st[i]);
+            if (lane == 0 && v) atomicAdd(stripe + i, (unsigned long long)v);
         }
-        __syncthreads();
-        pass_encode<N>(T, P, tid);
-        __syncthreads();
-        phase_clear<N>(T, tid);
-        if (tid < 8 && sstats[tid]) atomicAdd(reinterpret_cast<unsigned long long *>(P.stats) + tid, (unsigned long long)sstats[tid]);
     } else if (P.mode == MODE_RESET) {
-        phase_reset<N>(T, P, tid, rec);
-        __syncthreads();
-        pass_encode<N>(T, P, tid);
-        __syncthreads();
-        phase_clear<N>(T, tid);
+        game_reset<N>(P, g, rec, flg);
     } else {
-        phase_ply<N>(T, P, tid, rec);
-        __syncthreads();
-        pass_relabel<N>(T, T.prm1, tid);
+        game_ply<N>(L, P, g, rec, prmA, flg);
+    }
+    if (g < P.G) store_rec<N>(P, g, rec);
+    __syncwarp();  // every game's new stones are in shared memory
+
+    // ---- warp-per-game row jobs: relabel / terminal observation / clear + opening stone
+    uint32_t pending = __ballot_sync(FULL, (flg & F_ROWJOB) != 0u);
+    while (pending) {
+        const int r = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r), rf = __shfl_sync(FULL, flg, r);
+        row_job_lane<N>(chunk, r, ra, rb, rf, P, g0 + r, lane, [] { __syncwarp(); });
+        __syncwarp();
     }
 
-    // ---- tile out
-    if (T.g0 + tid < P.G) store_rec<N>(P, T.g0 + tid, rec);
-    if (use_bulk) {
-        fence_async_smem();  // generic-proxy writes to smem -> visible to the async proxy
-        __syncthreads();
-        if (tid == 0) {
-            bulk_s2g(gl, T.lab, TB);
-            bulk_wait_read();
+    // ---- observation + mask
+    if (P.mode != MODE_PLY && (P.obs || P.mask)) {
+        encode_chunk<N>(chunk, P, g0, lane);
+        uint32_t views = __ballot_sync(FULL, (flg & F_VIEW_OPP) != 0u);  // only without auto-reset: finished by the agent's own ply
+        if (views) __syncwarp();
+        while (views) {
+            const int r = __ffs(views) - 1;
+            views &= views - 1;
+            view_row_lane<N>(chunk, r, P, g0 + r, lane);
         }
-    } else {
-        __syncthreads();
-        const uint4 *s = reinterpret_cast<const uint4 *>(T.lab);
-        uint4 *d = reinterpret_cast<uint4 *>(gl);
-        for (int i = tid; i < TB / 16; i += kTile) d[i] = s[i];
+    }
+
+    // ---- chunk out
+    fence_async_smem();  // generic-proxy writes to shared memory -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+        bulk_s2g(gl, chunk, SL::CHUNK);
+        bulk_wait_read();
     }
 }
 
@@ -176,14 +196,17 @@ __global__ void hexb_import_kernel(Params P, const int8_t *board_true, const int
 }
 
 __global__ void hexb_stats_kernel(const long long *src, int64_t *dst) {
-    if (threadIdx.x < 8) dst[threadIdx.x] = (int64_t)src[threadIdx.x];
+    if (threadIdx.x < 8) {
+        long long v = 0;
+        for (int s = 0; s < kStatStripes; ++s) v += src[8 * s + threadIdx.x];
+        dst[threadIdx.x] = (int64_t)v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 struct hexb_env {
     hexb_config cfg;
     Params base;  // state pointers + config, I/O pointers null
-    int use_bulk;
 };
 
 static thread_local int g_last_cuda = 0;
@@ -221,7 +244,7 @@ static Layout layout_of(const hexb_config *c) {
     L.labels_off = 0;
     L.rec_off = align256((size_t)(L.Gpad * C));
     L.stats_off = L.rec_off + align256((size_t)(R * L.Gpad * 4));
-    L.total = L.stats_off + 256;
+    L.total = L.stats_off + align256((size_t)kStatStripes * 8 * 8);
     return L;
 }
 
@@ -269,8 +292,6 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     P.opponent_first = cfg->opponent_first;
     P.agent_mode = cfg->agent_mode;
     P.raw = cfg->raw;
-    const char *b = getenv("HEXB_BULK");
-    e->use_bulk = (b && b[0] == '0') ? 0 : 1;
     *out = e;
     return HEXB_OK;
 }
@@ -288,11 +309,12 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     constexpr int smem = SmemLayout<N>::BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-        CK(cudaFuncSetAttribute(hexb_tile_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
     const unsigned grid = (unsigned)(P.Gpad / kTile);
-    hexb_tile_kernel<N><<<grid, kTile, smem, s>>>(P, e->use_bulk);
+    (void)e;
+    hexb_step_kernel<N><<<grid, kTile, smem, s>>>(P);
     CK(cudaGetLastError());
     return HEXB_OK;
 }

@@ -1,41 +1,44 @@
-// hexb_phases.cuh - the phases of the fused step kernel, one function per phase.
+// hexb_phases.cuh - the pieces of the fused step kernel.
 //
-// A CTA owns a TILE of kTile consecutive games. Its label bytes (kTile*C contiguous bytes, the same
-// layout as the obs / mask outputs) sit in shared memory for the whole step:
+// A WARP owns a CHUNK of 32 consecutive games. The chunk's label bytes (32*C contiguous, 16-byte aligned bytes, the
+// same flat [game][cell] layout as the obs / mask outputs) sit in shared memory for the whole step. The step is
 //
-//   phase_agent      thread-per-game   agent ply: validity, stone, neighbour labels, merge request, win
-//   pass_relabel     cooperative       byte-SIMD relabel of the tile's label words (request #1)
-//   phase_opponent   thread-per-game   random opponent ply (k-th empty cell, column-major), win, reward/done,
-//                                      episode accounting, auto-reset bookkeeping (+ opening stone)
-//   pass_encode      cooperative       relabel request #2 fused with obs + mask encoding and the coalesced
-//                                      global stores; rare byte-wise path for straddling words, resets,
-//                                      terminal observations and the opponent's (transposed) view
-//   phase_clear      thread-per-game   games that reset: zero their label bytes, drop the opening stone
+//   game_step        thread-per-game   agent ply + random-opponent ply (validity, stone, neighbour labels, merge request,
+//                                      win), reward / done, episode accounting, auto-reset bookkeeping. Purely thread
+//                                      local: a ply only looks at the mover's OWN labels, so the opponent's ply does not
+//                                      depend on the agent's pending relabel and both requests are applied together.
+//   row jobs         warp-per-game     for every game that asked for one (ballot): the 32 lanes sweep that game's row
+//                                      of label words once - relabel (both plies' requests in one pass), or terminal
+//                                      observation + clear + opening stone when the game restarts.
+//   encode_chunk     warp, elementwise label bytes -> obs + mask bytes, 16 bytes per lane per iteration, written straight
+//                                      to the [G,C] outputs. Encoding depends only on emptiness and the owner bit, never
+//                                      on the game index, so no per-word bookkeeping is needed.
 //
-// Between phases the kernel puts a __syncthreads(); the host emulator (tests/emu) simply runs each
-// phase for all threads before the next one.
+// The device kernel (hexb_kernels.cu) strings these together with __ballot_sync / __shfl_sync / __syncwarp; the host
+// emulator (tests/emu) runs the same functions with plain loops over lanes.
 #pragma once
 #include "hexb_core.cuh"
 
 namespace hexb {
 
+constexpr int kWarp = 32;
+constexpr int kStatStripes = 128;  // episode statistics are accumulated into [kStatStripes][8] to spread the atomics
+
 template <int N>
-struct Tile {
-    uint8_t *lab;     // [kTile*C] label bytes, 16-byte aligned
-    uint32_t *prm1;   // [kTile] relabel request of the first ply
-    uint32_t *prm2;   // [kTile] relabel request of the second ply
-    uint32_t *flg;    // [kTile] reset / view / terminal flags for pass_encode
-    long long g0;     // first game of the tile
+struct Chunk {
+    static constexpr int C = N * N;
+    static constexpr int BYTES = kWarp * C;   // multiple of 16
+    static constexpr int WORDS = BYTES / 4;
+    static constexpr int VECS = BYTES / 16;
+    static constexpr bool ALIGNED_ROWS = (C % 4) == 0;
 };
 
-// per-thread values that live from phase_agent to phase_opponent
+// per-thread values of one step
 struct Loc {
-    uint32_t f;     // bit 0 inactive (g >= G or never reset), bit 1 was done before this step
     float reward;
     int action;
-    int st[8];      // episode statistics increments (see hexb.h: hexb_stats)
+    int st[8];  // episode statistics increments (see hexb.h: hexb_stats)
 };
-constexpr uint32_t L_INACTIVE = 1u, L_WASDONE = 2u;
 
 template <int N>
 HEXB_HD void load_rec(const Params &P, long long g, Rec<N> &r) {
@@ -69,160 +72,97 @@ HEXB_HD float stale_reward_A(uint32_t meta) {
     return w == 1u ? 1.f : (w == 2u ? -1.f : 0.f);
 }
 
-// ---------------------------------------------------------------------------------------------- agent ply
-// SelfPlayEnv.step -> HexEnv.step (SelfplayWrapper.py:174-176, HexSingleGame.py:233-263) or variant-A
-// HexEnv.step (HexGame.py:244-253). With actions == null the agent is BaseRandomPolicy / random_policy
-// itself and takes one draw from the game's stream first, exactly like the reference loop
-//   a = BaseRandomPolicy().choose_action(obs); env.step(a).
+// The two draws a step normally consumes, computed up front (they only depend on the stream position) so that the
+// device can do the Philox arithmetic while the chunk's label bytes are still in flight:
+//   u_agent  BaseRandomPolicy.choose_action of the driving loop (only when actions == null)       at draws
+//   u_opp    BaseRandomPolicy.choose_action / random_policy of the opponent's reply                at draws (+1 if the agent
+//            drew) (+1 for the unused random.uniform of SelfplayWrapper.py:159 in variant B)
 template <int N>
-HEXB_HD void phase_agent(const Tile<N> &T, const Params &P, int t, Rec<N> &rec, Loc &loc) {
+HEXB_HD void pre_draws(const Params &P, const Rec<N> &rec, unsigned long long gid, double &u_agent, double &u_opp) {
+    uint32_t idx = rec.draws;
+    u_agent = 0.0;
+    u_opp = 0.0;
+    if (!(rec.meta & M_LIVE) || (rec.meta & M_DONE)) return;
+    if (!P.actions) u_agent = draw01(P.seed, gid, idx++);
+    if (!P.opp_u) u_opp = draw01(P.seed, gid, idx + (P.variant == VARIANT_B ? 1u : 0u));
+}
+
+// ---------------------------------------------------------------------------------------------- one env step of one game
+// SelfPlayEnv.step (SelfplayWrapper.py:174-199) -> HexEnv.step (HexSingleGame.py:233-263) + continue_game (:146-172), or
+// variant-A HexEnv.step (HexGame.py:244-295) + opponent_move (:332-349); then the DummyVecEnv-style auto-reset and the
+// episode counters. With actions == null the agent is BaseRandomPolicy / random_policy itself and takes one draw from the
+// game's stream first, exactly like the reference loop  a = BaseRandomPolicy().choose_action(obs); env.step(a).
+// L = this game's C label bytes. prmA / prmB = relabel requests of the two plies, flg = row job for the warp.
+template <int N>
+HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, double u_agent, double u_opp, Loc &loc, uint32_t &prmA,
+                       uint32_t &prmB, uint32_t &flg) {
     constexpr int C = Geo<N>::C;
-    loc.f = 0; loc.reward = 0.f; loc.action = -1;
+    loc.reward = 0.f;
+    loc.action = -1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) loc.st[i] = 0;
-    T.prm1[t] = 0; T.prm2[t] = 0; T.flg[t] = 0;
-    const long long g = T.g0 + t;
-    if (g >= P.G || !(rec.meta & M_LIVE)) { loc.f = L_INACTIVE; return; }
-    if (rec.meta & M_DONE) {
-        loc.f = L_WASDONE;
-        loc.reward = P.variant == VARIANT_A ? stale_reward_A(rec.meta) : 0.f;
-        return;
-    }
-    const unsigned long long gid = (unsigned long long)(P.game_offset + g);
-    int a;
-    if (P.actions) a = P.actions[g];
-    else {
-        const int n = count_empty<N>(rec.occ_rm);
-        a = select_kth_zero<N>(rec.occ_rm, choice_of(draw01(P.seed, gid, rec.draws++), n));
-    }
-    loc.action = a;
-    loc.st[6] = 1;
-    const bool valid = (unsigned)a < (unsigned)C && !test_bit<N>(rec.occ_rm, a);
-    if (!valid) {  // fast_move returns 3, state untouched; the env ends the episode (HexGame.py:252-253, HexSingleGame.py:240-241)
-        rec.meta |= M_DONE | M_INVALID | M_AGENT_ENDED;
-        loc.reward = P.variant == VARIANT_A ? -100.f : 0.f;
-        return;
-    }
-    uint32_t prm;
-    const bool won = place_stone<N>(T.lab + t * C, rec, 0, a, prm);
-    T.prm1[t] = prm;
-    rec.aux++;
-    loc.st[7]++;
-    rec.meta ^= M_TOMOVE;
-    if (won) {
-        rec.meta |= M_DONE | (1u << M_WIN_SHIFT) | M_AGENT_ENDED;
-        loc.reward = 1.f;
-    } else if (P.variant == VARIANT_B && count_empty<N>(rec.occ_rm) == 0) {
-        rec.meta |= M_DONE | M_AGENT_ENDED;  // HexSingleGame.py:117-119 (cannot happen from an empty start)
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- raw ply (hexb_ply)
-// Batched HexGame.make_move: variant A in true coordinates (HexGame.py:85-111, no done guard); variant B
-// with the action in the mover's perspective, as HexEnv.step feeds it (HexSingleGame.py:239, 98-106).
-template <int N>
-HEXB_HD void phase_ply(const Tile<N> &T, const Params &P, int t, Rec<N> &rec) {
-    constexpr int C = Geo<N>::C;
-    T.prm1[t] = 0; T.prm2[t] = 0; T.flg[t] = 0;
-    const long long g = T.g0 + t;
-    if (g >= P.G || !(rec.meta & M_LIVE)) return;
-    const int a = P.actions[g];
-    const int p = (rec.meta & M_TOMOVE) ? 1 : 0;
-    int r = 3;
-    if ((unsigned)a < (unsigned)C) {
-        const int cell = (P.variant == VARIANT_B && p) ? transpose_cell<N>(a) : a;
-        if (!test_bit<N>(rec.occ_rm, cell)) {
-            uint32_t prm;
-            const bool won = place_stone<N>(T.lab + t * C, rec, p, cell, prm);
-            T.prm1[t] = prm;
-            rec.aux++;
-            rec.meta ^= M_TOMOVE;
-            r = -1;
-            if (won) {
-                rec.meta = (rec.meta & ~M_WIN_MASK) | M_DONE | ((uint32_t)(p + 1) << M_WIN_SHIFT);
-                r = p;
-            } else if (P.variant == VARIANT_B && count_empty<N>(rec.occ_rm) == 0) {
-                rec.meta |= M_DONE;
-            }
-        }
-    }
-    if (r == 3 && P.variant == VARIANT_B) rec.meta |= M_DONE | M_INVALID;  // HexSingleGame.py:240-241
-    if (P.ret) P.ret[g] = (int8_t)r;
-}
-
-// ---------------------------------------------------------------------------------------------- relabel pass
-// regions[regions == label] = new_region_label (HexGame.py:141-142, HexSingleGame.py:152-153) for every game
-// of the tile at once: thread `tid` owns words tid, tid+kTile, ... of the tile's label bytes. A word whose four
-// cells straddle two games is handled byte by byte. Warps skip words whose games requested nothing.
-template <int N>
-HEXB_HD void pass_relabel(const Tile<N> &T, const uint32_t *prm, int tid) {
-    constexpr int C = Geo<N>::C;
-    uint32_t *lab32 = reinterpret_cast<uint32_t *>(T.lab);
-    for (int j = tid; j < Geo<N>::TILE_WORDS; j += kTile) {
-        const int byte0 = 4 * j;
-        const int gA = byte0 / C, c0 = byte0 - gA * C;
-        const bool whole = c0 + 4 <= C;
-        const uint32_t pa = prm[gA];
-        const uint32_t pb = whole ? 0u : prm[gA + 1];
-        if (!((pa | pb) & P_NEED)) continue;  // a warp whose 32 words (about one game) asked for nothing skips as a whole
-        if (whole) {
-            if (pa & P_NEED) {
-                const uint32_t x = lab32[j];
-                const uint32_t x2 = relabel_word(x, pa);
-                if (x2 != x) lab32[j] = x2;
-            }
-        } else {
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t pk = (c0 + k < C) ? pa : pb;
-                const uint32_t b = T.lab[byte0 + k];
-                const uint32_t b2 = relabel_byte(b, pk);
-                if (b2 != b) T.lab[byte0 + k] = (uint8_t)b2;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- opponent ply
-// SelfPlayEnv.continue_game (SelfplayWrapper.py:146-172) / HexEnv.opponent_move (HexGame.py:332-349) with the
-// random policy, then reward / done, DummyVecEnv-style auto-reset and the episode counters.
-template <int N>
-HEXB_HD void phase_opponent(const Tile<N> &T, const Params &P, int t, Rec<N> &rec, Loc &loc) {
-    constexpr int C = Geo<N>::C;
-    const long long g = T.g0 + t;
+    prmA = 0; prmB = 0; flg = 0;
     if (g >= P.G) return;
-    if (loc.f & L_INACTIVE) {
+    if (!(rec.meta & M_LIVE)) {  // never reset: nothing to play
         if (P.reward) P.reward[g] = 0.f;
         if (P.done) P.done[g] = 1;
         if (P.actions_out) P.actions_out[g] = -1;
         return;
     }
     const unsigned long long gid = (unsigned long long)(P.game_offset + g);
-    const bool was_done = (loc.f & L_WASDONE) != 0u;
-    if (!was_done && !(rec.meta & M_DONE)) {
-        double u;
-        if (P.opp_u) u = P.opp_u[2 * g];
+    const bool was_done = (rec.meta & M_DONE) != 0u;
+    if (was_done) {
+        loc.reward = P.variant == VARIANT_A ? stale_reward_A(rec.meta) : 0.f;
+    } else {
+        // ---- agent ply
+        int a;
+        if (P.actions) a = P.actions[g];
         else {
-            if (P.variant == VARIANT_B) rec.draws++;  // rv = random.uniform(0,1), unused (SelfplayWrapper.py:159)
-            u = draw01(P.seed, gid, rec.draws++);
+            rec.draws++;
+            a = select_kth_zero<N>(rec.occ_rm, choice_of(u_agent, count_empty<N>(rec.occ_rm)));
         }
-        const int n = count_empty<N>(rec.occ_cm);
-        const int i = select_kth_zero<N>(rec.occ_cm, choice_of(u, n));
-        const int x = i / N, y = i - x * N;
-        uint32_t prm;
-        const bool won = place_stone<N>(T.lab + t * C, rec, 1, y * N + x, prm);
-        T.prm2[t] = prm;
-        rec.aux++;
-        loc.st[7]++;
-        rec.meta ^= M_TOMOVE;
-        if (won) {
-            rec.meta |= M_DONE | (2u << M_WIN_SHIFT);
-            loc.reward = -1.f;
-        } else if (P.variant == VARIANT_B && n == 1) {
-            rec.meta |= M_DONE;
+        loc.action = a;
+        loc.st[6] = 1;
+        const bool valid = (unsigned)a < (unsigned)C && !test_bit<N>(rec.occ_rm, a);
+        if (!valid) {  // fast_move returns 3, state untouched; the env ends the episode (HexGame.py:252-253, HexSingleGame.py:240-241)
+            rec.meta |= M_DONE | M_INVALID | M_AGENT_ENDED;
+            loc.reward = P.variant == VARIANT_A ? -100.f : 0.f;
+        } else {
+            const bool won = place_stone<N>(L, rec, 0, a, prmA);
+            rec.aux++;
+            loc.st[7]++;
+            rec.meta ^= M_TOMOVE;
+            if (won) {
+                rec.meta |= M_DONE | (1u << M_WIN_SHIFT) | M_AGENT_ENDED;
+                loc.reward = 1.f;
+            } else if (P.variant == VARIANT_B && count_empty<N>(rec.occ_rm) == 0) {
+                rec.meta |= M_DONE | M_AGENT_ENDED;  // HexSingleGame.py:117-119 (cannot happen from an empty start)
+            }
+        }
+        // ---- opponent ply: continue_game (SelfplayWrapper.py:146-172) / opponent_move (HexGame.py:332-349), random policy
+        if (!(rec.meta & M_DONE)) {
+            double u;
+            if (P.opp_u) u = P.opp_u[2 * g];
+            else {
+                rec.draws += (P.variant == VARIANT_B) ? 2u : 1u;  // variant B: rv = random.uniform(0,1), unused (:159), then the choice
+                u = u_opp;
+            }
+            const int n = count_empty<N>(rec.occ_cm);
+            const int i = select_kth_zero<N>(rec.occ_cm, choice_of(u, n));  // k-th empty cell of the opponent's view = stored column-major
+            const int x = i / N, y = i - x * N;
+            const bool won = place_stone<N>(L, rec, 1, y * N + x, prmB);
+            rec.aux++;
+            loc.st[7]++;
+            rec.meta ^= M_TOMOVE;
+            if (won) {
+                rec.meta |= M_DONE | (2u << M_WIN_SHIFT);
+                loc.reward = -1.f;
+            } else if (P.variant == VARIANT_B && n == 1) {
+                rec.meta |= M_DONE;
+            }
         }
     }
     const bool is_done = (rec.meta & M_DONE) != 0u;
-    uint32_t flg = 0;
     if (is_done && !was_done) {  // episode accounting (true colours)
         const uint32_t w = (rec.meta & M_WIN_MASK) >> M_WIN_SHIFT;
         const bool tr = (rec.meta & M_TRANSPOSED) != 0u;
@@ -241,114 +181,167 @@ HEXB_HD void phase_opponent(const Tile<N> &T, const Params &P, int t, Rec<N> &re
         if (P.auto_reset) {
             reset_game<N>(rec, P, gid, P.opp_u ? &P.opp_u[2 * g + 1] : nullptr, flg);
             if (flg & F_OPEN) loc.st[7]++;  // the opponent's opening stone is a ply of this step
+        } else if ((rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B) {
+            flg |= F_VIEW_OPP;
         }
-        else if ((rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B) flg |= F_VIEW_OPP;
     }
-    T.flg[t] = flg;
+    if (!(flg & F_RESET) && ((prmA | prmB) & P_NEED)) flg |= F_RELABEL;
+}
+
+// ---------------------------------------------------------------------------------------------- raw ply (hexb_ply)
+// Batched HexGame.make_move: variant A in true coordinates (HexGame.py:85-111, no done guard); variant B with the action
+// in the mover's perspective, as HexEnv.step feeds it (HexSingleGame.py:239, 98-106).
+template <int N>
+HEXB_HD void game_ply(uint8_t *L, const Params &P, long long g, Rec<N> &rec, uint32_t &prmA, uint32_t &flg) {
+    constexpr int C = Geo<N>::C;
+    prmA = 0; flg = 0;
+    if (g >= P.G || !(rec.meta & M_LIVE)) return;
+    const int a = P.actions[g];
+    const int p = (rec.meta & M_TOMOVE) ? 1 : 0;
+    int r = 3;
+    if ((unsigned)a < (unsigned)C) {
+        const int cell = (P.variant == VARIANT_B && p) ? transpose_cell<N>(a) : a;
+        if (!test_bit<N>(rec.occ_rm, cell)) {
+            const bool won = place_stone<N>(L, rec, p, cell, prmA);
+            rec.aux++;
+            rec.meta ^= M_TOMOVE;
+            r = -1;
+            if (won) {
+                rec.meta = (rec.meta & ~M_WIN_MASK) | M_DONE | ((uint32_t)(p + 1) << M_WIN_SHIFT);
+                r = p;
+            } else if (P.variant == VARIANT_B && count_empty<N>(rec.occ_rm) == 0) {
+                rec.meta |= M_DONE;
+            }
+        }
+    }
+    if (r == 3 && P.variant == VARIANT_B) rec.meta |= M_DONE | M_INVALID;  // HexSingleGame.py:240-241
+    if (P.ret) P.ret[g] = (int8_t)r;
+    if (prmA & P_NEED) flg |= F_RELABEL;
 }
 
 // ---------------------------------------------------------------------------------------------- reset (hexb_reset)
 template <int N>
-HEXB_HD void phase_reset(const Tile<N> &T, const Params &P, int t, Rec<N> &rec) {
-    T.prm1[t] = 0; T.prm2[t] = 0;
-    uint32_t flg = 0;
-    const long long g = T.g0 + t;
-    if (g < P.G) {
-        if (!P.reset_mask || P.reset_mask[g]) {
-            reset_game<N>(rec, P, (unsigned long long)(P.game_offset + g), P.open_u ? &P.open_u[g] : nullptr, flg);
-        } else if ((rec.meta & M_DONE) && (rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B && !P.raw) {
-            flg |= F_VIEW_OPP;
-        }
-    }
-    T.flg[t] = flg;
-}
-
-// ---------------------------------------------------------------------------------------------- encode pass
-HEXB_HD void store_out_word(uint8_t *base, long long off, long long limit, uint32_t w) {
-    if (off + 4 <= limit) *reinterpret_cast<uint32_t *>(base + off) = w;
-    else
-        for (int k = 0; k < 4; ++k)
-            if (off + k < limit) base[off + k] = (uint8_t)(w >> (8 * k));
-}
-
-// get_action_mask (HexGame.py:203-204) / legal_actions (HexSingleGame.py:205-206) and the observation the env
-// returns (the live simulator.board: HexGame.py:294, HexSingleGame.py:262 after invert_board :265-271), for all
-// games of the tile, 4 cells per thread per iteration, written straight to global memory in [G,C] order.
-template <int N>
-HEXB_HD void pass_encode(const Tile<N> &T, const Params &P, int tid) {
-    constexpr int C = Geo<N>::C;
-    uint32_t *lab32 = reinterpret_cast<uint32_t *>(T.lab);
-    const long long out0 = T.g0 * C;          // byte offset of the tile in obs / mask / term_obs
-    const long long limit = P.G * C;          // bytes that exist in the caller's buffers
-    for (int j = tid; j < Geo<N>::TILE_WORDS; j += kTile) {
-        const int byte0 = 4 * j;
-        const int gA = byte0 / C, c0 = byte0 - gA * C;
-        const bool whole = c0 + 4 <= C;
-        const uint32_t fa = T.flg[gA];
-        uint32_t obsw, mskw;
-        if (whole && fa == 0u) {  // common case: one game, no reset, agent's view
-            const uint32_t pa = T.prm2[gA];
-            uint32_t x = lab32[j];
-            if (pa & P_NEED) {
-                const uint32_t x2 = relabel_word(x, pa);
-                if (x2 != x) lab32[j] = x2;
-                x = x2;
-            }
-            encode_word(x, P.variant, obsw, mskw);
-        } else {
-            obsw = 0; mskw = 0;
-            for (int k = 0; k < 4; ++k) {
-                int gg = gA, cc = c0 + k;
-                if (cc >= C) { gg += 1; cc -= C; }
-                const uint32_t pk = T.prm2[gg], fk = T.flg[gg];
-                const uint8_t *Lg = T.lab + gg * C;
-                const uint32_t b = Lg[cc];
-                const uint32_t b2 = relabel_byte(b, pk);
-                if (b2 != b) T.lab[byte0 + k] = (uint8_t)b2;
-                const int ct = transpose_cell<N>(cc);
-                uint32_t mk, ob;
-                if (fk & F_TERM) {  // info["terminal_observation"]: what step() itself returned
-                    uint32_t tmk;
-                    const uint32_t tb = (fk & F_TERM_OPP) ? encode_byte(relabel_byte(Lg[ct], pk), P.variant, true, tmk)
-                                                          : encode_byte(b2, P.variant, false, tmk);
-                    const long long o = out0 + byte0 + k;
-                    if (o < limit) P.term_obs[o] = (int8_t)tb;
-                }
-                if (fk & F_RESET) {
-                    const uint32_t bo = ((fk & F_OPEN) && (uint32_t)cc == (fk >> 16)) ? ((fk >> 8) & 0xffu) : 0u;
-                    ob = encode_byte(bo, P.variant, false, mk);
-                } else if (fk & F_VIEW_OPP) {
-                    ob = encode_byte(relabel_byte(Lg[ct], pk), P.variant, true, mk);
-                } else {
-                    ob = encode_byte(b2, P.variant, false, mk);
-                }
-                obsw |= ob << (8 * k);
-                mskw |= mk << (8 * k);
-            }
-        }
-        if (P.obs) store_out_word(reinterpret_cast<uint8_t *>(P.obs), out0 + byte0, limit, obsw);
-        if (P.mask) store_out_word(P.mask, out0 + byte0, limit, mskw);
+HEXB_HD void game_reset(const Params &P, long long g, Rec<N> &rec, uint32_t &flg) {
+    flg = 0;
+    if (g >= P.G) return;
+    if (!P.reset_mask || P.reset_mask[g]) {
+        reset_game<N>(rec, P, (unsigned long long)(P.game_offset + g), P.open_u ? &P.open_u[g] : nullptr, flg);
+    } else if ((rec.meta & M_DONE) && (rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B && !P.raw) {
+        flg |= F_VIEW_OPP;
     }
 }
 
-// ---------------------------------------------------------------------------------------------- clear
-// Games that reset get an empty board (HexSingleGame.py:208-231 / HexGame.py:206-220) plus the opponent's
-// opening stone when it moves first. Head and tail of the game's byte range are not word aligned, so they
-// are cleared byte-wise (neighbouring games own the other bytes of those words).
+// ---------------------------------------------------------------------------------------------- row jobs (one lane's share)
+// Row r of the chunk = bytes [r*C, (r+1)*C) = words (r*C)>>2 .. ((r+1)*C-1)>>2. For odd N a row is not word aligned and its
+// first / last word also holds cells of the neighbouring games: row_mask() keeps a lane's read-modify-write inside the row.
+// Rows are processed one at a time by the whole warp, so neighbouring rows are never updated concurrently.
 template <int N>
-HEXB_HD void phase_clear(const Tile<N> &T, int t) {
+HEXB_HD uint32_t row_mask(int row_start, int row_end, int w) {
+    if (Chunk<N>::ALIGNED_ROWS) return 0xffffffffu;
+    const int lo = row_start - 4 * w;  // bytes below lo belong to the previous game
+    const int hi = row_end - 4 * w;    // bytes from hi on belong to the next game
+    uint32_t m = 0xffffffffu;
+    if (lo > 0) m &= 0xffffffffu << (8 * lo);
+    if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
+    return m;
+}
+
+// 0x80 in every byte of y that is zero
+HEXB_HD uint32_t zero_flags(uint32_t y) { return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u; }
+
+// regions[regions == label] = new_region_label (HexGame.py:141-142, HexSingleGame.py:152-153) for both plies of the step
+// in one sweep. The two requests touch disjoint byte values (the owner bit is part of the byte), so their order is free.
+// A request of 0 (nothing to do) degenerates to "replace empty by empty".
+template <int N>
+HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t prmB, int lane) {
     constexpr int C = Geo<N>::C;
-    const uint32_t f = T.flg[t];
-    if (!(f & F_RESET)) return;
-    int b = t * C;
-    const int e = b + C;
-    while ((b & 3) && b < e) T.lab[b++] = 0;
-    uint32_t *w = reinterpret_cast<uint32_t *>(T.lab + b);
-    const int nw = (e - b) >> 2;
-    for (int i = 0; i < nw; ++i) w[i] = 0u;
-    b += 4 * nw;
-    while (b < e) T.lab[b++] = 0;
-    if (f & F_OPEN) T.lab[t * C + (int)(f >> 16)] = (uint8_t)((f >> 8) & 0xffu);
+    const int rs = r * C, re = rs + C;
+    const uint32_t a1 = splat(prmA & 0xffu), a2 = splat((prmA >> 8) & 0xffu), am = splat((prmA >> 16) & 0xffu);
+    const uint32_t b1 = splat(prmB & 0xffu), b2 = splat((prmB >> 8) & 0xffu), bm = splat((prmB >> 16) & 0xffu);
+    for (int w = (rs >> 2) + lane; w <= ((re - 1) >> 2); w += kWarp) {
+        const uint32_t x = lab32[w];
+        const uint32_t rm = row_mask<N>(rs, re, w);
+        const uint32_t ma = (((zero_flags(x ^ a1) | zero_flags(x ^ a2)) >> 7) * 0xffu) & rm;
+        const uint32_t mb = (((zero_flags(x ^ b1) | zero_flags(x ^ b2)) >> 7) * 0xffu) & rm;
+        const uint32_t x2 = (x & ~(ma | mb)) | (am & ma) | (bm & mb);
+        if (x2 != x) lab32[w] = x2;
+    }
+}
+
+// Games that restart get an empty board (HexSingleGame.py:208-231 / HexGame.py:206-220) plus the opponent's opening stone
+// when it moves first (flg bits 8-15 = its byte, 16-31 = its cell).
+template <int N>
+HEXB_HD void clear_row_lane(uint32_t *lab32, int r, uint32_t flg, int lane) {
+    constexpr int C = Geo<N>::C;
+    const int rs = r * C, re = rs + C;
+    const int ob = rs + (int)(flg >> 16);  // chunk byte of the opening stone
+    for (int w = (rs >> 2) + lane; w <= ((re - 1) >> 2); w += kWarp) {
+        const uint32_t rm = row_mask<N>(rs, re, w);
+        uint32_t x = Chunk<N>::ALIGNED_ROWS ? 0u : (lab32[w] & ~rm);
+        if ((flg & F_OPEN) && (ob >> 2) == w) x |= ((flg >> 8) & 0xffu) << (8 * (ob & 3));
+        lab32[w] = x;
+    }
+}
+
+// info["terminal_observation"] of a game that finished in this step: what step() itself returned, i.e. the opponent's view
+// (transposed, signs swapped) when the agent's own ply ended the game (HexSingleGame.py:259-262), else the agent's view.
+template <int N>
+HEXB_HD void term_row_lane(const uint8_t *chunk, int r, uint32_t flg, const Params &P, long long g, int lane) {
+    constexpr int C = Geo<N>::C;
+    const uint8_t *Lg = chunk + r * C;
+    const bool opp = (flg & F_TERM_OPP) != 0u;
+    for (int c = lane; c < C; c += kWarp) {
+        uint32_t mk;
+        const uint32_t b = Lg[opp ? transpose_cell<N>(c) : c];
+        P.term_obs[g * C + c] = (int8_t)encode_byte(b, P.variant, opp, mk);
+    }
+}
+
+// obs + mask of a finished, not restarted game whose last ply was the agent's: the opponent's view (see term_row_lane).
+template <int N>
+HEXB_HD void view_row_lane(const uint8_t *chunk, int r, const Params &P, long long g, int lane) {
+    constexpr int C = Geo<N>::C;
+    const uint8_t *Lg = chunk + r * C;
+    for (int c = lane; c < C; c += kWarp) {
+        uint32_t mk;
+        const uint32_t ob = encode_byte(Lg[transpose_cell<N>(c)], P.variant, true, mk);
+        if (P.obs) P.obs[g * C + c] = (int8_t)ob;
+        if (P.mask) P.mask[g * C + c] = (uint8_t)mk;
+    }
+}
+
+// one row job, one lane's share. Order: terminal observation (reads the finished board) -> clear (+ opening stone);
+// the caller separates the two with a warp barrier (`sync`), because different lanes read and write the same words.
+template <int N, class SyncFn>
+HEXB_HD void row_job_lane(uint8_t *chunk, int r, uint32_t prmA, uint32_t prmB, uint32_t flg, const Params &P, long long g, int lane,
+                          SyncFn sync) {
+    uint32_t *lab32 = reinterpret_cast<uint32_t *>(chunk);
+    if (flg & F_TERM) {
+        term_row_lane<N>(chunk, r, flg, P, g, lane);
+        sync();
+    }
+    if (flg & F_RESET) clear_row_lane<N>(lab32, r, flg, lane);
+    else if (flg & F_RELABEL) relabel_row_lane<N>(lab32, r, prmA, prmB, lane);
+}
+
+// ---------------------------------------------------------------------------------------------- encode (one lane's share)
+// get_action_mask (HexGame.py:203-204) / legal_actions (HexSingleGame.py:205-206) and the observation the env returns (the
+// live simulator.board: HexGame.py:294, HexSingleGame.py:262 after invert_board :265-271) in the agent's view = the stored
+// orientation, for the whole chunk, elementwise: output byte i of the chunk depends on label byte i only.
+struct Vec4 {
+    uint32_t x, y, z, w;
+};
+HEXB_HD void store_tail(uint8_t *base, long long off, long long limit, const Vec4 &v) {
+    const uint32_t a[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < 16; ++k)
+        if (off + k < limit) base[off + k] = (uint8_t)(a[k >> 2] >> (8 * (k & 3)));
+}
+template <int N>
+HEXB_HD void encode_vec(const Vec4 &in, int variant, Vec4 &o, Vec4 &m) {
+    encode_word(in.x, variant, o.x, m.x);
+    encode_word(in.y, variant, o.y, m.y);
+    encode_word(in.z, variant, o.z, m.z);
+    encode_word(in.w, variant, o.w, m.w);
 }
 
 }  // namespace hexb

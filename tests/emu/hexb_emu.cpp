@@ -27,38 +27,53 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 template <int N>
 static void run_tiles(Params P) {
     constexpr int C = Geo<N>::C;
-    std::vector<uint8_t> smem(Geo<N>::TILE_BYTES);
-    std::vector<uint32_t> prm1(kTile), prm2(kTile), flg(kTile);
-    std::vector<Rec<N>> recs(kTile);
-    std::vector<Loc> locs(kTile);
-    for (long long g0 = 0; g0 < P.Gpad; g0 += kTile) {
-        Tile<N> T;
-        T.lab = smem.data();
-        T.prm1 = prm1.data();
-        T.prm2 = prm2.data();
-        T.flg = flg.data();
-        T.g0 = g0;
-        memcpy(T.lab, P.labels + g0 * C, Geo<N>::TILE_BYTES);
-        for (int t = 0; t < kTile; ++t) load_rec<N>(P, g0 + t, recs[t]);
-        if (P.mode == MODE_STEP) {
-            for (int t = 0; t < kTile; ++t) phase_agent<N>(T, P, t, recs[t], locs[t]);
-            for (int t = 0; t < kTile; ++t) pass_relabel<N>(T, T.prm1, t);
-            for (int t = 0; t < kTile; ++t) phase_opponent<N>(T, P, t, recs[t], locs[t]);
-            for (int t = 0; t < kTile; ++t)
-                for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
-            for (int t = 0; t < kTile; ++t) pass_encode<N>(T, P, t);
-            for (int t = 0; t < kTile; ++t) phase_clear<N>(T, t);
-        } else if (P.mode == MODE_RESET) {
-            for (int t = 0; t < kTile; ++t) phase_reset<N>(T, P, t, recs[t]);
-            for (int t = 0; t < kTile; ++t) pass_encode<N>(T, P, t);
-            for (int t = 0; t < kTile; ++t) phase_clear<N>(T, t);
-        } else {
-            for (int t = 0; t < kTile; ++t) phase_ply<N>(T, P, t, recs[t]);
-            for (int t = 0; t < kTile; ++t) pass_relabel<N>(T, T.prm1, t);
+    std::vector<uint8_t> smem(Chunk<N>::BYTES + 16);
+    uint8_t *chunk = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
+    std::vector<Rec<N>> recs(kWarp);
+    std::vector<Loc> locs(kWarp);
+    uint32_t prmA[kWarp], prmB[kWarp], flg[kWarp];
+    for (long long g0 = 0; g0 < P.Gpad; g0 += kWarp) {   // one "warp" = one chunk of 32 games at a time
+        memcpy(chunk, P.labels + g0 * C, Chunk<N>::BYTES);
+        for (int t = 0; t < kWarp; ++t) {
+            load_rec<N>(P, g0 + t, recs[t]);
+            prmA[t] = prmB[t] = flg[t] = 0;
         }
-        for (int t = 0; t < kTile; ++t)
-            if (g0 + t < P.G) store_rec<N>(P, g0 + t, recs[t]);
-        memcpy(P.labels + g0 * C, T.lab, Geo<N>::TILE_BYTES);
+        for (int t = 0; t < kWarp; ++t) {   // thread-per-game phase
+            const long long g = g0 + t;
+            uint8_t *L = chunk + t * C;
+            if (P.mode == MODE_STEP) {
+                double ua = 0.0, uo = 0.0;
+                if (g < P.G) pre_draws<N>(P, recs[t], (unsigned long long)(P.game_offset + g), ua, uo);
+                game_step<N>(L, P, g, recs[t], ua, uo, locs[t], prmA[t], prmB[t], flg[t]);
+                for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
+            } else if (P.mode == MODE_RESET) {
+                game_reset<N>(P, g, recs[t], flg[t]);
+            } else {
+                game_ply<N>(L, P, g, recs[t], prmA[t], flg[t]);
+            }
+            if (g < P.G) store_rec<N>(P, g, recs[t]);
+        }
+        for (int r = 0; r < kWarp; ++r) {   // warp-per-game row jobs; a lane-level barrier = finish the loop over lanes
+            if (!(flg[r] & F_ROWJOB)) continue;
+            if (flg[r] & F_TERM)
+                for (int lane = 0; lane < kWarp; ++lane) term_row_lane<N>(chunk, r, flg[r], P, g0 + r, lane);
+            for (int lane = 0; lane < kWarp; ++lane)
+                row_job_lane<N>(chunk, r, prmA[r], prmB[r], flg[r] & ~F_TERM, P, g0 + r, lane, [] {});
+        }
+        if (P.mode != MODE_PLY && (P.obs || P.mask)) {   // elementwise encode, then the rare opponent-view rows
+            const long long out0 = g0 * C, limit = P.G * C;
+            for (int i = 0; i < Chunk<N>::VECS; ++i) {
+                Vec4 in, o, m;
+                memcpy(&in, chunk + 16 * i, 16);
+                encode_vec<N>(in, P.variant, o, m);
+                if (P.obs) store_tail(reinterpret_cast<uint8_t *>(P.obs), out0 + 16ll * i, limit, o);
+                if (P.mask) store_tail(P.mask, out0 + 16ll * i, limit, m);
+            }
+            for (int r = 0; r < kWarp; ++r)
+                if (flg[r] & F_VIEW_OPP)
+                    for (int lane = 0; lane < kWarp; ++lane) view_row_lane<N>(chunk, r, P, g0 + r, lane);
+        }
+        memcpy(P.labels + g0 * C, chunk, Chunk<N>::BYTES);
     }
 }
 
