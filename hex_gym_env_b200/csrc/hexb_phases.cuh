@@ -214,7 +214,6 @@ HEXB_HD void game_ply(uint8_t *L, const Params &P, long long g, Rec<N> &rec, uin
             }
         }
     }
-    if (r == 3 && P.variant == VARIANT_B) rec.meta |= M_DONE | M_INVALID;  // HexSingleGame.py:240-241
     if (P.ret) P.ret[g] = (int8_t)r;
     if (prmA & P_NEED) flg |= F_RELABEL;
 }
