@@ -1,0 +1,156 @@
+"""HexVecEnv - G games as ONE vectorised environment, shaped like a stable-baselines3 `VecEnv`.
+
+This is what replaces `DummyVecEnv([lambda: ActionMasker(SelfPlayEnv(...), mask_fn)])` of the reference training scripts
+(scripts/experiments/*.py:34-47) when the rollout is collected from many games at once: one fused kernel launch per
+`step()` for all games instead of one Python env per process.
+
+SB3 surface mirrored (stable-baselines3 2.2.1 / sb3-contrib, from memory - SB3 is not installed in the build image, so
+this contract is duck-typed; if gymnasium / SB3 are importable the spaces are real gymnasium spaces):
+  num_envs, observation_space, action_space
+  reset() -> obs[G,N,N]
+  step_async(actions); step_wait() -> (obs, rewards, dones, infos);  step(actions)
+  auto-reset on done, with infos[i]["terminal_observation"] for the finished games
+  env_method("action_masks") / action_masks() -> bool[G,C]      (what sb3_contrib's get_action_masks() calls)
+  get_attr / set_attr / env_is_wrapped / seed / close
+
+`output="numpy"` (default, what SB3 expects) copies results to host arrays; `output="torch"` returns device tensors and
+never touches the host (use it when the policy lives on the same GPU; `infos` is then a lazy object, not a list).
+"""
+import numpy as np
+import torch
+
+from .batch import AGENT_BLACK, AGENT_RANDOM, AGENT_WHITE, VARIANT_A, VARIANT_B, HexBatch
+from .minihex_compat import _spaces
+
+
+class _LazyInfos(object):
+    """List-of-dicts view over the step's device results, materialised only for the indices that are read."""
+
+    def __init__(self, done, term_obs, n):
+        self._done, self._term, self._n = done, term_obs, n
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if bool(self._done[i]):
+            t = self._term[i]
+            return {"terminal_observation": t if isinstance(t, np.ndarray) else t.clone(), "TimeLimit.truncated": False}
+        return {}
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+
+class HexVecEnv(object):
+    def __init__(self, board_size=5, num_envs=1024, variant="selfplay", agent_player_num=None, opponent_first=False,
+                 seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0):
+        if variant in ("selfplay", "B", VARIANT_B):
+            v = VARIANT_B
+            agent_mode = AGENT_RANDOM if agent_player_num is None else (AGENT_WHITE if int(agent_player_num) else AGENT_BLACK)
+            low, high = -1, 1
+        elif variant in ("hex-v0", "A", VARIANT_A):
+            v, agent_mode, low, high = VARIANT_A, AGENT_BLACK, 0, 2
+        else:
+            raise ValueError("variant must be 'selfplay' (SelfPlayEnv, variant B) or 'hex-v0' (HexEnv, variant A)")
+        if output not in ("numpy", "torch"):
+            raise ValueError("output must be 'numpy' or 'torch'")
+        self.num_envs, self.board_size, self.output = int(num_envs), int(board_size), output
+        self.batch = HexBatch(board_size, num_envs, variant=v, device=device, seed=seed, game_offset=game_offset,
+                              agent_mode=agent_mode, opponent_first=opponent_first, auto_reset=True)
+        self.device = self.batch.device
+        self.obs_dtype = obs_dtype or (np.float32 if output == "numpy" else torch.float32)
+        self.observation_space = _spaces.Box(low=low, high=high, shape=(board_size, board_size),
+                                             dtype=np.int64 if v == VARIANT_B else np.uint8)
+        self.action_space = _spaces.Discrete(board_size ** 2)
+        self.render_mode = None
+        self._actions = None
+        self._mask = None
+        self._pinned = None
+
+    # ------------------------------------------------------------------ helpers
+    def _host(self, name, t):
+        """Device tensor -> numpy through a reusable pinned staging buffer."""
+        if self._pinned is None:
+            self._pinned = {}
+        p = self._pinned.get(name)
+        if p is None or p.shape != t.shape or p.dtype != t.dtype:
+            p = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._pinned[name] = p
+        p.copy_(t, non_blocking=True)
+        return p
+
+    def _obs_out(self, obs):
+        if self.output == "torch":
+            return obs.to(self.obs_dtype)
+        h = self._host("obs", obs)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h.numpy().astype(self.obs_dtype)
+
+    # ------------------------------------------------------------------ VecEnv API
+    def reset(self):
+        obs, mask = self.batch.reset()
+        self._mask = mask
+        return self._obs_out(obs)
+
+    def step_async(self, actions):
+        if isinstance(actions, np.ndarray):
+            actions = torch.from_numpy(np.ascontiguousarray(actions.astype(np.int32, copy=False)))
+        self._actions = actions
+
+    def step_wait(self):
+        o = self.batch.step(self._actions, want_term=True)
+        self._mask = o["mask"]
+        if self.output == "torch":
+            infos = _LazyInfos(o["done"], o["term_obs"], self.num_envs)
+            return o["obs"].to(self.obs_dtype), o["reward"], o["done"].bool(), infos
+        h = {k: self._host(k, o[k]) for k in ("obs", "reward", "done", "term_obs")}
+        torch.cuda.current_stream(self.device).synchronize()
+        done = h["done"].numpy().astype(bool)
+        term = h["term_obs"].numpy()
+        infos = [{} for _ in range(self.num_envs)]
+        for i in np.flatnonzero(done):
+            infos[i] = {"terminal_observation": term[i].astype(self.obs_dtype), "TimeLimit.truncated": False}
+        return h["obs"].numpy().astype(self.obs_dtype), h["reward"].numpy().copy(), done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def action_masks(self):
+        """bool[G,C] legal-action masks of the current observations (HexEnv.legal_actions / get_action_mask)."""
+        if self._mask is None:
+            _, self._mask = self.batch.encode(0)
+        if self.output == "torch":
+            return self._mask.bool()
+        h = self._host("mask", self._mask)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h.numpy().astype(bool)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        if method_name in ("action_masks", "legal_actions", "get_action_mask"):
+            m = self.action_masks()
+            idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+            return [m[i] for i in idx]
+        raise AttributeError("HexVecEnv has no per-env method %r" % (method_name,))
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else (1 if isinstance(indices, int) else len(indices))
+        return [getattr(self, attr_name)] * n
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self, attr_name, value)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else (1 if isinstance(indices, int) else len(indices))
+        return [False] * n
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs  # like the reference, which accepts and ignores reset(seed=...)
+
+    def episode_stats(self):
+        from .batch import STAT_NAMES
+        return dict(zip(STAT_NAMES, self.batch.stats().cpu().tolist()))
+
+    def close(self):
+        self.batch.close()
