@@ -37,11 +37,11 @@ def contract_bytes(N):
 
 
 def moved_bytes(N, sampled=True):
-    """Bytes this implementation really moves per env-step per game: packed state in + out (C label bytes + (2W+3) u32
+    """Bytes this implementation really moves per env-step per game: packed state in + out (C label bytes + (2W+2) u32
     record words), obs + mask + reward + done out (+ actions in when the agent is external)."""
     C = N * N
     W = (C + 31) // 32
-    S = C + 4 * (2 * W + 3)
+    S = C + 4 * (2 * W + 2)
     return 2 * S + 2 * C + 5 + (0 if sampled else 4)
 
 

@@ -73,7 +73,7 @@ template <int N>
 struct Geo {
     static constexpr int C = N * N;
     static constexpr int W = (C + 31) / 32;      // bitboard words
-    static constexpr int R = 2 * W + 3;          // record words: occ_rm[W], occ_cm[W], meta, draws, aux
+    static constexpr int R = 2 * W + 2;          // record words: occ_rm[W], occ_cm[W], meta, draws
     static constexpr int TILE_BYTES = kTile * C;  // label bytes per tile (multiple of 16)
     static constexpr int TILE_WORDS = TILE_BYTES / 4;
     static constexpr uint32_t LAST_MASK = (C % 32) ? ((1u << (C % 32)) - 1u) : 0xffffffffu;
@@ -83,7 +83,7 @@ template <int N>
 struct Rec {
     uint32_t occ_rm[Geo<N>::W];
     uint32_t occ_cm[Geo<N>::W];
-    uint32_t meta, draws, aux;  // aux: bits 0-15 plies in the running episode
+    uint32_t meta, draws;  // (plies of the running episode = stones on the board = popcount of the occupancy)
 };
 
 struct Params {
@@ -296,12 +296,22 @@ HEXB_HD uint32_t relabel_byte(uint32_t b, uint32_t prm) {
 // observation / mask bytes in the STORED orientation (the agent's view)
 //   variant B (HexSingleGame.py:15-19, 265-271): own -1, opponent +1, empty 0; own = R
 //   variant A (HexGame.py:10-13): BLACK 0 (= R, the agent), WHITE 1, EMPTY 2
+// 0xff in every byte of f whose top bit is set (PRMT with the sign-replicate selector bit on the device)
+HEXB_HD uint32_t sign_fill(uint32_t f) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(f), "r"(0u), "r"(0xba98u));  // selector bit 3 = replicate the byte's msb
+    return d;
+#else
+    return ((f >> 7) & 0x01010101u) * 0xffu;
+#endif
+}
 HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) {
-    const uint32_t nz1 = nz_flags(x) >> 7;            // 0x01 per stone
-    const uint32_t c1 = (x >> 7) & 0x01010101u;       // 0x01 per C stone
-    msk = nz1 ^ 0x01010101u;                          // legal == empty
-    if (variant == VARIANT_B) obs = ((nz1 & ~c1) * 0xffu) | c1;
-    else obs = c1 | (msk << 1);
+    const uint32_t n = nz_flags(x);                   // 0x80 per stone
+    const uint32_t c = x & 0x80808080u;               // 0x80 per C stone
+    msk = (n >> 7) ^ 0x01010101u;                     // legal == empty
+    if (variant == VARIANT_B) obs = sign_fill(n ^ c) | (c >> 7);
+    else obs = (c >> 7) | (msk << 1);
 }
 // one byte, optionally seen from the opponent's side (sign swap; the caller transposes the cell index)
 HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &msk) {
@@ -325,7 +335,6 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
     meta |= M_LIVE | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
 #pragma unroll
     for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
-    rec.aux = 0;
     bool opp_opens;
     if (P.raw) {
         opp_opens = false;
@@ -358,7 +367,6 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
         else { lab = 3u; meta += 1u << M_CTR_C_SHIFT; }
         set_bit<N>(rec.occ_rm, y * N + x);
         set_bit<N>(rec.occ_cm, k);
-        rec.aux = 1;
         flg |= F_OPEN | ((lab | 0x80u) << 8) | ((uint32_t)(y * N + x) << 16);
     }
     rec.meta = meta;  // R (the agent) to move

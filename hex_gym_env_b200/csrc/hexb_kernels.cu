@@ -63,6 +63,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 //   warp-per-game row jobs, the elementwise obs/mask encode with 16-byte coalesced stores, the record stores and one
 //   bulk copy of the chunk back to global memory.
 constexpr int kWarpsPerCta = kTile / kWarp;
+// resident CTAs per SM the register allocation should allow: 12 (48 warps) while the record is small, else whatever the
+// shared-memory footprint of the four chunks permits anyway
+constexpr int min_ctas(int n) {
+    const int smem = kWarpsPerCta * kWarp * n * n + 64;
+    const int by_smem = 220 * 1024 / smem;
+    return n <= 12 ? 12 : (by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem));
+}
 
 template <int N>
 struct SmemLayout {
@@ -78,8 +85,21 @@ __device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params 
     const long long limit = P.G * C;      // bytes that exist in the caller's buffers
     const uint4 *src = reinterpret_cast<const uint4 *>(chunk);
     uint8_t *obs = reinterpret_cast<uint8_t *>(P.obs);
-    const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)P.mask)) & 15) == 0;
-#pragma unroll 2
+    uint8_t *msk = P.mask;
+    const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)msk)) & 15) == 0;
+    if (vec_ok && obs && msk && out0 + Chunk<N>::BYTES <= limit) {
+        // the common case (warp-uniform): whole chunk inside the buffers, both outputs wanted, 16-byte aligned
+        uint4 *po = reinterpret_cast<uint4 *>(obs + out0), *pm = reinterpret_cast<uint4 *>(msk + out0);
+#pragma unroll 4
+        for (int i = lane; i < Chunk<N>::VECS; i += kWarp) {
+            const uint4 x = src[i];
+            Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
+            encode_vec<N>(in, P.variant, o, m);
+            __stcs(po + i, make_uint4(o.x, o.y, o.z, o.w));
+            __stcs(pm + i, make_uint4(m.x, m.y, m.z, m.w));
+        }
+        return;
+    }
     for (int i = lane; i < Chunk<N>::VECS; i += kWarp) {
         const uint4 x = src[i];
         Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
@@ -87,16 +107,16 @@ __device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params 
         const long long off = out0 + 16ll * i;
         if (vec_ok && off + 16 <= limit) {
             if (obs) __stcs(reinterpret_cast<uint4 *>(obs + off), make_uint4(o.x, o.y, o.z, o.w));
-            if (P.mask) __stcs(reinterpret_cast<uint4 *>(P.mask + off), make_uint4(m.x, m.y, m.z, m.w));
+            if (msk) __stcs(reinterpret_cast<uint4 *>(msk + off), make_uint4(m.x, m.y, m.z, m.w));
         } else {
             if (obs) store_tail(obs, off, limit, o);
-            if (P.mask) store_tail(P.mask, off, limit, m);
+            if (msk) store_tail(msk, off, limit, m);
         }
     }
 }
 
 template <int N>
-__global__ void __launch_bounds__(kTile) hexb_step_kernel(const Params P) {
+__global__ void __launch_bounds__(kTile, min_ctas(N)) hexb_step_kernel(const Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using SL = SmemLayout<N>;
     constexpr int C = Geo<N>::C;
@@ -128,12 +148,24 @@ __global__ void __launch_bounds__(kTile) hexb_step_kernel(const Params P) {
     if (P.mode == MODE_STEP) {
         Loc loc;
         game_step<N>(L, P, g, rec, u_agent, u_opp, loc, prmA, prmB, flg);
-        // K7: episode statistics - warp reduction, then one atomic per non-zero counter into this warp's stripe
-        unsigned long long *stripe = reinterpret_cast<unsigned long long *>(P.stats) + 8 * (wglobal & (kStatStripes - 1));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int v = __reduce_add_sync(FULL, loc.st[i]);
-            if (lane == 0 && v) atomicAdd(stripe + i, (unsigned long long)v);
+        // K7: episode statistics - the eight per-game increments are packed into two words (fields wide enough for the
+        // sum over 32 lanes), reduced with two redux.sync, and lane 0 adds the non-zero counters to this warp's stripe
+        const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) | ((uint32_t)loc.st[3] << 18) |
+                            ((uint32_t)loc.st[5] << 24);
+        const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
+        const uint32_t sa = __reduce_add_sync(FULL, pa), sb = __reduce_add_sync(FULL, pb);
+        if (lane == 0) {
+            unsigned long long *stripe = reinterpret_cast<unsigned long long *>(P.stats) + 8 * (wglobal & (kStatStripes - 1));
+            if (sa) {
+                if (sa & 63u) atomicAdd(stripe + 0, (unsigned long long)(sa & 63u));
+                if ((sa >> 6) & 63u) atomicAdd(stripe + 1, (unsigned long long)((sa >> 6) & 63u));
+                if ((sa >> 12) & 63u) atomicAdd(stripe + 2, (unsigned long long)((sa >> 12) & 63u));
+                if ((sa >> 18) & 63u) atomicAdd(stripe + 3, (unsigned long long)((sa >> 18) & 63u));
+                if ((sa >> 24) & 63u) atomicAdd(stripe + 5, (unsigned long long)((sa >> 24) & 63u));
+                atomicAdd(stripe + 4, (unsigned long long)(sb & 0x3fffu));
+            }
+            if ((sb >> 14) & 63u) atomicAdd(stripe + 6, (unsigned long long)((sb >> 14) & 63u));
+            if (sb >> 20) atomicAdd(stripe + 7, (unsigned long long)(sb >> 20));
         }
     } else if (P.mode == MODE_RESET) {
         game_reset<N>(P, g, rec, flg);
@@ -239,7 +271,7 @@ struct Layout {
 static Layout layout_of(const hexb_config *c) {
     Layout L;
     const long long C = (long long)c->board_size * c->board_size;
-    const long long W = (C + 31) / 32, R = 2 * W + 3;
+    const long long W = (C + 31) / 32, R = 2 * W + 2;
     L.Gpad = (c->num_games + kTile - 1) / kTile * kTile;
     L.labels_off = 0;
     L.rec_off = align256((size_t)(L.Gpad * C));
@@ -310,6 +342,7 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
         CK(cudaFuncSetAttribute(hexb_step_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     const unsigned grid = (unsigned)(P.Gpad / kTile);

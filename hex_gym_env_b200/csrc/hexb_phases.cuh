@@ -50,7 +50,6 @@ HEXB_HD void load_rec(const Params &P, long long g, Rec<N> &r) {
     for (int w = 0; w < W; ++w) r.occ_cm[w] = b[(long long)(W + w) * P.Gpad];
     r.meta = b[(long long)(2 * W) * P.Gpad];
     r.draws = b[(long long)(2 * W + 1) * P.Gpad];
-    r.aux = b[(long long)(2 * W + 2) * P.Gpad];
 }
 template <int N>
 HEXB_HD void store_rec(const Params &P, long long g, const Rec<N> &r) {
@@ -62,7 +61,6 @@ HEXB_HD void store_rec(const Params &P, long long g, const Rec<N> &r) {
     for (int w = 0; w < W; ++w) b[(long long)(W + w) * P.Gpad] = r.occ_cm[w];
     b[(long long)(2 * W) * P.Gpad] = r.meta;
     b[(long long)(2 * W + 1) * P.Gpad] = r.draws;
-    b[(long long)(2 * W + 2) * P.Gpad] = r.aux;
 }
 
 // reward HexEnv.step would hand out again for an already finished variant-A game (HexGame.py:250,267-279)
@@ -129,7 +127,6 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
             loc.reward = P.variant == VARIANT_A ? -100.f : 0.f;
         } else {
             const bool won = place_stone<N>(L, rec, 0, a, prmA);
-            rec.aux++;
             loc.st[7]++;
             rec.meta ^= M_TOMOVE;
             if (won) {
@@ -151,7 +148,6 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
             const int i = select_kth_zero<N>(rec.occ_cm, choice_of(u, n));  // k-th empty cell of the opponent's view = stored column-major
             const int x = i / N, y = i - x * N;
             const bool won = place_stone<N>(L, rec, 1, y * N + x, prmB);
-            rec.aux++;
             loc.st[7]++;
             rec.meta ^= M_TOMOVE;
             if (won) {
@@ -170,7 +166,7 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
         loc.st[1] = (w == 1u && !tr) || (w == 2u && tr);
         loc.st[2] = (w == 2u && !tr) || (w == 1u && tr);
         loc.st[3] = (w == 1u);
-        loc.st[4] = (int)(rec.aux & 0xffffu);
+        loc.st[4] = Geo<N>::C - count_empty<N>(rec.occ_rm);  // plies of the episode = stones on the board
         loc.st[5] = (rec.meta & M_INVALID) != 0u;
         if (P.term_obs) flg |= F_TERM | (((rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B) ? F_TERM_OPP : 0u);
     }
@@ -203,7 +199,6 @@ HEXB_HD void game_ply(uint8_t *L, const Params &P, long long g, Rec<N> &rec, uin
         const int cell = (P.variant == VARIANT_B && p) ? transpose_cell<N>(a) : a;
         if (!test_bit<N>(rec.occ_rm, cell)) {
             const bool won = place_stone<N>(L, rec, p, cell, prmA);
-            rec.aux++;
             rec.meta ^= M_TOMOVE;
             r = -1;
             if (won) {
@@ -248,21 +243,44 @@ HEXB_HD uint32_t row_mask(int row_start, int row_end, int w) {
 // 0x80 in every byte of y that is zero
 HEXB_HD uint32_t zero_flags(uint32_t y) { return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u; }
 
+// words a row can span, and sweeps of 32 lanes needed to cover them
+template <int N>
+struct RowSpan {
+    static constexpr int WORDS = (Geo<N>::C + 3) / 4 + (Chunk<N>::ALIGNED_ROWS ? 0 : 1);
+    static constexpr int SWEEPS = (WORDS + kWarp - 1) / kWarp;
+};
+
+// one relabel request applied to one word: every byte equal to o1 (or o2) becomes m; zf = 0x80 flags of the bytes to change
+HEXB_HD uint32_t relabel_flags(uint32_t x, uint32_t prm) {
+    const uint32_t o1 = prm & 0xffu, o2 = (prm >> 8) & 0xffu;
+    uint32_t zf = zero_flags(x ^ splat(o1));
+    if (o2 != o1) zf |= zero_flags(x ^ splat(o2));  // a third adjacent group is rare; the branch is warp-uniform
+    return zf;
+}
+
 // regions[regions == label] = new_region_label (HexGame.py:141-142, HexSingleGame.py:152-153) for both plies of the step
 // in one sweep. The two requests touch disjoint byte values (the owner bit is part of the byte), so their order is free.
-// A request of 0 (nothing to do) degenerates to "replace empty by empty".
+// Usually only one of the two plies merges groups, and only two of them: the branches below are warp-uniform.
 template <int N>
 HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t prmB, int lane) {
     constexpr int C = Geo<N>::C;
     const int rs = r * C, re = rs + C;
-    const uint32_t a1 = splat(prmA & 0xffu), a2 = splat((prmA >> 8) & 0xffu), am = splat((prmA >> 16) & 0xffu);
-    const uint32_t b1 = splat(prmB & 0xffu), b2 = splat((prmB >> 8) & 0xffu), bm = splat((prmB >> 16) & 0xffu);
-    for (int w = (rs >> 2) + lane; w <= ((re - 1) >> 2); w += kWarp) {
+    const int wl = (re - 1) >> 2;
+#pragma unroll
+    for (int it = 0; it < RowSpan<N>::SWEEPS; ++it) {
+        const int w = (rs >> 2) + lane + it * kWarp;
+        if (w > wl) break;
         const uint32_t x = lab32[w];
         const uint32_t rm = row_mask<N>(rs, re, w);
-        const uint32_t ma = (((zero_flags(x ^ a1) | zero_flags(x ^ a2)) >> 7) * 0xffu) & rm;
-        const uint32_t mb = (((zero_flags(x ^ b1) | zero_flags(x ^ b2)) >> 7) * 0xffu) & rm;
-        const uint32_t x2 = (x & ~(ma | mb)) | (am & ma) | (bm & mb);
+        uint32_t x2 = x;
+        if (prmA & P_NEED) {
+            const uint32_t mk = ((relabel_flags(x, prmA) >> 7) * 0xffu) & rm;
+            x2 = (x2 & ~mk) | (splat((prmA >> 16) & 0xffu) & mk);
+        }
+        if (prmB & P_NEED) {
+            const uint32_t mk = ((relabel_flags(x, prmB) >> 7) * 0xffu) & rm;
+            x2 = (x2 & ~mk) | (splat((prmB >> 16) & 0xffu) & mk);
+        }
         if (x2 != x) lab32[w] = x2;
     }
 }
@@ -274,7 +292,10 @@ HEXB_HD void clear_row_lane(uint32_t *lab32, int r, uint32_t flg, int lane) {
     constexpr int C = Geo<N>::C;
     const int rs = r * C, re = rs + C;
     const int ob = rs + (int)(flg >> 16);  // chunk byte of the opening stone
-    for (int w = (rs >> 2) + lane; w <= ((re - 1) >> 2); w += kWarp) {
+#pragma unroll
+    for (int it = 0; it < RowSpan<N>::SWEEPS; ++it) {
+        const int w = (rs >> 2) + lane + it * kWarp;
+        if (w > ((re - 1) >> 2)) break;
         const uint32_t rm = row_mask<N>(rs, re, w);
         uint32_t x = Chunk<N>::ALIGNED_ROWS ? 0u : (lab32[w] & ~rm);
         if ((flg & F_OPEN) && (ob >> 2) == w) x |= ((flg >> 8) & 0xffu) << (8 * (ob & 3));

@@ -113,14 +113,12 @@ HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true,
     for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
     rec.meta = M_LIVE | M_COLOUR_SET | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
     rec.draws = 0;
-    rec.aux = 0;
     for (int c = 0; c < C; ++c) L[c] = 0;
     for (int c = 0; c < C; ++c) {
         const int v = board_true[g * C + c];
         if (v != 0 && v != 1) continue;
         uint32_t prm;
         place_stone<N>(L, rec, v, c, prm);
-        rec.aux++;
         if (prm & P_NEED)
             for (int k = 0; k < C; ++k) L[k] = (uint8_t)relabel_byte(L[k], prm);
     }

@@ -107,7 +107,7 @@ void *emu_create(int N, int variant, long long G, long long game_offset, unsigne
     if (N < 3 || N > 19 || G < 1) return nullptr;
     emu_env *e = new emu_env();
     e->N = N;
-    const long long C = (long long)N * N, W = (C + 31) / 32, R = 2 * W + 3;
+    const long long C = (long long)N * N, W = (C + 31) / 32, R = 2 * W + 2;
     const long long Gpad = (G + kTile - 1) / kTile * kTile;
     const size_t rec_off = align256((size_t)(Gpad * C)), stats_off = rec_off + align256((size_t)(R * Gpad * 4));
     e->state.assign(stats_off + 256 + 256, 0);
