@@ -112,3 +112,43 @@ def versus_oracle(make, kind, N, G, T, seed=0, game_offset=0, fused=True, auto_r
                 eq(e[key], re_[key], w + key)
     eq(env.stats(), ref.stats(), "stats")
     return ref, env
+
+
+def snake_moves(N):
+    """Deterministic adversarial game (BASELINE config 5): BLACK builds ONE serpentine chain through every even row (joined at
+    alternating ends of the odd rows), first placing every other stone of the path (about N*N/4 isolated stones = as many
+    distinct labels as the board can hold), then filling the gaps so that every move merges two groups and the final moves
+    relabel a chain of ~N*N/2 stones; WHITE fills the rest of the odd rows. Worst case for a flood-fill based checker."""
+    path = []
+    for r in range(N):
+        if r % 2 == 0:
+            xs = range(N) if (r // 2) % 2 == 0 else range(N - 1, -1, -1)
+            path += [r * N + x for x in xs]
+        else:
+            path.append(r * N + (N - 1 if (r // 2) % 2 == 0 else 0))
+    black = path[0::2] + path[1::2]
+    taken = set(path)
+    white = [c for c in range(N * N) if c not in taken]
+    moves = []
+    for i in range(min(len(black), len(white))):
+        moves += [black[i], white[i]]
+    return moves
+
+
+def snake_chain(make, N):
+    moves = snake_moves(N)
+    G = 40
+    env = make(hexref.KIND_GAME_A, N, G)
+    ref = hexref.RefBatch(hexref.KIND_GAME_A, N, G)
+    env.reset()
+    rs = np.random.RandomState(1)
+    lag = rs.randint(0, 3, size=G)          # games run the same list with small offsets so that lanes are out of step
+    for t in range(len(moves) + 2):
+        idx = np.clip(t - lag, 0, len(moves) - 1)
+        a = np.array(moves, np.int32)[idx]
+        eq(env.ply(a), ref.ply(a), "snake ret t=%d" % t)
+        if t % 7 == 0 or t >= len(moves) - 3:
+            e, r = env.export(), ref.export()
+            for k in ("board", "regions", "region_counter", "cur", "done", "winner"):
+                eq(e[k], r[k], "snake %s t=%d" % (k, t))
+    assert ref.export()["region_counter"].max() >= N * N // 5   # the label range really was exercised

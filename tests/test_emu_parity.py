@@ -52,3 +52,24 @@ def test_no_auto_reset(kind):
 
 def test_eval_state_draws():
     parity.versus_oracle(make, hexref.KIND_SELFPLAY_B, 5, 130, 40, seed=9, agent_mode=2, eval_state=True)
+
+
+@pytest.mark.parametrize("N", [7, 19])
+def test_snake_chain_worst_case(N):
+    parity.snake_chain(make, N)
+
+
+@pytest.mark.parametrize("N", [4, 11])
+def test_preset_board_rebuild(N):
+    """hexb_import_boards (HexGame.__init__ with a preset board, raster-order flood_fill) vs the oracle."""
+    rs = np.random.RandomState(N)
+    G = 50
+    boards = rs.choice([0, 1, 2], size=(G, N, N), p=[0.3, 0.3, 0.4]).astype(np.int8)
+    env = EmuBatch(0, N, G, raw=True)
+    env.reset()
+    env.import_boards(boards, np.zeros(G, np.int8))
+    ref = hexref.RefBatch(hexref.KIND_GAME_A, N, G)
+    ref.set_board(boards, cur=0)
+    e, r = env.export(), ref.export()
+    for k in ("board", "regions", "region_counter", "cur"):
+        parity.eq(e[k], r[k], k)

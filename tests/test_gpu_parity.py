@@ -132,3 +132,8 @@ def test_step_host_matches_device(make):
     io = b.step_host(acts.cpu())
     for k in ("obs", "mask", "reward", "done"):
         assert np.array_equal(o[k].cpu().numpy(), io[k].numpy()), k
+
+
+@pytest.mark.parametrize("N", [7, 11, 19])
+def test_snake_chain_worst_case(make, N):
+    parity.snake_chain(make, N)
