@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""BASELINE config 4: 6x6 MaskablePPO-style self-play training with the batched env feeding a device-resident rollout buffer.
+
+What scripts/experiments/6x6_MLP-default_lr-0.0003.py of the reference does with SB3 (MaskablePPO("MlpPolicy"), lr 3e-4,
+gamma 0.99, lambda 0.95, clip 0.2, 10 epochs, default MlpPolicy = separate 2x64 tanh nets for pi and vf - shapes read from
+models/6x6_MLP-default_lr-0.0003_71), here with G games collected in lockstep on one GPU. The opponent is the random policy
+(BaseRandomPolicy); SB3 itself is not installed, so the learner below is a plain torch restatement of the PPO update.
+
+    python examples/ppo_selfplay.py --board 6 --games 4096 --n-steps 128 --iters 20
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+from hex_gym_env_b200 import AGENT_RANDOM, VARIANT_B, HexBatch  # noqa: E402
+from hex_gym_env_b200.rollout import RolloutCollector  # noqa: E402
+
+
+class MlpPolicy(nn.Module):
+    def __init__(self, cells, hidden=64):
+        super().__init__()
+        self.pi = nn.Sequential(nn.Flatten(), nn.Linear(cells, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(), nn.Linear(hidden, cells))
+        self.vf = nn.Sequential(nn.Flatten(), nn.Linear(cells, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(), nn.Linear(hidden, 1))
+
+    def forward(self, obs):
+        return self.pi(obs), self.vf(obs).squeeze(-1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--board", type=int, default=6)
+    ap.add_argument("--games", type=int, default=4096)
+    ap.add_argument("--n-steps", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--epochs", type=int, default=10)
+    ap.add_argument("--minibatch", type=int, default=16384)
+    ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    torch.manual_seed(args.seed)
+    dev = torch.device("cuda", 0)
+    env = HexBatch(args.board, args.games, variant=VARIANT_B, device=0, seed=args.seed, agent_mode=AGENT_RANDOM, auto_reset=True)
+    policy = MlpPolicy(env.C).to(dev)
+    opt = torch.optim.Adam(policy.parameters(), lr=args.lr, eps=1e-5)
+    col = RolloutCollector(env, args.n_steps, gamma=0.99, gae_lambda=0.95, seed=args.seed)
+    prev = env.stats().cpu()
+    for it in range(args.iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        buf = col.collect(policy)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(args.epochs):
+            for mb in buf.minibatches(args.minibatch):
+                logits, values = policy(mb["obs"].float())
+                logits = logits.masked_fill(mb["action_masks"] == 0, -1e8)      # sb3_contrib's HUGE_NEG masking
+                logp_all = torch.log_softmax(logits, dim=-1)
+                logp = logp_all.gather(1, mb["actions"].long().unsqueeze(1)).squeeze(1)
+                adv = mb["advantages"]
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                ratio = torch.exp(logp - mb["log_probs"])
+                pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+                vloss = torch.nn.functional.mse_loss(values, mb["returns"])
+                ent = -(torch.exp(logp_all) * logp_all.masked_fill(mb["action_masks"] == 0, 0.0)).sum(-1).mean()
+                loss = pg + 0.5 * vloss - 0.0 * ent
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(policy.parameters(), 0.5)
+                opt.step()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        st = env.stats().cpu()
+        d = (st - prev).tolist()
+        prev = st
+        steps = args.games * args.n_steps
+        print(json.dumps({"iter": it, "collect_env_steps_per_sec": steps / (t1 - t0), "end_to_end_env_steps_per_sec": steps / (t2 - t0),
+                          "episodes": d[0], "agent_win_rate": d[3] / max(d[0], 1), "invalid_rate": d[5] / max(d[0], 1),
+                          "mean_episode_plies": d[4] / max(d[0], 1), "loss": float(loss)}))
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,7 @@ SYMBOLS = {
     "hexb_export_state": (_i32, [_vp] * 10),
     "hexb_import_boards": (_i32, [_vp] * 4),
     "hexb_stats": (_i32, [_vp] * 3),
+    "hexb_masked_sample": (_i32, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp, _vp, _vp, _i32, _vp]),
 }
 
 _LIB = None

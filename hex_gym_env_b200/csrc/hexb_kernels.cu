@@ -235,6 +235,84 @@ __global__ void hexb_stats_kernel(const long long *src, int64_t *dst) {
     }
 }
 
+// K8: masked categorical sampling, one warp per game. Cells are dealt to lanes in blocks of 32 (cell = 32*k + lane), so a
+// block's inclusive scan over lanes continues the running CDF in cell order.
+__global__ void __launch_bounds__(128) hexb_masked_sample_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ mask,
+                                                                 const double *__restrict__ u, long long G, int C, int32_t *actions,
+                                                                 float *logp, float *entropy) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int KMAX = (HEXB_MAX_BOARD * HEXB_MAX_BOARD + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= G) return;
+    const float *lg = logits + g * C;
+    const uint8_t *mk = mask + g * C;
+    const int K = (C + 31) >> 5;
+    float l[KMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int c = 32 * k + lane;
+        l[k] = (k < K && c < C && mk[c]) ? lg[c] : -INFINITY;
+        mx = fmaxf(mx, l[k]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    if (mx == -INFINITY) {  // no legal cell
+        if (lane == 0) {
+            if (actions) actions[g] = -1;
+            if (logp) logp[g] = 0.f;
+            if (entropy) entropy[g] = 0.f;
+        }
+        return;
+    }
+    float e[KMAX], z = 0.f, sel = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        e[k] = (l[k] == -INFINITY) ? 0.f : __expf(l[k] - mx);
+        z += e[k];
+        sel += e[k] * ((l[k] == -INFINITY) ? 0.f : (l[k] - mx));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        z += __shfl_xor_sync(FULL, z, o);
+        sel += __shfl_xor_sync(FULL, sel, o);
+    }
+    const float logz = __logf(z);
+    const float target = (float)(u[g] * (double)z);
+    float run = 0.f;
+    int pick = -1, last_legal = -1;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+            float s = e[k];  // inclusive scan over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(FULL, s, o);
+                if (lane >= o) s += t;
+            }
+            const float cum = run + s;
+            const uint32_t hit = __ballot_sync(FULL, e[k] > 0.f && cum > target);
+            const uint32_t legal = __ballot_sync(FULL, e[k] > 0.f);
+            if (pick < 0 && hit) pick = 32 * k + (__ffs(hit) - 1);
+            if (legal) last_legal = 32 * k + (31 - __clz(legal));
+            run += __shfl_sync(FULL, s, 31);
+        }
+    }
+    if (pick < 0) pick = last_legal;  // u*z rounded up to the total: the last legal cell
+    const int pk = pick >> 5, pl = pick & 31;
+    float lp = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k == pk) lp = l[k];
+    lp = __shfl_sync(FULL, lp, pl) - mx - logz;
+    if (lane == 0) {
+        if (actions) actions[g] = pick;
+        if (logp) logp[g] = lp;
+        if (entropy) entropy[g] = logz - sel / z;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct hexb_env {
     hexb_config cfg;
@@ -503,6 +581,16 @@ int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream) {
     if (!env || !out8) return HEXB_ERR_ARG;
     CK(cudaSetDevice(env->cfg.device));
     hexb_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->base.stats, out8);
+    CK(cudaGetLastError());
+    return HEXB_OK;
+}
+
+int32_t hexb_masked_sample(const float *logits, const uint8_t *mask, const double *u, int64_t num_games, int32_t num_cells,
+                           int32_t *actions, float *logp, float *entropy, int32_t device, void *stream) {
+    if (!logits || !mask || !u || num_games < 1 || num_cells < 1 || num_cells > HEXB_MAX_BOARD * HEXB_MAX_BOARD) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(device));
+    const unsigned grid = (unsigned)((num_games * 32 + 127) / 128);
+    hexb_masked_sample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(logits, mask, u, num_games, num_cells, actions, logp, entropy);
     CK(cudaGetLastError());
     return HEXB_OK;
 }

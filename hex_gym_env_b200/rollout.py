@@ -1,0 +1,111 @@
+"""Device-resident rollout feed for MaskablePPO-style training (BASELINE config 4).
+
+The reference collects rollouts with stable-baselines3: `MaskablePPO.collect_rollouts` steps ONE Python env, asks it for its
+action mask, samples from a masked categorical and appends to a `MaskableRolloutBuffer`
+(scripts/experiments/6x6_MLP-default_lr-0.0003.py:34-47; SB3 2.2.1 / sb3-contrib from memory - not installed here, so the
+buffer layout is duck-typed: obs [T,G,N,N], action_masks [T,G,C], actions, rewards, episode_starts, values, log_probs,
+advantages, returns). Here the whole loop stays on the GPU: the fused step kernel writes observations and masks straight
+into the buffer's slices, `masked_sample` (hexb_masked_sample, one warp per game) replaces the distribution object, and
+nothing crosses PCIe until the learner wants a scalar.
+"""
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import check
+from .batch import HexBatch
+
+
+def masked_sample(logits, mask, u=None, generator=None, want_entropy=False):
+    """Sample one legal action per row. logits f32[G,C], mask u8/bool[G,C] (1 = legal), u f64[G] uniforms (drawn with
+    torch if None). Returns (actions i32[G], log_prob f32[G][, entropy f32[G]])."""
+    if not logits.is_cuda:
+        raise RuntimeError("masked_sample runs on the GPU only (no CPU fallback)")
+    G, C = logits.shape
+    logits = logits.contiguous().float()
+    mask = mask.contiguous()
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    if u is None:
+        u = torch.rand(G, dtype=torch.float64, device=logits.device, generator=generator)
+    u = u.contiguous().double()
+    actions = torch.empty(G, dtype=torch.int32, device=logits.device)
+    logp = torch.empty(G, dtype=torch.float32, device=logits.device)
+    ent = torch.empty(G, dtype=torch.float32, device=logits.device) if want_entropy else None
+    p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    with torch.cuda.device(logits.device):
+        check(_native.lib().hexb_masked_sample(p(logits), p(mask), p(u), G, C, p(actions), p(logp), p(ent), logits.device.index,
+                                               ctypes.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)))
+    return (actions, logp, ent) if want_entropy else (actions, logp)
+
+
+class RolloutBuffer(object):
+    """[T, G] rollout storage on the device in MaskableRolloutBuffer's layout. Observations are kept as the int8 bytes the
+    step kernel emits (obs_f32() converts a slice for the network)."""
+
+    def __init__(self, n_steps, batch: HexBatch, gamma=0.99, gae_lambda=0.95):
+        T, G, N, C, dev = n_steps, batch.G, batch.N, batch.C, batch.device
+        self.T, self.G, self.gamma, self.gae_lambda = T, G, gamma, gae_lambda
+        self.obs = torch.zeros((T + 1, G, N, N), dtype=torch.int8, device=dev)       # slot T = the observation after the last step
+        self.action_masks = torch.zeros((T + 1, G, C), dtype=torch.uint8, device=dev)
+        self.actions = torch.zeros((T, G), dtype=torch.int32, device=dev)
+        self.rewards = torch.zeros((T, G), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((T, G), dtype=torch.uint8, device=dev)
+        self.episode_starts = torch.zeros((T + 1, G), dtype=torch.float32, device=dev)
+        self.values = torch.zeros((T + 1, G), dtype=torch.float32, device=dev)
+        self.log_probs = torch.zeros((T, G), dtype=torch.float32, device=dev)
+        self.advantages = torch.zeros((T, G), dtype=torch.float32, device=dev)
+        self.returns = torch.zeros((T, G), dtype=torch.float32, device=dev)
+
+    def compute_returns_and_advantage(self):
+        """GAE(lambda) exactly as SB3's RolloutBuffer: a finished episode (auto-reset) cuts the bootstrap."""
+        last = torch.zeros(self.G, dtype=torch.float32, device=self.values.device)
+        for t in reversed(range(self.T)):
+            nonterminal = 1.0 - self.episode_starts[t + 1]
+            delta = self.rewards[t] + self.gamma * self.values[t + 1] * nonterminal - self.values[t]
+            last = delta + self.gamma * self.gae_lambda * nonterminal * last
+            self.advantages[t] = last
+        self.returns = self.advantages + self.values[:-1]
+
+    def minibatches(self, batch_size, generator=None):
+        n = self.T * self.G
+        perm = torch.randperm(n, device=self.obs.device, generator=generator)
+        flat = dict(obs=self.obs[:-1].reshape(n, *self.obs.shape[2:]), action_masks=self.action_masks[:-1].reshape(n, -1),
+                    actions=self.actions.reshape(n), values=self.values[:-1].reshape(n), log_probs=self.log_probs.reshape(n),
+                    advantages=self.advantages.reshape(n), returns=self.returns.reshape(n))
+        for s in range(0, n, batch_size):
+            idx = perm[s:s + batch_size]
+            yield {k: v[idx] for k, v in flat.items()}
+
+
+class RolloutCollector(object):
+    """collect(): T fused env steps of all games with actions sampled from `policy` under the legal-action mask.
+    `policy(obs_f32[G,N,N]) -> (logits f32[G,C], values f32[G])` is any torch callable living on the same GPU."""
+
+    def __init__(self, batch: HexBatch, n_steps, gamma=0.99, gae_lambda=0.95, seed=0):
+        self.batch, self.buf = batch, RolloutBuffer(n_steps, batch, gamma, gae_lambda)
+        self.gen = torch.Generator(device=batch.device)
+        self.gen.manual_seed(seed)
+        self._started = False
+
+    def collect(self, policy):
+        b, buf = self.batch, self.buf
+        if not self._started:
+            b.reset(obs=buf.obs[0], mask=buf.action_masks[0])
+            buf.episode_starts[0] = 1.0
+            self._started = True
+        else:  # continue from where the previous rollout stopped
+            buf.obs[0].copy_(buf.obs[-1])
+            buf.action_masks[0].copy_(buf.action_masks[-1])
+            buf.episode_starts[0].copy_(buf.episode_starts[-1])
+        with torch.no_grad():
+            for t in range(buf.T):
+                logits, values = policy(buf.obs[t].float())
+                actions, logp = masked_sample(logits, buf.action_masks[t], generator=self.gen)
+                buf.actions[t], buf.log_probs[t], buf.values[t] = actions, logp, values
+                b.step(actions, obs=buf.obs[t + 1], mask=buf.action_masks[t + 1], reward=buf.rewards[t], done=buf.dones[t])
+                buf.episode_starts[t + 1] = buf.dones[t].float()
+            _, buf.values[buf.T] = policy(buf.obs[buf.T].float())
+        buf.compute_returns_and_advantage()
+        return buf

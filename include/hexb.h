@@ -136,6 +136,15 @@ int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t
  * layer all-reduces this vector with NCCL; nothing else ever crosses GPUs. */
 int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream);
 
+/* Masked categorical sampling for a batch of policy outputs (the rollout feed of SURVEY.md section 8f, row 1). Replaces what
+ * sb3_contrib's MaskableCategoricalDistribution does between MaskablePPO's policy network and env.step in the reference's
+ * training scripts (scripts/experiments/ *.py:40-47): illegal cells get probability 0, an action is drawn by inverse CDF from
+ * the caller's uniforms and its log-probability is returned. No env handle: logits f32[G,C] row-major, mask u8[G,C]
+ * (1 = legal, as hexb_step writes it), u f64[G] in [0,1); out: actions i32[G], logp f32[G] (either may be null),
+ * entropy f32[G] (nullable). A row without a legal cell yields action -1, logp 0. */
+int32_t hexb_masked_sample(const float *logits, const uint8_t *mask, const double *u, int64_t num_games, int32_t num_cells,
+                           int32_t *actions, float *logp, float *entropy, int32_t device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
