@@ -74,7 +74,8 @@ def lib():
     global _LIB
     if _LIB is None:
         try:
-            path = build()
+            # HEXB_LIB: load this build of the same CUDA library instead (kernel-tuning experiments, e.g. other CTA shapes)
+            path = os.environ.get("HEXB_LIB") or build()
             L = ctypes.CDLL(path)
         except (OSError, RuntimeError) as exc:
             raise RuntimeError("hex_gym_env_b200: the CUDA library libhexb.so is required and could not be loaded "

@@ -74,8 +74,8 @@ struct Geo {
     static constexpr int C = N * N;
     static constexpr int W = (C + 31) / 32;      // bitboard words
     static constexpr int R = 2 * W + 2;          // record words: occ_rm[W], occ_cm[W], meta, draws
-    static constexpr int TILE_BYTES = kTile * C;  // label bytes per tile (multiple of 16)
-    static constexpr int TILE_WORDS = TILE_BYTES / 4;
+    static constexpr int CHUNK_LAB = 32 * C;               // label bytes of a chunk (multiple of 16)
+    static constexpr int CHUNK_STATE = 32 * (C + 4 * R);   // whole chunk: labels + records (multiple of 16)
     static constexpr uint32_t LAST_MASK = (C % 32) ? ((1u << (C % 32)) - 1u) : 0xffffffffu;
 };
 
@@ -86,15 +86,23 @@ struct Rec {
     uint32_t meta, draws;  // (plies of the running episode = stones on the board = popcount of the occupancy)
 };
 
+// Packed state, chunk-major: games are grouped in chunks of 32 (one warp); chunk k occupies CHUNK_STATE contiguous,
+// 16-byte aligned bytes = the 32 games' label bytes [32][C] followed by their record words [R][32] (word-major so that lane
+// i reads word w at [w*32 + i] without bank conflicts). One bulk copy moves a whole chunk.
+HEXB_HD long long chunk_state_bytes(int C) { return 32ll * (C + 4 * (2 * ((C + 31) / 32) + 2)); }
+HEXB_HD long long labels_offset(long long g, int C) { return (g >> 5) * chunk_state_bytes(C) + (g & 31) * C; }
+HEXB_HD long long rec_offset(long long g, int C) { return (g >> 5) * chunk_state_bytes(C) + 32ll * C + 4 * (g & 31); }  // word w: + 128*w
+constexpr int kRecStride = 32;  // words between consecutive record words of one game
+
 struct Params {
     // packed state (owned by the handle)
-    uint8_t *labels;      // [Gpad][C]
-    uint32_t *rec;        // [R][Gpad]
+    uint8_t *state;       // [Gpad/32] chunks of { labels u8[32][C], records u32[R][32] }
     long long *stats;     // [kStatStripes][8]
     long long G, Gpad, game_offset;
     unsigned long long seed;
     int variant, auto_reset, eval_state, opponent_first, agent_mode, mode;
     int raw;  // 1: bare HexGame batch (hexb_ply): reset draws nothing and nobody opens
+    uint32_t one;  // always 1, but opaque to the compiler: a * one + b is issued as IMAD on the FMA pipe (see fma_add)
     // borrowed I/O (device pointers, any may be null unless noted)
     const int32_t *actions;    // [G]   null => sample the agent's move on device (one draw)
     const double *opp_u;       // [G,2] null => Philox stream
@@ -306,12 +314,27 @@ HEXB_HD uint32_t sign_fill(uint32_t f) {
     return ((f >> 7) & 0x01010101u) * 0xffu;
 #endif
 }
-HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) {
-    const uint32_t n = nz_flags(x);                   // 0x80 per stone
+// a + b issued as a multiply-add (IMAD, FMA pipe) instead of an add (IADD3 / VIADD, ALU pipe). `one` is Params::one: the
+// step kernel is bound by the ALU pipe (LOP3 / SHF / PRMT / ISETP, rt 2 cycles per warp instruction and SMSP) while the FMA
+// pipe idles, so the adds and shifts of the byte-SIMD loops are steered there.
+HEXB_HD uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+
+// x >> 7 for a word of 0x80 byte flags, issued as a multiply-high so that it runs on the (idle) FMA pipe instead of the ALU
+// pipe, which is the busy one in the step kernel (ncu: sm__pipe_alu_cycles_active is the top pipe)
+HEXB_HD uint32_t flags_to_ones(uint32_t f) { return mulhi32(f, 1u << 25); }
+
+template <int VARIANT>
+HEXB_HD void encode_word_v(uint32_t x, uint32_t one, uint32_t &obs, uint32_t &msk) {
+    const uint32_t t = fma_add(x & 0x7f7f7f7fu, 0x7f7f7f7fu, one);
+    const uint32_t z = ~(t | x) & 0x80808080u;        // 0x80 per EMPTY cell
     const uint32_t c = x & 0x80808080u;               // 0x80 per C stone
-    msk = (n >> 7) ^ 0x01010101u;                     // legal == empty
-    if (variant == VARIANT_B) obs = sign_fill(n ^ c) | (c >> 7);
-    else obs = (c >> 7) | (msk << 1);
+    msk = flags_to_ones(z);                           // legal == empty
+    if (VARIANT == VARIANT_B) obs = sign_fill(~(z | x) & 0x80808080u) | flags_to_ones(c);   // R -> 0xff, C -> 0x01
+    else obs = flags_to_ones(c) | (msk << 1);         // BLACK 0 (= R), WHITE 1 (= C), EMPTY 2
+}
+HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) {
+    if (variant == VARIANT_B) encode_word_v<VARIANT_B>(x, 1u, obs, msk);
+    else encode_word_v<VARIANT_A>(x, 1u, obs, msk);
 }
 // one byte, optionally seen from the opponent's side (sign swap; the caller transposes the cell index)
 HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &msk) {

@@ -62,18 +62,24 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 //   [word][game] layout) and runs the Philox rounds of the step's two draws; then the thread-per-game plies, the
 //   warp-per-game row jobs, the elementwise obs/mask encode with 16-byte coalesced stores, the record stores and one
 //   bulk copy of the chunk back to global memory.
-constexpr int kWarpsPerCta = kTile / kWarp;
+#ifndef HEXB_WARPS_PER_CTA
+#define HEXB_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = HEXB_WARPS_PER_CTA;   // Gpad is a multiple of kTile = 128 games, so 1, 2 and 4 all divide it
+constexpr int kCtaThreads = kWarpsPerCta * kWarp;
 // resident CTAs per SM the register allocation should allow: 12 (48 warps) while the record is small, else whatever the
 // shared-memory footprint of the four chunks permits anyway
 constexpr int min_ctas(int n) {
-    const int smem = kWarpsPerCta * kWarp * n * n + 64;
+    const int smem = kWarpsPerCta * 32 * (n * n + 4 * (2 * ((n * n + 31) / 32) + 2)) + 64;
     const int by_smem = 220 * 1024 / smem;
-    return n <= 12 ? 12 : (by_smem < 1 ? 1 : (by_smem > 8 ? 8 : by_smem));
+    const int want = 12 * 4 / kWarpsPerCta;   // 48 warps per SM while the record is small
+    const int cap = 8 * 4 / kWarpsPerCta;
+    return n <= 12 ? (want > 32 ? 32 : want) : (by_smem < 1 ? 1 : (by_smem > cap ? cap : by_smem));
 }
 
 template <int N>
 struct SmemLayout {
-    static constexpr int CHUNK = Chunk<N>::BYTES;
+    static constexpr int CHUNK = Geo<N>::CHUNK_STATE;    // labels + records of 32 games
     static constexpr int BAR = kWarpsPerCta * CHUNK;   // multiple of 16
     static constexpr int BYTES = BAR + kWarpsPerCta * 8;
 };
@@ -90,13 +96,24 @@ __device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params 
     if (vec_ok && obs && msk && out0 + Chunk<N>::BYTES <= limit) {
         // the common case (warp-uniform): whole chunk inside the buffers, both outputs wanted, 16-byte aligned
         uint4 *po = reinterpret_cast<uint4 *>(obs + out0), *pm = reinterpret_cast<uint4 *>(msk + out0);
+        if (P.variant == VARIANT_B) {
 #pragma unroll 4
-        for (int i = lane; i < Chunk<N>::VECS; i += kWarp) {
-            const uint4 x = src[i];
-            Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
-            encode_vec<N>(in, P.variant, o, m);
-            __stcs(po + i, make_uint4(o.x, o.y, o.z, o.w));
-            __stcs(pm + i, make_uint4(m.x, m.y, m.z, m.w));
+            for (int i = lane; i < Chunk<N>::VECS; i += kWarp) {
+                const uint4 x = src[i];
+                Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
+                encode_vec_v<VARIANT_B>(in, P.one, o, m);
+                __stcs(po + i, make_uint4(o.x, o.y, o.z, o.w));
+                __stcs(pm + i, make_uint4(m.x, m.y, m.z, m.w));
+            }
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < Chunk<N>::VECS; i += kWarp) {
+                const uint4 x = src[i];
+                Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
+                encode_vec_v<VARIANT_A>(in, P.one, o, m);
+                __stcs(po + i, make_uint4(o.x, o.y, o.z, o.w));
+                __stcs(pm + i, make_uint4(m.x, m.y, m.z, m.w));
+            }
         }
         return;
     }
@@ -116,7 +133,7 @@ __device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params 
 }
 
 template <int N>
-__global__ void __launch_bounds__(kTile, min_ctas(N)) hexb_step_kernel(const Params P) {
+__global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(const Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using SL = SmemLayout<N>;
     constexpr int C = Geo<N>::C;
@@ -127,27 +144,52 @@ __global__ void __launch_bounds__(kTile, min_ctas(N)) hexb_step_kernel(const Par
     const long long wglobal = (long long)blockIdx.x * kWarpsPerCta + wid;
     const long long g0 = wglobal * kWarp;   // first game of the chunk
     const long long g = g0 + lane;          // this lane's game
-    uint8_t *gl = P.labels + g0 * C;
+    uint8_t *gl = P.state + wglobal * SL::CHUNK;
 
-    // ---- chunk in (asynchronous), record in, draws
+    // ---- chunk in (asynchronous: labels and records in ONE bulk copy); meanwhile the two draws of the step, which only need
+    //      the game's meta and stream-position words (two plain loads of lines the bulk copy is fetching anyway)
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, SL::CHUNK);
         bulk_g2s(chunk, gl, SL::CHUNK, bar);
     }
-    Rec<N> rec;
-    load_rec<N>(P, g, rec);
+    uint32_t *recw = reinterpret_cast<uint32_t *>(chunk + Geo<N>::CHUNK_LAB) + lane;   // this lane's record word 0 (shared memory)
     double u_agent = 0.0, u_opp = 0.0;
-    if (P.mode == MODE_STEP && g < P.G) pre_draws<N>(P, rec, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+#if defined(HEXB_EXP_NO_PHILOX)     // timing experiment only: a cheap hash instead of the two Philox draws
+    if (P.mode == MODE_STEP && g < P.G) {
+        uint32_t h = (uint32_t)g * 2654435761u + rec.draws * 40503u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        u_agent = (double)(h >> 8) * (1.0 / 16777216.0);
+        h *= 3266489917u; h ^= h >> 16;
+        u_opp = (double)(h >> 8) * (1.0 / 16777216.0);
+    }
+#else
+    if (P.mode == MODE_STEP && g < P.G) {
+        const uint32_t *grec = reinterpret_cast<const uint32_t *>(gl + Geo<N>::CHUNK_LAB) + lane;
+        pre_draws(P, grec[(2 * Geo<N>::W) * kRecStride], grec[(2 * Geo<N>::W + 1) * kRecStride],
+                  (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+    }
+#endif
     __syncwarp();  // the barrier's initialisation is visible to the other lanes
     mbar_wait(bar, 0);
+    Rec<N> rec;
+    load_rec<N>(recw, rec);
 
     // ---- thread-per-game phase
     uint32_t prmA = 0, prmB = 0, flg = 0;
     uint8_t *L = chunk + lane * C;
     if (P.mode == MODE_STEP) {
         Loc loc;
+#if defined(HEXB_EXP_NO_COMPUTE)   // timing experiment only: memory pipeline without the plies
+        loc.reward = 0.f; loc.action = 0;
+        for (int i = 0; i < 8; ++i) loc.st[i] = 0;
+        rec.draws++;
+#else
         game_step<N>(L, P, g, rec, u_agent, u_opp, loc, prmA, prmB, flg);
+#endif
+#if defined(HEXB_EXP_NO_ROWJOBS)   // timing experiment only
+        flg &= ~F_ROWJOB;
+#endif
         // K7: episode statistics - the eight per-game increments are packed into two words (fields wide enough for the
         // sum over 32 lanes), reduced with two redux.sync, and lane 0 adds the non-zero counters to this warp's stripe
         const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) | ((uint32_t)loc.st[3] << 18) |
@@ -172,8 +214,8 @@ __global__ void __launch_bounds__(kTile, min_ctas(N)) hexb_step_kernel(const Par
     } else {
         game_ply<N>(L, P, g, rec, prmA, flg);
     }
-    if (g < P.G) store_rec<N>(P, g, rec);
-    __syncwarp();  // every game's new stones are in shared memory
+    if (g < P.G) store_rec<N>(recw, rec);
+    __syncwarp();  // every game's new stones and record are in shared memory
 
     // ---- warp-per-game row jobs: relabel / terminal observation / clear + opening stone
     uint32_t pending = __ballot_sync(FULL, (flg & F_ROWJOB) != 0u);
@@ -352,8 +394,9 @@ static Layout layout_of(const hexb_config *c) {
     const long long W = (C + 31) / 32, R = 2 * W + 2;
     L.Gpad = (c->num_games + kTile - 1) / kTile * kTile;
     L.labels_off = 0;
-    L.rec_off = align256((size_t)(L.Gpad * C));
-    L.stats_off = L.rec_off + align256((size_t)(R * L.Gpad * 4));
+    L.rec_off = 0;   // chunk-major: records follow the labels inside every chunk
+    (void)W; (void)R;
+    L.stats_off = align256((size_t)(L.Gpad / 32 * chunk_state_bytes((int)C)));
     L.total = L.stats_off + align256((size_t)kStatStripes * 8 * 8);
     return L;
 }
@@ -389,8 +432,7 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     if (!e) return HEXB_ERR_ARG;
     e->cfg = *cfg;
     Params &P = e->base;
-    P.labels = (uint8_t *)state + L.labels_off;
-    P.rec = (uint32_t *)((uint8_t *)state + L.rec_off);
+    P.state = (uint8_t *)state;
     P.stats = (long long *)((uint8_t *)state + L.stats_off);
     P.G = cfg->num_games;
     P.Gpad = L.Gpad;
@@ -402,6 +444,7 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     P.opponent_first = cfg->opponent_first;
     P.agent_mode = cfg->agent_mode;
     P.raw = cfg->raw;
+    P.one = 1u;
     *out = e;
     return HEXB_OK;
 }
@@ -423,9 +466,9 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
         CK(cudaFuncSetAttribute(hexb_step_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
-    const unsigned grid = (unsigned)(P.Gpad / kTile);
+    const unsigned grid = (unsigned)(P.Gpad / kCtaThreads);
     (void)e;
-    hexb_step_kernel<N><<<grid, kTile, smem, s>>>(P);
+    hexb_step_kernel<N><<<grid, kCtaThreads, smem, s>>>(P);
     CK(cudaGetLastError());
     return HEXB_OK;
 }
@@ -444,8 +487,7 @@ static int dispatch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
 
 static View view_of(const hexb_env *e) {
     View V;
-    V.labels = e->base.labels;
-    V.rec = e->base.rec;
+    V.state = e->base.state;
     V.G = e->base.G;
     V.Gpad = e->base.Gpad;
     V.N = e->cfg.board_size;

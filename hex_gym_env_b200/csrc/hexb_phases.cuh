@@ -40,27 +40,26 @@ struct Loc {
     int st[8];  // episode statistics increments (see hexb.h: hexb_stats)
 };
 
+// b = address of record word 0 of this game (global memory or the chunk copy in shared memory); words are kRecStride apart
 template <int N>
-HEXB_HD void load_rec(const Params &P, long long g, Rec<N> &r) {
+HEXB_HD void load_rec(const uint32_t *b, Rec<N> &r) {
     constexpr int W = Geo<N>::W;
-    const uint32_t *b = P.rec + g;
 #pragma unroll
-    for (int w = 0; w < W; ++w) r.occ_rm[w] = b[(long long)w * P.Gpad];
+    for (int w = 0; w < W; ++w) r.occ_rm[w] = b[w * kRecStride];
 #pragma unroll
-    for (int w = 0; w < W; ++w) r.occ_cm[w] = b[(long long)(W + w) * P.Gpad];
-    r.meta = b[(long long)(2 * W) * P.Gpad];
-    r.draws = b[(long long)(2 * W + 1) * P.Gpad];
+    for (int w = 0; w < W; ++w) r.occ_cm[w] = b[(W + w) * kRecStride];
+    r.meta = b[(2 * W) * kRecStride];
+    r.draws = b[(2 * W + 1) * kRecStride];
 }
 template <int N>
-HEXB_HD void store_rec(const Params &P, long long g, const Rec<N> &r) {
+HEXB_HD void store_rec(uint32_t *b, const Rec<N> &r) {
     constexpr int W = Geo<N>::W;
-    uint32_t *b = P.rec + g;
 #pragma unroll
-    for (int w = 0; w < W; ++w) b[(long long)w * P.Gpad] = r.occ_rm[w];
+    for (int w = 0; w < W; ++w) b[w * kRecStride] = r.occ_rm[w];
 #pragma unroll
-    for (int w = 0; w < W; ++w) b[(long long)(W + w) * P.Gpad] = r.occ_cm[w];
-    b[(long long)(2 * W) * P.Gpad] = r.meta;
-    b[(long long)(2 * W + 1) * P.Gpad] = r.draws;
+    for (int w = 0; w < W; ++w) b[(W + w) * kRecStride] = r.occ_cm[w];
+    b[(2 * W) * kRecStride] = r.meta;
+    b[(2 * W + 1) * kRecStride] = r.draws;
 }
 
 // reward HexEnv.step would hand out again for an already finished variant-A game (HexGame.py:250,267-279)
@@ -75,12 +74,11 @@ HEXB_HD float stale_reward_A(uint32_t meta) {
 //   u_agent  BaseRandomPolicy.choose_action of the driving loop (only when actions == null)       at draws
 //   u_opp    BaseRandomPolicy.choose_action / random_policy of the opponent's reply                at draws (+1 if the agent
 //            drew) (+1 for the unused random.uniform of SelfplayWrapper.py:159 in variant B)
-template <int N>
-HEXB_HD void pre_draws(const Params &P, const Rec<N> &rec, unsigned long long gid, double &u_agent, double &u_opp) {
-    uint32_t idx = rec.draws;
+HEXB_HD void pre_draws(const Params &P, uint32_t meta, uint32_t draws, unsigned long long gid, double &u_agent, double &u_opp) {
+    uint32_t idx = draws;
     u_agent = 0.0;
     u_opp = 0.0;
-    if (!(rec.meta & M_LIVE) || (rec.meta & M_DONE)) return;
+    if (!(meta & M_LIVE) || (meta & M_DONE)) return;
     if (!P.actions) u_agent = draw01(P.seed, gid, idx++);
     if (!P.opp_u) u_opp = draw01(P.seed, gid, idx + (P.variant == VARIANT_B ? 1u : 0u));
 }
@@ -241,7 +239,7 @@ HEXB_HD uint32_t row_mask(int row_start, int row_end, int w) {
 }
 
 // 0x80 in every byte of y that is zero
-HEXB_HD uint32_t zero_flags(uint32_t y) { return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u; }
+HEXB_HD uint32_t zero_flags(uint32_t y, uint32_t one) { return ~(fma_add(y & 0x7f7f7f7fu, 0x7f7f7f7fu, one) | y) & 0x80808080u; }
 
 // words a row can span, and sweeps of 32 lanes needed to cover them
 template <int N>
@@ -251,10 +249,10 @@ struct RowSpan {
 };
 
 // one relabel request applied to one word: every byte equal to o1 (or o2) becomes m; zf = 0x80 flags of the bytes to change
-HEXB_HD uint32_t relabel_flags(uint32_t x, uint32_t prm) {
+HEXB_HD uint32_t relabel_flags(uint32_t x, uint32_t prm, uint32_t one) {
     const uint32_t o1 = prm & 0xffu, o2 = (prm >> 8) & 0xffu;
-    uint32_t zf = zero_flags(x ^ splat(o1));
-    if (o2 != o1) zf |= zero_flags(x ^ splat(o2));  // a third adjacent group is rare; the branch is warp-uniform
+    uint32_t zf = zero_flags(x ^ splat(o1), one);
+    if (o2 != o1) zf |= zero_flags(x ^ splat(o2), one);  // a third adjacent group is rare; the branch is warp-uniform
     return zf;
 }
 
@@ -262,7 +260,7 @@ HEXB_HD uint32_t relabel_flags(uint32_t x, uint32_t prm) {
 // in one sweep. The two requests touch disjoint byte values (the owner bit is part of the byte), so their order is free.
 // Usually only one of the two plies merges groups, and only two of them: the branches below are warp-uniform.
 template <int N>
-HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t prmB, int lane) {
+HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t prmB, int lane, uint32_t one) {
     constexpr int C = Geo<N>::C;
     const int rs = r * C, re = rs + C;
     const int wl = (re - 1) >> 2;
@@ -274,11 +272,11 @@ HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t pr
         const uint32_t rm = row_mask<N>(rs, re, w);
         uint32_t x2 = x;
         if (prmA & P_NEED) {
-            const uint32_t mk = ((relabel_flags(x, prmA) >> 7) * 0xffu) & rm;
+            const uint32_t mk = sign_fill(relabel_flags(x, prmA, one)) & rm;
             x2 = (x2 & ~mk) | (splat((prmA >> 16) & 0xffu) & mk);
         }
         if (prmB & P_NEED) {
-            const uint32_t mk = ((relabel_flags(x, prmB) >> 7) * 0xffu) & rm;
+            const uint32_t mk = sign_fill(relabel_flags(x, prmB, one)) & rm;
             x2 = (x2 & ~mk) | (splat((prmB >> 16) & 0xffu) & mk);
         }
         if (x2 != x) lab32[w] = x2;
@@ -341,7 +339,7 @@ HEXB_HD void row_job_lane(uint8_t *chunk, int r, uint32_t prmA, uint32_t prmB, u
         sync();
     }
     if (flg & F_RESET) clear_row_lane<N>(lab32, r, flg, lane);
-    else if (flg & F_RELABEL) relabel_row_lane<N>(lab32, r, prmA, prmB, lane);
+    else if (flg & F_RELABEL) relabel_row_lane<N>(lab32, r, prmA, prmB, lane, P.one);
 }
 
 // ---------------------------------------------------------------------------------------------- encode (one lane's share)
@@ -356,12 +354,17 @@ HEXB_HD void store_tail(uint8_t *base, long long off, long long limit, const Vec
     for (int k = 0; k < 16; ++k)
         if (off + k < limit) base[off + k] = (uint8_t)(a[k >> 2] >> (8 * (k & 3)));
 }
+template <int VARIANT>
+HEXB_HD void encode_vec_v(const Vec4 &in, uint32_t one, Vec4 &o, Vec4 &m) {
+    encode_word_v<VARIANT>(in.x, one, o.x, m.x);
+    encode_word_v<VARIANT>(in.y, one, o.y, m.y);
+    encode_word_v<VARIANT>(in.z, one, o.z, m.z);
+    encode_word_v<VARIANT>(in.w, one, o.w, m.w);
+}
 template <int N>
 HEXB_HD void encode_vec(const Vec4 &in, int variant, Vec4 &o, Vec4 &m) {
-    encode_word(in.x, variant, o.x, m.x);
-    encode_word(in.y, variant, o.y, m.y);
-    encode_word(in.z, variant, o.z, m.z);
-    encode_word(in.w, variant, o.w, m.w);
+    if (variant == VARIANT_B) encode_vec_v<VARIANT_B>(in, 1u, o, m);
+    else encode_vec_v<VARIANT_A>(in, 1u, o, m);
 }
 
 }  // namespace hexb

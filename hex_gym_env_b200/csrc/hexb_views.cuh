@@ -7,14 +7,17 @@
 namespace hexb {
 
 struct View {
-    const uint8_t *labels;
-    const uint32_t *rec;
+    const uint8_t *state;
     long long G, Gpad;
     int N, variant, raw;
 };
+HEXB_HD const uint32_t *view_rec(const View &V, long long g) {
+    return reinterpret_cast<const uint32_t *>(V.state + rec_offset(g, V.N * V.N));
+}
+HEXB_HD const uint8_t *view_labels(const View &V, long long g) { return V.state + labels_offset(g, V.N * V.N); }
 HEXB_HD uint32_t view_meta(const View &V, long long g) {
     const int W = (V.N * V.N + 31) / 32;
-    return V.rec[(long long)(2 * W) * V.Gpad + g];
+    return view_rec(V, g)[(2 * W) * kRecStride];
 }
 
 // K5: obs + mask of the current state. view 0: the agent's (stored orientation, or the opponent's for an episode the
@@ -30,7 +33,7 @@ HEXB_HD void encode_at(const View &V, int view, long long i, int8_t *obs, uint8_
         else opp = (meta & M_DONE) && (meta & M_AGENT_ENDED);
     }
     const int y = c / V.N, x = c - y * V.N;
-    const uint32_t b = V.labels[g * C + (opp ? x * V.N + y : c)];
+    const uint32_t b = view_labels(V, g)[opp ? x * V.N + y : c];
     uint32_t mk;
     const uint32_t ob = encode_byte(b, V.variant, opp, mk);
     if (obs) obs[i] = (int8_t)ob;
@@ -41,11 +44,12 @@ HEXB_HD void encode_at(const View &V, int view, long long i, int8_t *obs, uint8_
 template <int N>
 HEXB_HD void sample_at(const View &V, int view, long long g, const double *u, int32_t *out) {
     constexpr int W = Geo<N>::W;
-    const uint32_t meta = V.rec[(long long)(2 * W) * V.Gpad + g];
+    const uint32_t *rw = view_rec(V, g);
+    const uint32_t meta = rw[(2 * W) * kRecStride];
     const bool opp = V.variant == VARIANT_B && (view == 1 || V.raw) && (meta & M_TOMOVE);
     uint32_t occ[W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) occ[w] = V.rec[(long long)((opp ? W : 0) + w) * V.Gpad + g];
+    for (int w = 0; w < W; ++w) occ[w] = rw[((opp ? W : 0) + w) * kRecStride];
     const int n = count_empty<N>(occ);
     out[g] = n > 0 ? select_kth_zero<N>(occ, choice_of(u[g], n)) : -1;
 }
@@ -62,7 +66,7 @@ HEXB_HD void export_at(const View &V, long long i, double *board, double *region
     const uint32_t meta = view_meta(V, g);
     const int tr = (meta & M_TRANSPOSED) ? 1 : 0;
     const int sp = pl ^ tr;  // stored player that is true colour `pl`
-    const uint8_t *L = V.labels + g * C;
+    const uint8_t *L = view_labels(V, g);
     if (regions) {
         const uint32_t far = (meta & (sp ? M_FAR_C1 : M_FAR_R1)) ? 1u : 2u;
         uint32_t v = 0;
@@ -99,7 +103,7 @@ HEXB_HD void export_at(const View &V, long long i, double *board, double *region
             winner[g] = (int8_t)(w == 0u ? -1 : (int)((w - 1u) ^ (uint32_t)tr));
         }
         if (agent) agent[g] = (int8_t)tr;
-        if (draws) draws[g] = V.rec[(long long)(2 * W + 1) * V.Gpad + g];
+        if (draws) draws[g] = view_rec(V, g)[(2 * W + 1) * kRecStride];
     }
 }
 
@@ -107,7 +111,7 @@ HEXB_HD void export_at(const View &V, long long i, double *board, double *region
 template <int N>
 HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true, const int8_t *to_move) {
     constexpr int C = Geo<N>::C;
-    uint8_t *L = P.labels + g * C;
+    uint8_t *L = P.state + labels_offset(g, C);
     Rec<N> rec;
 #pragma unroll
     for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
@@ -123,7 +127,7 @@ HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true,
             for (int k = 0; k < C; ++k) L[k] = (uint8_t)relabel_byte(L[k], prm);
     }
     if (to_move && to_move[g]) rec.meta |= M_TOMOVE;
-    store_rec<N>(P, g, rec);
+    store_rec<N>(reinterpret_cast<uint32_t *>(P.state + rec_offset(g, C)), rec);
 }
 
 }  // namespace hexb

@@ -65,8 +65,9 @@ int32_t hexb_version(void);
 const char *hexb_strerror(int32_t code);
 int32_t hexb_last_cuda_error(void);
 
-/* Bytes of packed device state for `cfg` (0 on a bad config). Layout: label bytes [Gpad][N*N] u8, then the
- * per-game record words [R][Gpad] u32 (occupancy bitboards, counters, flags, draw index), then int64[8] stats. */
+/* Bytes of packed device state for `cfg` (0 on a bad config). Layout (chunk-major): per chunk of 32 games the label bytes
+ * u8[32][N*N] followed by the record words u32[R][32] (occupancy bitboards, counters, flags, draw index); then striped
+ * int64[128][8] statistics. */
 size_t hexb_state_bytes(const hexb_config *cfg);
 
 /* Create a handle over caller-allocated, 256-byte-aligned device memory and zero it on `stream`.

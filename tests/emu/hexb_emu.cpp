@@ -27,15 +27,17 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 template <int N>
 static void run_tiles(Params P) {
     constexpr int C = Geo<N>::C;
-    std::vector<uint8_t> smem(Chunk<N>::BYTES + 16);
+    std::vector<uint8_t> smem(Geo<N>::CHUNK_STATE + 16);
     uint8_t *chunk = smem.data() + ((16 - ((uintptr_t)smem.data() & 15)) & 15);
     std::vector<Rec<N>> recs(kWarp);
     std::vector<Loc> locs(kWarp);
     uint32_t prmA[kWarp], prmB[kWarp], flg[kWarp];
     for (long long g0 = 0; g0 < P.Gpad; g0 += kWarp) {   // one "warp" = one chunk of 32 games at a time
-        memcpy(chunk, P.labels + g0 * C, Chunk<N>::BYTES);
+        uint8_t *gl = P.state + (g0 / kWarp) * Geo<N>::CHUNK_STATE;
+        memcpy(chunk, gl, Geo<N>::CHUNK_STATE);
+        uint32_t *recw = reinterpret_cast<uint32_t *>(chunk + Geo<N>::CHUNK_LAB);
         for (int t = 0; t < kWarp; ++t) {
-            load_rec<N>(P, g0 + t, recs[t]);
+            load_rec<N>(recw + t, recs[t]);
             prmA[t] = prmB[t] = flg[t] = 0;
         }
         for (int t = 0; t < kWarp; ++t) {   // thread-per-game phase
@@ -43,7 +45,7 @@ static void run_tiles(Params P) {
             uint8_t *L = chunk + t * C;
             if (P.mode == MODE_STEP) {
                 double ua = 0.0, uo = 0.0;
-                if (g < P.G) pre_draws<N>(P, recs[t], (unsigned long long)(P.game_offset + g), ua, uo);
+                if (g < P.G) pre_draws(P, recs[t].meta, recs[t].draws, (unsigned long long)(P.game_offset + g), ua, uo);
                 game_step<N>(L, P, g, recs[t], ua, uo, locs[t], prmA[t], prmB[t], flg[t]);
                 for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
             } else if (P.mode == MODE_RESET) {
@@ -51,7 +53,7 @@ static void run_tiles(Params P) {
             } else {
                 game_ply<N>(L, P, g, recs[t], prmA[t], flg[t]);
             }
-            if (g < P.G) store_rec<N>(P, g, recs[t]);
+            if (g < P.G) store_rec<N>(recw + t, recs[t]);
         }
         for (int r = 0; r < kWarp; ++r) {   // warp-per-game row jobs; a lane-level barrier = finish the loop over lanes
             if (!(flg[r] & F_ROWJOB)) continue;
@@ -73,7 +75,7 @@ static void run_tiles(Params P) {
                 if (flg[r] & F_VIEW_OPP)
                     for (int lane = 0; lane < kWarp; ++lane) view_row_lane<N>(chunk, r, P, g0 + r, lane);
         }
-        memcpy(P.labels + g0 * C, chunk, Chunk<N>::BYTES);
+        memcpy(gl, chunk, Geo<N>::CHUNK_STATE);
     }
 }
 
@@ -90,8 +92,7 @@ static void dispatch(const emu_env *e, const Params &P) {
 
 static View view_of(const emu_env *e) {
     View V;
-    V.labels = e->base.labels;
-    V.rec = e->base.rec;
+    V.state = e->base.state;
     V.G = e->base.G;
     V.Gpad = e->base.Gpad;
     V.N = e->N;
@@ -107,20 +108,19 @@ void *emu_create(int N, int variant, long long G, long long game_offset, unsigne
     if (N < 3 || N > 19 || G < 1) return nullptr;
     emu_env *e = new emu_env();
     e->N = N;
-    const long long C = (long long)N * N, W = (C + 31) / 32, R = 2 * W + 2;
+    const long long C = (long long)N * N;
     const long long Gpad = (G + kTile - 1) / kTile * kTile;
-    const size_t rec_off = align256((size_t)(Gpad * C)), stats_off = rec_off + align256((size_t)(R * Gpad * 4));
+    const size_t stats_off = align256((size_t)(Gpad / 32 * chunk_state_bytes((int)C)));
     e->state.assign(stats_off + 256 + 256, 0);
     uint8_t *base = e->state.data();
     base += (256 - ((uintptr_t)base & 255)) & 255;
     Params &P = e->base;
     memset(&P, 0, sizeof(P));
-    P.labels = base;
-    P.rec = (uint32_t *)(base + rec_off);
+    P.state = base;
     P.stats = (long long *)(base + stats_off);
     P.G = G; P.Gpad = Gpad; P.game_offset = game_offset; P.seed = seed;
     P.variant = variant; P.auto_reset = auto_reset; P.eval_state = eval_state; P.opponent_first = opponent_first;
-    P.agent_mode = agent_mode; P.raw = raw;
+    P.agent_mode = agent_mode; P.raw = raw; P.one = 1u;
     return e;
 }
 void emu_destroy(void *h) { delete (emu_env *)h; }
