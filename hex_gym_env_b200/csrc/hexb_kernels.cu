@@ -58,10 +58,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // ------------------------------------------------------------------------------------------------ step kernel
 // One warp = one chunk of 32 games; a CTA is 4 independent warps (no __syncthreads anywhere). Per warp:
 //   lane 0 starts ONE bulk asynchronous copy (cp.async.bulk = the 1-D TMA path, completion on the warp's own mbarrier)
-//   of the chunk's 32*C label bytes into shared memory; meanwhile every lane loads its game's record words (coalesced,
-//   [word][game] layout) and runs the Philox rounds of the step's two draws; then the thread-per-game plies, the
-//   warp-per-game row jobs, the elementwise obs/mask encode with 16-byte coalesced stores, the record stores and one
-//   bulk copy of the chunk back to global memory.
+//   of the chunk (32 games' label bytes + record words, one contiguous block) into shared memory; meanwhile every lane
+//   fetches its game's meta / stream-position words and runs the Philox rounds of the step's two draws; then the
+//   thread-per-game plies, the rare finished-game rows, the elementwise obs/mask encode with 16-byte coalesced stores, the
+//   warp-per-game relabel sweeps, and one bulk copy of the chunk back to global memory.
 #ifndef HEXB_WARPS_PER_CTA
 #define HEXB_WARPS_PER_CTA 4
 #endif
@@ -217,17 +217,18 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     if (g < P.G) store_rec<N>(recw, rec);
     __syncwarp();  // every game's new stones and record are in shared memory
 
-    // ---- warp-per-game row jobs: relabel / terminal observation / clear + opening stone
-    uint32_t pending = __ballot_sync(FULL, (flg & F_ROWJOB) != 0u);
+    // ---- warp-per-game row jobs, part 1 (rare): games that finished - terminal observation, clear, opening stone
+    uint32_t pending = __ballot_sync(FULL, (flg & (F_RESET | F_TERM)) != 0u);
     while (pending) {
         const int r = __ffs(pending) - 1;
         pending &= pending - 1;
-        const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r), rf = __shfl_sync(FULL, flg, r);
-        row_job_lane<N>(chunk, r, ra, rb, rf, P, g0 + r, lane, [] { __syncwarp(); });
+        const uint32_t rf = __shfl_sync(FULL, flg, r);
+        row_job_lane<N>(chunk, r, 0u, 0u, rf & ~F_RELABEL, P, g0 + r, lane, [] { __syncwarp(); });
         __syncwarp();
     }
 
-    // ---- observation + mask
+    // ---- observation + mask. They depend on emptiness and owner bits only, not on the labels, so they are issued BEFORE
+    //      the relabel sweeps: the output stores drain to HBM while the warp works through its relabel rows.
     if (P.mode != MODE_PLY && (P.obs || P.mask)) {
         encode_chunk<N>(chunk, P, g0, lane);
         uint32_t views = __ballot_sync(FULL, (flg & F_VIEW_OPP) != 0u);  // only without auto-reset: finished by the agent's own ply
@@ -237,6 +238,16 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
             views &= views - 1;
             view_row_lane<N>(chunk, r, P, g0 + r, lane);
         }
+    }
+
+    // ---- warp-per-game row jobs, part 2: relabel sweeps (regions[regions == label] = new label, both plies at once)
+    pending = __ballot_sync(FULL, (flg & (F_RELABEL | F_RESET)) == F_RELABEL);
+    while (pending) {
+        const int r = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r);
+        relabel_row_lane<N>(reinterpret_cast<uint32_t *>(chunk), r, ra, rb, lane, P.one);
+        __syncwarp();   // (sweeping two non-adjacent rows per iteration for ILP was measured: slower, 114 vs 111 us)
     }
 
     // ---- chunk out
