@@ -40,7 +40,8 @@ class HexbConfig(ctypes.Structure):
     _fields_ = [("board_size", ctypes.c_int32), ("variant", ctypes.c_int32), ("num_games", ctypes.c_int64),
                 ("game_offset", ctypes.c_int64), ("seed", ctypes.c_uint64), ("agent_mode", ctypes.c_int32),
                 ("opponent_first", ctypes.c_int32), ("auto_reset", ctypes.c_int32), ("eval_state", ctypes.c_int32),
-                ("raw", ctypes.c_int32), ("device", ctypes.c_int32)]
+                ("raw", ctypes.c_int32), ("device", ctypes.c_int32), ("manual_opponent", ctypes.c_int32),
+                ("pool_size", ctypes.c_int32)]
 
 
 # every symbol include/hexb.h declares: name -> (restype, argtypes)
@@ -63,6 +64,8 @@ SYMBOLS = {
     "hexb_export_state": (_i32, [_vp] * 10),
     "hexb_import_boards": (_i32, [_vp] * 4),
     "hexb_stats": (_i32, [_vp] * 3),
+    "hexb_set_opponent_buffers": (_i32, [_vp, _vp, _vp]),
+    "hexb_half_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "hexb_masked_sample": (_i32, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp, _vp, _vp, _i32, _vp]),
 }
 

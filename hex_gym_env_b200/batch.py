@@ -36,7 +36,8 @@ def _ptr(t):
 
 class HexBatch(object):
     def __init__(self, board_size, num_games, variant=VARIANT_B, device=None, seed=0, game_offset=0,
-                 agent_mode=AGENT_BLACK, opponent_first=False, auto_reset=True, eval_state=False, raw=False):
+                 agent_mode=AGENT_BLACK, opponent_first=False, auto_reset=True, eval_state=False, raw=False,
+                 manual_opponent=False, pool_size=0):
         self._h = None
         self._lib = _native.lib()  # raises if libhexb.so cannot be built / loaded
         if not torch.cuda.is_available():
@@ -49,7 +50,8 @@ class HexBatch(object):
         self.cfg = HexbConfig(board_size=self.N, variant=self.variant, num_games=self.G, game_offset=int(game_offset),
                               seed=int(seed) & 0xFFFFFFFFFFFFFFFF, agent_mode=int(agent_mode), opponent_first=int(bool(opponent_first)),
                               auto_reset=int(bool(auto_reset)), eval_state=int(bool(eval_state)), raw=int(bool(raw)),
-                              device=self.device.index)
+                              device=self.device.index, manual_opponent=int(bool(manual_opponent)), pool_size=int(pool_size))
+        self.manual_opponent = bool(manual_opponent)
         nbytes = self._lib.hexb_state_bytes(ctypes.byref(self.cfg))
         if nbytes == 0:
             raise ValueError("unsupported configuration: board_size=%r num_games=%r variant=%r agent_mode=%r"
@@ -63,6 +65,11 @@ class HexBatch(object):
             check(self._lib.hexb_create(ctypes.byref(self.cfg), ctypes.c_void_p(self._state_ptr), self.state_bytes,
                                         self._stream(), ctypes.byref(h)))
         self._h = h
+        self.opp_index = self.to_move = None
+        if manual_opponent:  # per-game opponent bookkeeping, written by every reset / half step
+            self.opp_index = torch.full((self.G,), -1, dtype=torch.int32, device=self.device)
+            self.to_move = torch.full((self.G,), 2, dtype=torch.uint8, device=self.device)
+            check(self._lib.hexb_set_opponent_buffers(self._h, _ptr(self.opp_index), _ptr(self.to_move)))
         self._out = {}
         self._ws = None
         self._pinned = None
@@ -180,6 +187,46 @@ class HexBatch(object):
                                            _ptr(io["obs"]) if want_obs else None, _ptr(io["mask"]) if want_mask else None,
                                            _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
         return io
+
+    # ------------------------------------------------------------------ learned opponent (manual_opponent=True)
+    def half_step(self, side, actions, reward=None, done=None, term_obs=None, want_term=False):
+        """One ply of `side` (0 agent, 1 opponent) in every game whose turn it is; actions i32[G] in the mover's own view.
+        Returns dict(reward, done [, term_obs]); self.to_move / self.opp_index are updated in place."""
+        G, N = self.G, self.N
+        a = self._in(actions, (G,), torch.int32, "actions")
+        reward = self._chk(reward, (G,), torch.float32, "reward") if reward is not None else self._buf("h_reward%d" % side, (G,), torch.float32)
+        done = self._chk(done, (G,), torch.uint8, "done") if done is not None else self._buf("h_done%d" % side, (G,), torch.uint8)
+        if term_obs is not None:
+            term_obs = self._chk(term_obs, (G, N, N), torch.int8, "term_obs")
+        elif want_term:
+            term_obs = self._buf("term_obs", (G, N, N), torch.int8)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_half_step(self._h, int(side), _ptr(a), _ptr(reward), _ptr(done), _ptr(term_obs), self._stream()))
+        out = dict(reward=reward, done=done)
+        if term_obs is not None:
+            out["term_obs"] = term_obs
+        return out
+
+    def step_with_opponent(self, actions, opponent_fn, want_term=False):
+        """One env step against a learned opponent, all on the device: agent ply, then up to two opponent plies (the reply,
+        and the opening move of a game that restarted with the opponent to move). `opponent_fn(obs i8[G,N,N], mask u8[G,C],
+        to_move u8[G], opp_index i32[G]) -> actions i32[G]` sees the side-to-move view (what OpponentPolicy.choose_action gets,
+        SelfplayWrapper.py:161) and must answer for the games with to_move == 1; its other entries are ignored."""
+        G, N, C = self.G, self.N, self.C
+        term = self._buf("sw_term", (G, N, N), torch.int8) if want_term else None
+        h = self.half_step(0, actions, term_obs=term)
+        reward, done = h["reward"].clone(), h["done"].clone()
+        o1, m1 = self._buf("opp_obs", (G, N, N), torch.int8), self._buf("opp_mask", (G, C), torch.uint8)
+        for _ in range(2):
+            self.encode(1, obs=o1, mask=m1)
+            h = self.half_step(1, opponent_fn(o1, m1, self.to_move, self.opp_index), term_obs=term)
+            reward += h["reward"]
+            done |= h["done"]
+        obs, mask = self.encode(0)
+        out = dict(obs=obs, mask=mask, reward=reward, done=done)
+        if want_term:
+            out["term_obs"] = term
+        return out
 
     # ------------------------------------------------------------------ the pieces on their own
     def ply(self, actions, ret=None):

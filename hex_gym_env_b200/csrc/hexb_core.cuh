@@ -38,7 +38,7 @@ namespace hexb {
 constexpr int kTile = 128;  // games per CTA == threads per CTA (4 warps, each owning a chunk of 32 games)
 
 enum : int { VARIANT_A = 0, VARIANT_B = 1 };
-enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_PLY = 2 };
+enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_PLY = 2, MODE_HALF = 3 };
 
 // meta word
 constexpr uint32_t M_CTR_R_SHIFT = 0;   // bits 0-7   region_counter of R
@@ -102,6 +102,11 @@ struct Params {
     unsigned long long seed;
     int variant, auto_reset, eval_state, opponent_first, agent_mode, mode;
     int raw;  // 1: bare HexGame batch (hexb_ply): reset draws nothing and nobody opens
+    int manual_opponent;  // 1: the opponent's moves come from the caller (hexb_half_step); resets never play the opening move
+    int half_side;        // MODE_HALF: 0 = the agent's ply, 1 = the opponent's ply
+    int pool_size;        // setup_opponents: size of the opponent pool the index is drawn from
+    int32_t *opp_index;   // [G] nullable: opponent chosen at reset, -1 = best model, k = pool entry (SelfplayWrapper.py:97-103)
+    uint8_t *to_move;     // [G] MODE_HALF / MODE_RESET out: 0 agent to move, 1 opponent to move, 2 finished
     uint32_t one;  // always 1, but opaque to the compiler: a * one + b is issued as IMAD on the FMA pipe (see fma_add)
     // borrowed I/O (device pointers, any may be null unless noted)
     const int32_t *actions;    // [G]   null => sample the agent's move on device (one draw)
@@ -367,15 +372,22 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
             if (P.agent_mode == 2) colour = (int)(draw01(P.seed, gid, rec.draws++) * 2.0);
             meta |= M_COLOUR_SET | (colour ? M_TRANSPOSED : 0u);
         }
-        if (!inj_u && !P.eval_state) {  // setup_opponents (:97-103): every pool entry is a random policy, only the draws count
+        if (!inj_u && !P.eval_state) {  // setup_opponents (:97-103): 80 % the best model, else a uniformly drawn pool entry
             const double rv = draw01(P.seed, gid, rec.draws++);
-            if (!(rv < 0.8)) rec.draws++;
+            int pick = -1;
+            if (!(rv < 0.8)) {
+                const double ui = draw01(P.seed, gid, rec.draws++);
+                pick = P.pool_size > 0 ? choice_of(ui, P.pool_size) : -1;
+            }
+            if (P.opp_index) P.opp_index[gid - (unsigned long long)P.game_offset] = pick;
         }
         opp_opens = (meta & M_TRANSPOSED) != 0u;  // agent WHITE: BLACK (the opponent) opens (:79-80)
     } else {
         opp_opens = P.opponent_first != 0;  // HexGame.py:224-230
     }
-    if (opp_opens) {
+    if (opp_opens && P.manual_opponent) {
+        meta |= M_TOMOVE;  // the caller's opponent policy opens: nothing is placed here
+    } else if (opp_opens) {
         double u;
         if (inj_u) u = *inj_u;
         else {
@@ -392,7 +404,7 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
         set_bit<N>(rec.occ_cm, k);
         flg |= F_OPEN | ((lab | 0x80u) << 8) | ((uint32_t)(y * N + x) << 16);
     }
-    rec.meta = meta;  // R (the agent) to move
+    rec.meta = meta;  // R (the agent) to move unless a caller-driven opponent opens
     flg |= F_RESET;
 }
 

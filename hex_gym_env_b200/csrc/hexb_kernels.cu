@@ -132,6 +132,22 @@ __device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params 
     }
 }
 
+// K7: lane 0 adds the warp's packed, reduced statistics (see the packing at the call sites) to the warp's stripe
+__device__ __forceinline__ void add_stats(const Params &P, long long wglobal, int lane, uint32_t sa, uint32_t sb) {
+    if (lane != 0) return;
+    unsigned long long *stripe = reinterpret_cast<unsigned long long *>(P.stats) + 8 * (wglobal & (kStatStripes - 1));
+    if (sa) {
+        if (sa & 63u) atomicAdd(stripe + 0, (unsigned long long)(sa & 63u));
+        if ((sa >> 6) & 63u) atomicAdd(stripe + 1, (unsigned long long)((sa >> 6) & 63u));
+        if ((sa >> 12) & 63u) atomicAdd(stripe + 2, (unsigned long long)((sa >> 12) & 63u));
+        if ((sa >> 18) & 63u) atomicAdd(stripe + 3, (unsigned long long)((sa >> 18) & 63u));
+        if ((sa >> 24) & 63u) atomicAdd(stripe + 5, (unsigned long long)((sa >> 24) & 63u));
+        atomicAdd(stripe + 4, (unsigned long long)(sb & 0x3fffu));
+    }
+    if ((sb >> 14) & 63u) atomicAdd(stripe + 6, (unsigned long long)((sb >> 14) & 63u));
+    if (sb >> 20) atomicAdd(stripe + 7, (unsigned long long)(sb >> 20));
+}
+
 template <int N>
 __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(const Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -195,22 +211,16 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) | ((uint32_t)loc.st[3] << 18) |
                             ((uint32_t)loc.st[5] << 24);
         const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
-        const uint32_t sa = __reduce_add_sync(FULL, pa), sb = __reduce_add_sync(FULL, pb);
-        if (lane == 0) {
-            unsigned long long *stripe = reinterpret_cast<unsigned long long *>(P.stats) + 8 * (wglobal & (kStatStripes - 1));
-            if (sa) {
-                if (sa & 63u) atomicAdd(stripe + 0, (unsigned long long)(sa & 63u));
-                if ((sa >> 6) & 63u) atomicAdd(stripe + 1, (unsigned long long)((sa >> 6) & 63u));
-                if ((sa >> 12) & 63u) atomicAdd(stripe + 2, (unsigned long long)((sa >> 12) & 63u));
-                if ((sa >> 18) & 63u) atomicAdd(stripe + 3, (unsigned long long)((sa >> 18) & 63u));
-                if ((sa >> 24) & 63u) atomicAdd(stripe + 5, (unsigned long long)((sa >> 24) & 63u));
-                atomicAdd(stripe + 4, (unsigned long long)(sb & 0x3fffu));
-            }
-            if ((sb >> 14) & 63u) atomicAdd(stripe + 6, (unsigned long long)((sb >> 14) & 63u));
-            if (sb >> 20) atomicAdd(stripe + 7, (unsigned long long)(sb >> 20));
-        }
+        add_stats(P, wglobal, lane, __reduce_add_sync(FULL, pa), __reduce_add_sync(FULL, pb));
     } else if (P.mode == MODE_RESET) {
         game_reset<N>(P, g, rec, flg);
+    } else if (P.mode == MODE_HALF) {
+        Loc loc;
+        game_half<N>(L, P, g, rec, loc, prmA, prmB, flg);
+        const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) | ((uint32_t)loc.st[3] << 18) |
+                            ((uint32_t)loc.st[5] << 24);
+        const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
+        add_stats(P, wglobal, lane, __reduce_add_sync(FULL, pa), __reduce_add_sync(FULL, pb));
     } else {
         game_ply<N>(L, P, g, rec, prmA, flg);
     }
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
 
     // ---- observation + mask. They depend on emptiness and owner bits only, not on the labels, so they are issued BEFORE
     //      the relabel sweeps: the output stores drain to HBM while the warp works through its relabel rows.
-    if (P.mode != MODE_PLY && (P.obs || P.mask)) {
+    if (P.mode != MODE_PLY && P.mode != MODE_HALF && (P.obs || P.mask)) {
         encode_chunk<N>(chunk, P, g0, lane);
         uint32_t views = __ballot_sync(FULL, (flg & F_VIEW_OPP) != 0u);  // only without auto-reset: finished by the agent's own ply
         if (views) __syncwarp();
@@ -392,6 +402,7 @@ static bool cfg_ok(const hexb_config *c) {
     if (c->num_games < 1 || c->game_offset < 0) return false;
     if (c->agent_mode < 0 || c->agent_mode > 2) return false;
     if (c->variant == HEXB_VARIANT_A && c->agent_mode != HEXB_AGENT_BLACK) return false;
+    if (c->pool_size < 0 || (c->manual_opponent && c->raw)) return false;
     return true;
 }
 
@@ -414,7 +425,7 @@ static Layout layout_of(const hexb_config *c) {
 
 extern "C" {
 
-int32_t hexb_version(void) { return (1 << 16) | 0; }
+int32_t hexb_version(void) { return (1 << 16) | 1; }
 
 const char *hexb_strerror(int32_t code) {
     switch (code) {
@@ -455,6 +466,8 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     P.opponent_first = cfg->opponent_first;
     P.agent_mode = cfg->agent_mode;
     P.raw = cfg->raw;
+    P.manual_opponent = cfg->manual_opponent;
+    P.pool_size = cfg->pool_size;
     P.one = 1u;
     *out = e;
     return HEXB_OK;
@@ -509,6 +522,27 @@ static View view_of(const hexb_env *e) {
 
 extern "C" {
 
+int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to_move) {
+    if (!env) return HEXB_ERR_ARG;
+    env->base.opp_index = opp_index;
+    env->base.to_move = to_move;
+    return HEXB_OK;
+}
+
+int32_t hexb_half_step(hexb_env *env, int32_t side, const int32_t *actions, float *reward, uint8_t *done, int8_t *term_obs,
+                       void *stream) {
+    if (!env || !actions || env->cfg.raw || !env->cfg.manual_opponent || (side != 0 && side != 1)) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    Params P = env->base;
+    P.mode = MODE_HALF;
+    P.half_side = side;
+    P.actions = actions;
+    P.reward = reward;
+    P.done = done;
+    P.term_obs = term_obs;
+    return dispatch_tile(env, P, (cudaStream_t)stream);
+}
+
 int32_t hexb_reset(hexb_env *env, const uint8_t *reset_mask, const double *open_u, int8_t *obs, uint8_t *mask, void *stream) {
     if (!env) return HEXB_ERR_ARG;
     CK(cudaSetDevice(env->cfg.device));
@@ -523,7 +557,7 @@ int32_t hexb_reset(hexb_env *env, const uint8_t *reset_mask, const double *open_
 
 int32_t hexb_step(hexb_env *env, const int32_t *actions, const double *opp_u, int8_t *obs, uint8_t *mask, float *reward,
                   uint8_t *done, int8_t *term_obs, int32_t *actions_out, void *stream) {
-    if (!env || env->cfg.raw) return HEXB_ERR_ARG;
+    if (!env || env->cfg.raw || env->cfg.manual_opponent) return HEXB_ERR_ARG;
     CK(cudaSetDevice(env->cfg.device));
     Params P = env->base;
     P.mode = MODE_STEP;

@@ -182,6 +182,79 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
     if (!(flg & F_RESET) && ((prmA | prmB) & P_NEED)) flg |= F_RELABEL;
 }
 
+// ---------------------------------------------------------------------------------------------- half step (hexb_half_step)
+// One ply of ONE side for every game whose turn it is, the action coming from the caller: the agent's half of
+// SelfPlayEnv.step (SelfplayWrapper.py:174-176) or the opponent's half, continue_game (:146-172) with an OpponentPolicy
+// (:26-35) instead of the random policy - the caller runs the opponent network on the side-to-move view (hexb_encode view 1)
+// and passes its actions in the opponent's own perspective. Reward / done / statistics / auto-reset as in game_step, except
+// that a restarted game whose opponent opens is left waiting for the caller's opponent (to_move = 1).
+template <int N>
+HEXB_HD void game_half(uint8_t *L, const Params &P, long long g, Rec<N> &rec, Loc &loc, uint32_t &prmA, uint32_t &prmB, uint32_t &flg) {
+    constexpr int C = Geo<N>::C;
+    loc.reward = 0.f;
+    loc.action = -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) loc.st[i] = 0;
+    prmA = 0; prmB = 0; flg = 0;
+    if (g >= P.G) return;
+    if (!(rec.meta & M_LIVE)) {
+        if (P.reward) P.reward[g] = 0.f;
+        if (P.done) P.done[g] = 1;
+        if (P.to_move) P.to_move[g] = 2;
+        return;
+    }
+    const unsigned long long gid = (unsigned long long)(P.game_offset + g);
+    const int side = P.half_side;
+    const bool was_done = (rec.meta & M_DONE) != 0u;
+    const bool my_turn = (((rec.meta & M_TOMOVE) != 0u) == (side != 0));
+    if (!was_done && my_turn) {
+        const int a = P.actions[g];
+        loc.action = a;
+        if (side == 0) loc.st[6] = 1;                                   // an env step starts with the agent's ply
+        else if (P.variant == VARIANT_B) rec.draws++;                   // rv = random.uniform(0,1), unused (SelfplayWrapper.py:159)
+        int cell = a;
+        if (side != 0 && (unsigned)a < (unsigned)C) {                   // the opponent's view is the transpose of the stored board
+            const int x = a / N;
+            cell = (a - x * N) * N + x;
+        }
+        const bool valid = (unsigned)a < (unsigned)C && !test_bit<N>(rec.occ_rm, cell);
+        if (!valid) {  // fast_move returns 3; HexEnv.step ends the episode for either side (HexSingleGame.py:240-241, HexGame.py:252-253)
+            rec.meta |= M_DONE | M_INVALID | (side == 0 ? M_AGENT_ENDED : 0u);
+            loc.reward = (P.variant == VARIANT_A && side == 0) ? -100.f : 0.f;
+        } else {
+            const bool won = place_stone<N>(L, rec, side, cell, side == 0 ? prmA : prmB);
+            loc.st[7]++;
+            rec.meta ^= M_TOMOVE;
+            if (won) {
+                rec.meta |= M_DONE | ((uint32_t)(side + 1) << M_WIN_SHIFT) | (side == 0 ? M_AGENT_ENDED : 0u);
+                loc.reward = side == 0 ? 1.f : -1.f;
+            } else if (P.variant == VARIANT_B && count_empty<N>(rec.occ_rm) == 0) {
+                rec.meta |= M_DONE | (side == 0 ? M_AGENT_ENDED : 0u);
+            }
+        }
+    } else if (was_done && P.variant == VARIANT_A && side == 0) {
+        loc.reward = stale_reward_A(rec.meta);
+    }
+    const bool is_done = (rec.meta & M_DONE) != 0u;
+    if (is_done && !was_done) {
+        const uint32_t w = (rec.meta & M_WIN_MASK) >> M_WIN_SHIFT;
+        const bool tr = (rec.meta & M_TRANSPOSED) != 0u;
+        loc.st[0] = 1;
+        loc.st[1] = (w == 1u && !tr) || (w == 2u && tr);
+        loc.st[2] = (w == 2u && !tr) || (w == 1u && tr);
+        loc.st[3] = (w == 1u);
+        loc.st[4] = Geo<N>::C - count_empty<N>(rec.occ_rm);
+        loc.st[5] = (rec.meta & M_INVALID) != 0u;
+        // what step() returned: the board after invert_board, i.e. seen by the side that would move next
+        if (P.term_obs) flg |= F_TERM | (((rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B) ? F_TERM_OPP : 0u);
+    }
+    if (P.reward) P.reward[g] = loc.reward;
+    if (P.done) P.done[g] = is_done ? 1 : 0;
+    if (is_done && !was_done && P.auto_reset) reset_game<N>(rec, P, gid, nullptr, flg);
+    if (P.to_move) P.to_move[g] = (rec.meta & M_DONE) ? 2 : ((rec.meta & M_TOMOVE) ? 1 : 0);
+    if (!(flg & F_RESET) && ((prmA | prmB) & P_NEED)) flg |= F_RELABEL;
+}
+
 // ---------------------------------------------------------------------------------------------- raw ply (hexb_ply)
 // Batched HexGame.make_move: variant A in true coordinates (HexGame.py:85-111, no done guard); variant B with the action
 // in the mover's perspective, as HexEnv.step feeds it (HexSingleGame.py:239, 98-106).
@@ -221,6 +294,7 @@ HEXB_HD void game_reset(const Params &P, long long g, Rec<N> &rec, uint32_t &flg
     } else if ((rec.meta & M_DONE) && (rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B && !P.raw) {
         flg |= F_VIEW_OPP;
     }
+    if (P.to_move) P.to_move[g] = !(rec.meta & M_LIVE) || (rec.meta & M_DONE) ? 2 : ((rec.meta & M_TOMOVE) ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------- row jobs (one lane's share)

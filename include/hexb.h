@@ -58,6 +58,9 @@ typedef struct hexb_config {
     int32_t eval_state;     /* variant B: SelfPlayEnv.set_eval(True): setup_opponents draws nothing (SelfplayWrapper.py:92-96) */
     int32_t raw;            /* 1: bare HexGame batch for hexb_ply (no opponent, no draws) */
     int32_t device;         /* CUDA device ordinal */
+    int32_t manual_opponent;/* 1: the opponent is the caller's policy (OpponentPolicy, SelfplayWrapper.py:26-35): use
+                               hexb_half_step instead of hexb_step; resets leave the opening move to the caller */
+    int32_t pool_size;      /* opponent pool size for the index drawn in setup_opponents (SelfplayWrapper.py:97-103); 0 = none */
 } hexb_config;
 
 /* Library / ABI version (major << 16 | minor). */
@@ -136,6 +139,22 @@ int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t
  * [5] episodes ended by an illegal agent move, [6] env steps, [7] plies. Copies them to out8 (device). The multi-GPU
  * layer all-reduces this vector with NCCL; nothing else ever crosses GPUs. */
 int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream);
+
+/* Split step for a learned opponent. On a manual_opponent=1 handle one env step is
+ *   hexb_half_step(side 0, agent actions)  ->  hexb_encode(view 1) for the games with to_move == 1  ->  opponent network  ->
+ *   hexb_half_step(side 1, opponent actions)  [twice: a game the opponent just won restarts, and if the opponent also opens the
+ *   new episode it needs the opening move]
+ * hexb_half_step plays ONE ply of `side` (0 agent, 1 opponent) in every live, unfinished game whose turn it is: the agent's half
+ * of SelfPlayEnv.step (SelfplayWrapper.py:174-176, HexSingleGame.py:233-263) or continue_game (:146-172) with the action supplied
+ * by the caller in the mover's own perspective (exactly what OpponentPolicy.choose_action returns). Other games are untouched.
+ * reward f32[G]: this ply's reward for the AGENT (+1 agent won, -1 opponent won, 0; variant A: -100 illegal agent move); done u8[G];
+ * term_obs as in hexb_step (each nullable). Finished games auto-reset if configured; a restarted game whose opponent opens
+ * waits for the caller. hexb_set_opponent_buffers registers two optional per-game outputs written by every reset and half step:
+ * opp_index i32[G] (the opponent setup_opponents chose: -1 best model, k pool entry) and to_move u8[G] (0 agent, 1 opponent,
+ * 2 finished). */
+int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to_move);
+int32_t hexb_half_step(hexb_env *env, int32_t side, const int32_t *actions, float *reward, uint8_t *done, int8_t *term_obs,
+                       void *stream);
 
 /* Masked categorical sampling for a batch of policy outputs (the rollout feed of SURVEY.md section 8f, row 1). Replaces what
  * sb3_contrib's MaskableCategoricalDistribution does between MaskablePPO's policy network and env.step in the reference's

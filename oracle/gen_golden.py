@@ -13,6 +13,8 @@ Fixture families
                          agent either sampled by BaseRandomPolicy from the same stream ("fused") or given
                          externally (with some illegal moves)
   envA_N*_of*.npz        variant-A HexEnv(opponent_policy=minihex.random_policy) rollouts, same two agent modes
+  oppmodel_N*_a*.npz     SelfPlayEnv with OpponentPolicy opponents (scripted stand-ins for SB3 models, oracle/scripted.py): the
+                         learned-opponent path incl. the 80/20 best/pool choice of setup_opponents and the opponent's observation
   kat.npz                the four hand-checked known-answer tests of SURVEY.md section 8c
 """
 import os
@@ -123,6 +125,51 @@ def rollout(kind, N, G, T, seed, agent_mode, fused, opponent_first=False, illega
     return out
 
 
+def rollout_scripted_opponent(N, G, T, seed, agent_mode, pool, illegal_rate=0.04):
+    """SelfPlayEnv whose opponents are OpponentPolicy objects (SelfplayWrapper.py:26-35) around scripted models: the
+    learned-opponent path (setup_opponents' 80/20 choice, continue_game with action masks). One env per game."""
+    from oracle.scripted import ScriptedModel
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed ^ 0xBEEF)
+    C = N * N
+    out = dict(actions=np.zeros((T, G), np.int32), opp_actions=-np.ones((T, G, 2), np.int32), opp_model=-9 * np.ones((T, G, 2), np.int32),
+               opp0_action=-np.ones(G, np.int32), opp0_model=-9 * np.ones(G, np.int32),
+               obs=np.zeros((T, G, N, N), np.int8), mask=np.zeros((T, G, C), np.uint8), reward=np.zeros((T, G), np.float32),
+               done=np.zeros((T, G), np.uint8), term_obs=np.zeros((T, G, N, N), np.int8),
+               regions=np.zeros((T, G, 2, N + 2, N + 2), np.uint8), counter=np.zeros((T, G, 2), np.int16),
+               sim_cur=np.zeros((T, G), np.int8), draws=np.zeros((T, G), np.uint32), obs0=np.zeros((G, N, N), np.int8),
+               mask0=np.zeros((G, C), np.uint8), agent=np.zeros(G, np.int8), draws0=np.zeros(G, np.uint32))
+    for gi in range(G):
+        stream = GameStream(seed, gi)
+        rh.set_rng(stream)
+        log = []
+        env = S.selfplay_wrapper(B.HexEnv)(base_model=ScriptedModel(-1, log), scores=np.zeros(pool), board_size=N, buffer_size=pool,
+                                           agent_player_num=None if agent_mode == 2 else agent_mode)
+        for k in range(pool):
+            env.opponent_models[k] = S.OpponentPolicy(ScriptedModel(k, log))
+        obs, _ = env.reset()
+        if log:
+            out["opp0_model"][gi], out["opp0_action"][gi] = log[0]
+        del log[:]
+        out["obs0"][gi], out["mask0"][gi], out["agent"][gi], out["draws0"][gi] = obs, env.legal_actions(), env.agent_player_num, stream.idx
+        for t in range(T):
+            legal = np.flatnonzero(env.legal_actions())
+            a = int(rs.randint(C)) if rs.rand() < illegal_rate else int(legal[rs.randint(len(legal))])
+            obs, r, done, _, _ = env.step(a)
+            out["actions"][t, gi], out["reward"][t, gi], out["done"][t, gi] = a, r, done
+            if done:
+                out["term_obs"][t, gi] = obs
+                obs, _ = env.reset()
+            assert len(log) <= 2
+            for j, (ident, oa) in enumerate(log):
+                out["opp_model"][t, gi, j], out["opp_actions"][t, gi, j] = ident, oa
+            del log[:]
+            out["obs"][t, gi], out["mask"][t, gi] = obs, env.legal_actions()
+            out["regions"][t, gi], out["counter"][t, gi] = env.simulator.regions, env.simulator.region_counter
+            out["sim_cur"][t, gi], out["draws"][t, gi] = env.simulator.current_player_num, stream.idx
+    return out
+
+
 def gen_kats():
     """SURVEY.md section 8c KAT-1..4, re-derived from the reference here and stored verbatim."""
     minihex, A, B, S = rh.load()
@@ -181,6 +228,11 @@ def main():
                 o = rollout("A", N, G, T, seed=2000 + N, agent_mode=0, fused=bool(fused), opponent_first=bool(of))
                 np.savez_compressed(os.path.join(OUT, "envA_N%d_of%d_f%d.npz" % (N, of, fused)), N=N, seed=2000 + N,
                                     opponent_first=of, fused=fused, **o)
+    for N, G, T, pool in [(4, 16, 30, 3), (7, 10, 70, 5), (11, 6, 120, 20)]:
+        for agent_mode in (0, 1, 2):
+            o = rollout_scripted_opponent(N, G, T, seed=3000 + N, agent_mode=agent_mode, pool=pool)
+            np.savez_compressed(os.path.join(OUT, "oppmodel_N%d_a%d.npz" % (N, agent_mode)), N=N, seed=3000 + N, agent_mode=agent_mode,
+                                pool=pool, **o)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden fixtures: %d files, %.1f KiB" % (len(os.listdir(OUT)), total / 1024.0))
 

@@ -232,6 +232,9 @@ typedef struct {
     int eval_state;     /* SelfplayWrapper.py:92 */
     int64_t st[8];      /* episodes, black wins, white wins, agent wins, plies of finished episodes, invalid ends, env steps, plies */
     int plies;          /* plies in the running episode */
+    int manual;         /* the opponent's moves come from the caller (an OpponentPolicy, SelfplayWrapper.py:26-35): resets do not open */
+    int pool_size;      /* len(self.opponent_models) */
+    int opp_index;      /* opponent chosen by setup_opponents: -1 = best_model, k = opponent_models[k] */
 } env_t;
 
 /* --- variant A */
@@ -249,7 +252,7 @@ static void A_opponent_move(env_t *e, double u) {
 static void A_reset(env_t *e, const double *open_u) {
     game_init(&e->g, e->g.N, 0, e->start_player, NULL);
     e->plies = 0;
-    if (e->agent != e->start_player) A_opponent_move(e, open_u ? *open_u : rng_random(&e->rng));
+    if (e->agent != e->start_player && !e->manual) A_opponent_move(e, open_u ? *open_u : rng_random(&e->rng));
 }
 
 /* HexEnv.step HexGame.py:244-295 (self.player == BLACK) */
@@ -297,7 +300,11 @@ static void B_continue_game(env_t *e, const double *u_in, int reward[2]) {
 static void B_setup_opponents(env_t *e) {
     if (e->eval_state) return;
     double rv = rng_uniform01(&e->rng);
-    if (!(rv < 0.8)) (void)rng_random(&e->rng);
+    e->opp_index = -1;                       /* self.opponent_model = self.best_model */
+    if (!(rv < 0.8)) {
+        double ui = rng_random(&e->rng);     /* i = int(random.random() * len(self.opponent_models)) */
+        if (e->pool_size > 0) e->opp_index = (int)(ui * (double)e->pool_size);
+    }
 }
 
 /* SelfPlayEnv.reset SelfplayWrapper.py:69-89 + HexEnv.reset HexSingleGame.py:208-231 */
@@ -307,7 +314,7 @@ static void B_reset(env_t *e, const double *open_u) {
     e->plies = 0;
     if (e->agent < 0) e->agent = (int)(rng_random(&e->rng) * 2.0); /* random.randint(0,1), once per env */
     if (!open_u) B_setup_opponents(e);
-    if (e->env_cur != e->agent) {
+    if (e->env_cur != e->agent && !e->manual) {
         int reward[2];
         B_continue_game(e, open_u, reward);
     }
@@ -444,6 +451,77 @@ void hexref_batch_step(void *h, const int32_t *actions, const double *opp_u, int
     if (nt == 1) { step_range(&jobs[0]); return; }
     for (int t = 0; t < nt; ++t) pthread_create(&tids[t], NULL, step_range, &jobs[t]);
     for (int t = 0; t < nt; ++t) pthread_join(tids[t], NULL);
+}
+
+/* Caller-driven opponent: the env with an OpponentPolicy whose actions arrive from outside. */
+void hexref_batch_set_manual(void *h, int pool_size) {
+    batch_t *b = (batch_t *)h;
+    for (int64_t i = 0; i < b->G; ++i) { b->envs[i].manual = 1; b->envs[i].pool_size = pool_size; b->envs[i].opp_index = -1; }
+}
+
+static int agent_to_move(const env_t *e) { return e->kind == 0 ? (e->g.cur == e->agent) : (e->env_cur == e->agent); }
+
+/* One ply of `side` (0 agent, 1 opponent) in every unfinished game whose turn it is; actions in the mover's own perspective.
+ *   variant B: HexEnv.step (HexSingleGame.py:233-263), for the opponent preceded by continue_game's unused draw (SelfplayWrapper.py:159)
+ *   variant A: HexEnv.step's agent part (HexGame.py:250-253) / opponent_move with the action transposed back (:341-346)
+ * An illegal OPPONENT move ends the episode with reward 0 in both variants (variant A's reference would hand out -100 and play on;
+ * unreachable with a masked policy, not replicated). */
+void hexref_batch_half_step(void *h, int side, const int32_t *actions, int auto_reset, float *reward, uint8_t *done, uint8_t *to_move,
+                            int32_t *opp_index, int8_t *term_obs) {
+    batch_t *b = (batch_t *)h;
+    const int C = b->N * b->N;
+    for (int64_t i = 0; i < b->G; ++i) {
+        env_t *e = &b->envs[i];
+        const int was_done = e->g.done;
+        float r = 0.f;
+        if (!was_done && ((side == 0) == (agent_to_move(e) != 0))) {
+            int a = actions[i];
+            if (side == 0) e->st[6]++;
+            if (e->kind == 1) {
+                int rw[2];
+                if (side == 1) (void)rng_uniform01(&e->rng);
+                B_base_step(e, a, rw);
+                r = (float)rw[e->agent];
+            } else {
+                if (side == 1) a = (a >= 0 && a < C) ? transpose_action(a, b->N) : -1;
+                e->env_winner = fast_move(&e->g, a);
+                if (e->env_winner == INVALID) e->g.done = 1;
+                else { e->plies++; e->st[7]++; }
+                if (e->env_winner == e->agent) r = 1.f;
+                else if (e->env_winner == (e->agent + 1) % 2) r = -1.f;
+                else if (e->env_winner == INVALID && side == 0) r = -100.f;
+            }
+        } else if (was_done && e->kind == 0 && side == 0) {
+            if (e->env_winner == e->agent) r = 1.f;
+            else if (e->env_winner == (e->agent + 1) % 2) r = -1.f;
+            else if (e->env_winner == INVALID) r = -100.f;
+        }
+        if (reward) reward[i] = r;
+        if (done) done[i] = (uint8_t)e->g.done;
+        if (e->g.done && !was_done) {
+            account_episode(e);
+            if (term_obs) emit_obs_mask(e, term_obs + i * C, NULL);
+            if (auto_reset) env_reset(e, NULL);
+        }
+        if (to_move) to_move[i] = e->g.done ? 2 : (agent_to_move(e) ? 0 : 1);
+        if (opp_index) opp_index[i] = e->opp_index;
+    }
+}
+
+void hexref_batch_opp_state(void *h, uint8_t *to_move, int32_t *opp_index) {
+    batch_t *b = (batch_t *)h;
+    for (int64_t i = 0; i < b->G; ++i) {
+        const env_t *e = &b->envs[i];
+        if (to_move) to_move[i] = e->g.done ? 2 : (agent_to_move(e) ? 0 : 1);
+        if (opp_index) opp_index[i] = e->opp_index;
+    }
+}
+
+/* Current board (the live simulator.board, i.e. the side-to-move view in variant B) + mask, without stepping. */
+void hexref_batch_observe(void *h, int8_t *obs, uint8_t *mask) {
+    batch_t *b = (batch_t *)h;
+    const int C = b->N * b->N;
+    for (int64_t i = 0; i < b->G; ++i) emit_obs_mask(&b->envs[i], obs ? obs + i * C : NULL, mask ? mask + i * C : NULL);
 }
 
 /* Batched HexGame.make_move on raw games (kind 2 = A, kind 3 = B), or on the simulators inside envs. */

@@ -43,6 +43,10 @@ def lib():
         L.hexref_draw.argtypes = [u64, u64, ctypes.c_uint32]
         L.hexref_philox4x32_10.argtypes = [vp, vp, vp]
         L.hexref_set_threads.argtypes = [i32]
+        L.hexref_batch_set_manual.argtypes = [vp, i32]
+        L.hexref_batch_half_step.argtypes = [vp, i32, vp, i32] + [vp] * 5
+        L.hexref_batch_observe.argtypes = [vp, vp, vp]
+        L.hexref_batch_opp_state.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -55,13 +59,15 @@ class RefBatch(object):
     """G independent reference environments (or raw games) stepped in a loop on the CPU."""
 
     def __init__(self, kind, board_size, num_games, seed=0, game_offset=0, agent_mode=0,
-                 opponent_first=False, eval_state=False):
+                 opponent_first=False, eval_state=False, manual_opponent=False, pool_size=0):
         self.kind, self.N, self.G = kind, board_size, num_games
         self.C = board_size * board_size
         self._h = lib().hexref_batch_create(kind, board_size, num_games, seed, game_offset, agent_mode,
                                             int(opponent_first), int(eval_state))
         if not self._h:
             raise ValueError("bad oracle config")
+        if manual_opponent:
+            self.set_manual_opponent(pool_size)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -95,6 +101,37 @@ class RefBatch(object):
     def step_fast(self, auto_reset=True):
         """Fused-sampling step without output buffers (CPU baseline timing)."""
         lib().hexref_batch_step(self._h, None, None, int(auto_reset), None, None, None, None, None, None)
+
+    def set_manual_opponent(self, pool_size=0):
+        lib().hexref_batch_set_manual(self._h, pool_size)
+
+    def half_step(self, side, actions, auto_reset=True, want_term=False):
+        reward = np.empty(self.G, np.float32)
+        done = np.empty(self.G, np.uint8)
+        to_move = np.empty(self.G, np.uint8)
+        opp_index = np.empty(self.G, np.int32)
+        term = np.zeros((self.G, self.N, self.N), np.int8) if want_term else None
+        a = np.ascontiguousarray(actions, np.int32)
+        lib().hexref_batch_half_step(self._h, side, _p(a), int(auto_reset), _p(reward), _p(done), _p(to_move), _p(opp_index), _p(term))
+        out = dict(reward=reward, done=done, to_move=to_move, opp_index=opp_index)
+        if want_term:
+            out["term_obs"] = term
+        return out
+
+    def opp_state(self):
+        to_move = np.empty(self.G, np.uint8)
+        opp_index = np.empty(self.G, np.int32)
+        lib().hexref_batch_opp_state(self._h, _p(to_move), _p(opp_index))
+        return to_move, opp_index
+
+    def view1(self):
+        return self.observe()
+
+    def observe(self):
+        obs = np.empty((self.G, self.N, self.N), np.int8)
+        mask = np.empty((self.G, self.C), np.uint8)
+        lib().hexref_batch_observe(self._h, _p(obs), _p(mask))
+        return obs, mask
 
     def ply(self, actions):
         ret = np.empty(self.G, np.int8)

@@ -38,6 +38,8 @@ def lib():
         L.emu_export_state.argtypes = [vp] * 9
         L.emu_import_boards.argtypes = [vp] * 3
         L.emu_stats.argtypes = [vp, vp]
+        L.emu_set_manual_opponent.argtypes = [vp, i32, vp, vp]
+        L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -48,12 +50,16 @@ def _p(a):
 
 class EmuBatch(object):
     def __init__(self, variant, board_size, num_games, seed=0, game_offset=0, agent_mode=0, opponent_first=False,
-                 auto_reset=True, eval_state=False, raw=False):
+                 auto_reset=True, eval_state=False, raw=False, manual_opponent=False, pool_size=0):
         self.N, self.G, self.C = board_size, num_games, board_size * board_size
         self._h = lib().emu_create(board_size, variant, num_games, game_offset, seed, agent_mode, int(opponent_first),
                                    int(auto_reset), int(eval_state), int(raw))
         if not self._h:
             raise ValueError("bad emulator config")
+        if manual_opponent:
+            self.opp_index = np.full(num_games, -1, np.int32)
+            self.to_move = np.full(num_games, 9, np.uint8)
+            lib().emu_set_manual_opponent(self._h, pool_size, _p(self.opp_index), _p(self.to_move))
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -82,6 +88,23 @@ class EmuBatch(object):
         if want_term:
             out["term_obs"] = term
         return out
+
+    def half_step(self, side, actions, want_term=False):
+        reward = np.empty(self.G, np.float32)
+        done = np.empty(self.G, np.uint8)
+        term = np.zeros((self.G, self.N, self.N), np.int8) if want_term else None
+        a = np.ascontiguousarray(actions, np.int32)
+        lib().emu_half_step(self._h, side, _p(a), _p(reward), _p(done), _p(term))
+        out = dict(reward=reward, done=done, to_move=self.to_move.copy(), opp_index=self.opp_index.copy())
+        if want_term:
+            out["term_obs"] = term
+        return out
+
+    def opp_state(self):
+        return self.to_move.copy(), self.opp_index.copy()
+
+    def view1(self):
+        return self.encode(1)
 
     def ply(self, actions):
         ret = np.empty(self.G, np.int8)

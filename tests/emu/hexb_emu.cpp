@@ -50,6 +50,9 @@ static void run_tiles(Params P) {
                 for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
             } else if (P.mode == MODE_RESET) {
                 game_reset<N>(P, g, recs[t], flg[t]);
+            } else if (P.mode == MODE_HALF) {
+                game_half<N>(L, P, g, recs[t], locs[t], prmA[t], prmB[t], flg[t]);
+                for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
             } else {
                 game_ply<N>(L, P, g, recs[t], prmA[t], flg[t]);
             }
@@ -62,7 +65,7 @@ static void run_tiles(Params P) {
             for (int lane = 0; lane < kWarp; ++lane)
                 row_job_lane<N>(chunk, r, prmA[r], prmB[r], flg[r] & ~F_TERM, P, g0 + r, lane, [] {});
         }
-        if (P.mode != MODE_PLY && (P.obs || P.mask)) {   // elementwise encode, then the rare opponent-view rows
+        if (P.mode != MODE_PLY && P.mode != MODE_HALF && (P.obs || P.mask)) {   // elementwise encode, then the rare opponent-view rows
             const long long out0 = g0 * C, limit = P.G * C;
             for (int i = 0; i < Chunk<N>::VECS; ++i) {
                 Vec4 in, o, m;
@@ -124,6 +127,16 @@ void *emu_create(int N, int variant, long long G, long long game_offset, unsigne
     return e;
 }
 void emu_destroy(void *h) { delete (emu_env *)h; }
+void emu_set_manual_opponent(void *h, int pool_size, int32_t *opp_index, uint8_t *to_move) {
+    emu_env *e = (emu_env *)h;
+    e->base.manual_opponent = 1; e->base.pool_size = pool_size; e->base.opp_index = opp_index; e->base.to_move = to_move;
+}
+void emu_half_step(void *h, int side, const int32_t *actions, float *reward, uint8_t *done, int8_t *term_obs) {
+    emu_env *e = (emu_env *)h;
+    Params P = e->base;
+    P.mode = MODE_HALF; P.half_side = side; P.actions = actions; P.reward = reward; P.done = done; P.term_obs = term_obs;
+    dispatch(e, P);
+}
 
 void emu_reset(void *h, const uint8_t *reset_mask, const double *open_u, int8_t *obs, uint8_t *mask) {
     emu_env *e = (emu_env *)h;

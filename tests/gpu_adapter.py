@@ -26,6 +26,20 @@ class GpuBatch(object):
         o = self.b.step(actions, opp_u, want_term=want_term, want_actions=True)
         return {k: self._np(v) for k, v in o.items()}
 
+    def half_step(self, side, actions, want_term=False):
+        if want_term:
+            self.b._buf("term_obs", (self.G, self.N, self.N), torch.int8).zero_()
+        o = self.b.half_step(side, actions, want_term=want_term)
+        out = {k: self._np(v) for k, v in o.items()}
+        out["to_move"], out["opp_index"] = self.opp_state()
+        return out
+
+    def opp_state(self):
+        return self._np(self.b.to_move), self._np(self.b.opp_index)
+
+    def view1(self):
+        return self.encode(1)
+
     def ply(self, actions):
         return self._np(self.b.ply(actions))
 
@@ -48,9 +62,10 @@ class GpuBatch(object):
         return self._np(self.b.stats())
 
 
-def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False):
+def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False,
+         manual_opponent=False, pool_size=0):
     if kind == hexref.KIND_GAME_A:
         return GpuBatch(0, N, G, raw=True)
     variant = 0 if kind == hexref.KIND_ENV_A else 1
     return GpuBatch(variant, N, G, seed=seed, game_offset=game_offset, agent_mode=agent_mode, opponent_first=opponent_first,
-                    auto_reset=auto_reset, eval_state=eval_state)
+                    auto_reset=auto_reset, eval_state=eval_state, manual_opponent=manual_opponent, pool_size=pool_size)

@@ -152,3 +152,57 @@ def snake_chain(make, N):
             for k in ("board", "regions", "region_counter", "cur", "done", "winner"):
                 eq(e[k], r[k], "snake %s t=%d" % (k, t))
     assert ref.export()["region_counter"].max() >= N * N // 5   # the label range really was exercised
+
+
+def golden_oppmodel(make, name):
+    """Caller-driven opponent (hexb_half_step) against the reference run with OpponentPolicy opponents (scripted models).
+    The opponent's actions are re-derived here from the implementation's OWN side-to-move observation with the same scripted
+    rule the reference's models used, so the opponent view, the 80/20 opponent choice and the half steps are all pinned."""
+    from oracle.scripted import scripted_choice
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, am, pool = int(z["N"]), int(z["seed"]), int(z["agent_mode"]), int(z["pool"])
+    T, G = z["actions"].shape
+    env = make(hexref.KIND_SELFPLAY_B, N, G, seed=seed, agent_mode=am, manual_opponent=True, pool_size=pool)
+    env.reset()
+
+    def opponent_pass(expect_a, expect_model, what):
+        tm, idx = env.opp_state()
+        eq(tm == 1, expect_a >= 0, what + " who waits for the opponent")
+        obs1, mask1 = env.view1()
+        acts = np.zeros(G, np.int32)
+        for g in np.flatnonzero(tm == 1):
+            acts[g] = scripted_choice(obs1[g], mask1[g])
+            assert acts[g] == expect_a[g], (what, g, acts[g], expect_a[g])
+            assert idx[g] == expect_model[g], (what, "opponent index", g, idx[g], expect_model[g])
+        return env.half_step(1, acts, want_term=True)
+
+    opponent_pass(z["opp0_action"], z["opp0_model"], name + " opening")
+    obs, mask = env.view1()
+    eq(obs, z["obs0"], name + " obs0")
+    eq(mask, z["mask0"], name + " mask0")
+    e = env.export()
+    eq(e["agent"], z["agent"], name + " agent")
+    eq(e["draws"], z["draws0"], name + " draws0")
+    for t in range(T):
+        w = "%s t=%d " % (name, t)
+        h = env.half_step(0, z["actions"][t], want_term=True)
+        reward, done, term = h["reward"].copy(), h["done"].astype(bool), h["term_obs"].copy()
+        for j in (0, 1):
+            h = opponent_pass(z["opp_actions"][t, :, j], z["opp_model"][t, :, j], w + "pass %d" % j)
+            reward += h["reward"]
+            d = h["done"].astype(bool)
+            term[d] = h["term_obs"][d]
+            done |= d
+        tm, _ = env.opp_state()
+        assert (tm == 0).all(), w + "every game back at the agent"
+        eq(reward, z["reward"][t], w + "reward")
+        eq(done, z["done"][t].astype(bool), w + "done")
+        eq(term[done], z["term_obs"][t][done], w + "term_obs")
+        obs, mask = env.view1()
+        eq(obs, z["obs"][t], w + "obs")
+        eq(mask, z["mask"][t], w + "mask")
+        e = env.export()
+        eq(e["regions"], z["regions"][t].astype(np.float64), w + "regions")
+        eq(e["region_counter"], z["counter"][t].astype(np.float64), w + "counter")
+        eq(e["cur"], z["sim_cur"][t], w + "cur")
+        eq(e["draws"], z["draws"][t], w + "draws")

@@ -10,12 +10,18 @@ from oracle import hexref
 from emu.emu import EmuBatch
 
 
-def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False):
+def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False,
+         manual_opponent=False, pool_size=0):
     if kind == hexref.KIND_GAME_A:
         return EmuBatch(0, N, G, raw=True)
     variant = 0 if kind == hexref.KIND_ENV_A else 1
     return EmuBatch(variant, N, G, seed=seed, game_offset=game_offset, agent_mode=agent_mode, opponent_first=opponent_first,
-                    auto_reset=auto_reset, eval_state=eval_state)
+                    auto_reset=auto_reset, eval_state=eval_state, manual_opponent=manual_opponent, pool_size=pool_size)
+
+
+@pytest.mark.parametrize("name", golden_files("oppmodel_"))
+def test_golden_scripted_opponent(name):
+    parity.golden_oppmodel(make, name)
 
 
 @pytest.mark.parametrize("name", golden_files("game_A"))
@@ -73,3 +79,9 @@ def test_preset_board_rebuild(N):
     e, r = env.export(), ref.export()
     for k in ("board", "regions", "region_counter", "cur"):
         parity.eq(e[k], r[k], k)
+
+
+@pytest.mark.parametrize("N,kind", [(5, hexref.KIND_SELFPLAY_B), (6, hexref.KIND_ENV_A)])
+def test_half_step_vs_oracle(N, kind):
+    from test_gpu_parity import test_half_step_vs_oracle as driver
+    driver(make, N, kind)

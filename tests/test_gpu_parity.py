@@ -137,3 +137,83 @@ def test_step_host_matches_device(make):
 @pytest.mark.parametrize("N", [7, 11, 19])
 def test_snake_chain_worst_case(make, N):
     parity.snake_chain(make, N)
+
+
+@pytest.mark.parametrize("name", golden_files("oppmodel_"))
+def test_golden_scripted_opponent(make, name):
+    """hexb_half_step (learned opponent) against the reference run with OpponentPolicy opponents."""
+    parity.golden_oppmodel(make, name)
+
+
+@pytest.mark.parametrize("N,variant_kind", [(5, hexref.KIND_SELFPLAY_B), (11, hexref.KIND_SELFPLAY_B), (6, hexref.KIND_ENV_A)])
+def test_half_step_vs_oracle(make, N, variant_kind):
+    """Random legal (and a few illegal) moves of both sides through the split step, GPU vs oracle, with and without auto-reset."""
+    G, T, C = 700, 2 * N * N // 3, N * N
+    for auto_reset in (True, False):
+        kw = dict(agent_mode=2) if variant_kind == hexref.KIND_SELFPLAY_B else dict(opponent_first=True)
+        env = make(variant_kind, N, G, seed=N, auto_reset=auto_reset, manual_opponent=True, pool_size=7, **kw)
+        ref = hexref.RefBatch(variant_kind, N, G, seed=N, manual_opponent=True, pool_size=7, **kw)
+        env.reset(); ref.reset()
+        rs = np.random.RandomState(N)
+        for t in range(T):
+            for side in (1, 0, 1):
+                tm, idx = env.opp_state()
+                rtm, ridx = ref.opp_state()
+                parity.eq(tm, rtm, "to_move t=%d" % t)
+                parity.eq(idx, ridx, "opp_index t=%d" % t)
+                obs1, mask1 = env.view1()
+                if variant_kind == hexref.KIND_SELFPLAY_B:
+                    robs1, rmask1 = ref.view1()
+                    live = tm != 2
+                    parity.eq(obs1[live], robs1[live], "side-to-move obs t=%d" % t)
+                    parity.eq(mask1[live], rmask1[live], "side-to-move mask t=%d" % t)
+                else:   # variant A keeps the true board; the opponent's action index is the transposed cell
+                    mask1 = mask1.reshape(G, N, N).transpose(0, 2, 1).reshape(G, C) if side == 1 else mask1
+                cnt = np.maximum(mask1.sum(1), 1)
+                k = (rs.rand(G) * cnt).astype(np.int64)
+                acts = np.argsort(-mask1.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
+                bad = rs.rand(G) < 0.02
+                acts[bad] = rs.randint(-1, C + 1, size=int(bad.sum()))
+                o = env.half_step(side, acts, want_term=True)
+                r = ref.half_step(side, acts, auto_reset=auto_reset, want_term=True)
+                for key in ("reward", "done", "to_move", "opp_index"):
+                    parity.eq(o[key], r[key], "%s t=%d side=%d" % (key, t, side))
+                d = r["done"].astype(bool) if auto_reset else np.zeros(G, bool)
+                parity.eq(o["term_obs"][d], r["term_obs"][d], "term_obs t=%d" % t)
+            if t % 5 == 0:
+                e, re_ = env.export(), ref.export()
+                for key in ("regions", "region_counter", "cur", "done", "winner", "agent", "draws"):
+                    parity.eq(e[key], re_[key], "%s t=%d" % (key, t))
+        parity.eq(env.stats(), ref.stats(), "stats")
+
+
+def test_step_with_opponent_on_device():
+    """HexBatch.step_with_opponent with the scripted rule as a torch callable == three explicit half steps."""
+    import torch
+    from hex_gym_env_b200 import HexBatch, VARIANT_B
+    N, G = 7, 513
+    a = HexBatch(N, G, variant=VARIANT_B, device=0, seed=4, agent_mode=2, manual_opponent=True, pool_size=4)
+    b = HexBatch(N, G, variant=VARIANT_B, device=0, seed=4, agent_mode=2, manual_opponent=True, pool_size=4)
+
+    def first_legal(obs, mask, to_move, opp_index):
+        return torch.argmax(mask, dim=1).to(torch.int32)
+
+    for env in (a, b):
+        env.reset()
+        o1, m1 = env.encode(1)
+        env.half_step(1, first_legal(o1, m1, None, None))
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    for t in range(60):
+        _, mask = a.encode(0)
+        acts = a.sample_actions(torch.rand(G, dtype=torch.float64, device="cuda", generator=gen)).clone()
+        out = a.step_with_opponent(acts, first_legal)
+        h = b.half_step(0, acts)
+        rew, done = h["reward"].clone(), h["done"].clone()
+        for _ in range(2):
+            o1, m1 = b.encode(1)
+            h = b.half_step(1, first_legal(o1, m1, None, None))
+            rew += h["reward"]; done |= h["done"]
+        obs, mask = b.encode(0)
+        assert torch.equal(out["obs"], obs) and torch.equal(out["mask"], mask) and torch.equal(out["reward"], rew) and torch.equal(out["done"], done)
+        assert bool((a.to_move == 0).all())
+    assert int(a.stats()[0]) > 0 and int(a.stats()[5]) == 0

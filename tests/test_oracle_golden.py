@@ -75,6 +75,13 @@ def test_envA_rollouts(name):
     _check_rollout(name, hexref.KIND_ENV_A)
 
 
+@pytest.mark.parametrize("name", golden_files("oppmodel_"))
+def test_scripted_opponent_rollouts(name):
+    """The caller-driven opponent path of the oracle against the reference run with OpponentPolicy opponents."""
+    import parity
+    parity.golden_oppmodel(lambda kind, N, G, **kw: hexref.RefBatch(kind, N, G, **kw), name)
+
+
 def test_kats():
     """SURVEY.md section 8c KAT-1..4 (values stored from the reference in kat.npz)."""
     k = load("kat.npz")
