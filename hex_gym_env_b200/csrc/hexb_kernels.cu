@@ -148,7 +148,9 @@ __device__ __forceinline__ void add_stats(const Params &P, long long wglobal, in
     if (sb >> 20) atomicAdd(stripe + 7, (unsigned long long)(sb >> 20));
 }
 
-template <int N>
+// STEP_ONLY = true: the instantiation the timed path launches (MODE_STEP only, nothing else compiled in);
+// STEP_ONLY = false: reset / raw ply / half step, selected at run time by P.mode.
+template <int N, bool STEP_ONLY>
 __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(const Params P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using SL = SmemLayout<N>;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     uint32_t *recw = reinterpret_cast<uint32_t *>(chunk + Geo<N>::CHUNK_LAB) + lane;   // this lane's record word 0 (shared memory)
     double u_agent = 0.0, u_opp = 0.0;
 #if defined(HEXB_EXP_NO_PHILOX)     // timing experiment only: a cheap hash instead of the two Philox draws
-    if (P.mode == MODE_STEP && g < P.G) {
+    if (STEP_ONLY && g < P.G) {
         uint32_t h = (uint32_t)g * 2654435761u + rec.draws * 40503u;
         h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
         u_agent = (double)(h >> 8) * (1.0 / 16777216.0);
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         u_opp = (double)(h >> 8) * (1.0 / 16777216.0);
     }
 #else
-    if (P.mode == MODE_STEP && g < P.G) {
+    if (STEP_ONLY && g < P.G) {
         const uint32_t *grec = reinterpret_cast<const uint32_t *>(gl + Geo<N>::CHUNK_LAB) + lane;
         pre_draws(P, grec[(2 * Geo<N>::W) * kRecStride], grec[(2 * Geo<N>::W + 1) * kRecStride],
                   (unsigned long long)(P.game_offset + g), u_agent, u_opp);
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     // ---- thread-per-game phase
     uint32_t prmA = 0, prmB = 0, flg = 0;
     uint8_t *L = chunk + lane * C;
-    if (P.mode == MODE_STEP) {
+    if (STEP_ONLY) {
         Loc loc;
 #if defined(HEXB_EXP_NO_COMPUTE)   // timing experiment only: memory pipeline without the plies
         loc.reward = 0.f; loc.action = 0;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
 
     // ---- observation + mask. They depend on emptiness and owner bits only, not on the labels, so they are issued BEFORE
     //      the relabel sweeps: the output stores drain to HBM while the warp works through its relabel rows.
-    if (P.mode != MODE_PLY && P.mode != MODE_HALF && (P.obs || P.mask)) {
+    if ((STEP_ONLY || (P.mode != MODE_PLY && P.mode != MODE_HALF)) && (P.obs || P.mask)) {
         encode_chunk<N>(chunk, P, g0, lane);
         uint32_t views = __ballot_sync(FULL, (flg & F_VIEW_OPP) != 0u);  // only without auto-reset: finished by the agent's own ply
         if (views) __syncwarp();
@@ -486,13 +488,16 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     constexpr int smem = SmemLayout<N>::BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     const unsigned grid = (unsigned)(P.Gpad / kCtaThreads);
     (void)e;
-    hexb_step_kernel<N><<<grid, kCtaThreads, smem, s>>>(P);
+    if (P.mode == MODE_STEP) hexb_step_kernel<N, true><<<grid, kCtaThreads, smem, s>>>(P);
+    else hexb_step_kernel<N, false><<<grid, kCtaThreads, smem, s>>>(P);
     CK(cudaGetLastError());
     return HEXB_OK;
 }
