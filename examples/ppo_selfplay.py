@@ -19,7 +19,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
 from hex_gym_env_b200 import AGENT_RANDOM, VARIANT_B, HexBatch  # noqa: E402
-from hex_gym_env_b200.rollout import RolloutCollector  # noqa: E402
+from hex_gym_env_b200.rollout import RolloutCollector, masked_sample  # noqa: E402
 
 
 class MlpPolicy(nn.Module):
@@ -42,18 +42,35 @@ def main():
     ap.add_argument("--minibatch", type=int, default=16384)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--opponent", choices=["random", "self"], default="random",
+                    help="random: BaseRandomPolicy inside the fused step kernel; self: a frozen copy of the policy, refreshed every "
+                         "--refresh iterations, played through the split step (hexb_half_step), like the reference's OpponentPolicy pool")
+    ap.add_argument("--refresh", type=int, default=4)
     args = ap.parse_args()
     torch.manual_seed(args.seed)
     dev = torch.device("cuda", 0)
-    env = HexBatch(args.board, args.games, variant=VARIANT_B, device=0, seed=args.seed, agent_mode=AGENT_RANDOM, auto_reset=True)
+    env = HexBatch(args.board, args.games, variant=VARIANT_B, device=0, seed=args.seed, agent_mode=AGENT_RANDOM, auto_reset=True,
+                   manual_opponent=(args.opponent == "self"), pool_size=0)
     policy = MlpPolicy(env.C).to(dev)
+    frozen = MlpPolicy(env.C).to(dev)
+    frozen.load_state_dict(policy.state_dict())
+    ogen = torch.Generator(device=dev)
+    ogen.manual_seed(args.seed + 99)
+
+    def opponent_fn(obs, mask, to_move, opp_index):      # what OpponentPolicy.choose_action does, for all waiting games at once
+        with torch.no_grad():
+            logits, _ = frozen(obs.float())
+            return masked_sample(logits, mask, generator=ogen)[0]
+
     opt = torch.optim.Adam(policy.parameters(), lr=args.lr, eps=1e-5)
     col = RolloutCollector(env, args.n_steps, gamma=0.99, gae_lambda=0.95, seed=args.seed)
     prev = env.stats().cpu()
     for it in range(args.iters):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        buf = col.collect(policy)
+        if args.opponent == "self" and it and it % args.refresh == 0:
+            frozen.load_state_dict(policy.state_dict())
+        buf = col.collect(policy, opponent_fn if args.opponent == "self" else None)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         for _ in range(args.epochs):

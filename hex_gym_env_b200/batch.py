@@ -207,7 +207,13 @@ class HexBatch(object):
             out["term_obs"] = term_obs
         return out
 
-    def step_with_opponent(self, actions, opponent_fn, want_term=False):
+    def opponent_opening(self, opponent_fn):
+        """After reset(): let the caller's opponent open the games in which it moves first (agent is WHITE)."""
+        o1, m1 = self._buf("opp_obs", (self.G, self.N, self.N), torch.int8), self._buf("opp_mask", (self.G, self.C), torch.uint8)
+        self.encode(1, obs=o1, mask=m1)
+        self.half_step(1, opponent_fn(o1, m1, self.to_move, self.opp_index))
+
+    def step_with_opponent(self, actions, opponent_fn, want_term=False, obs=None, mask=None):
         """One env step against a learned opponent, all on the device: agent ply, then up to two opponent plies (the reply,
         and the opening move of a game that restarted with the opponent to move). `opponent_fn(obs i8[G,N,N], mask u8[G,C],
         to_move u8[G], opp_index i32[G]) -> actions i32[G]` sees the side-to-move view (what OpponentPolicy.choose_action gets,
@@ -222,7 +228,7 @@ class HexBatch(object):
             h = self.half_step(1, opponent_fn(o1, m1, self.to_move, self.opp_index), term_obs=term)
             reward += h["reward"]
             done |= h["done"]
-        obs, mask = self.encode(0)
+        obs, mask = self.encode(0, obs=obs, mask=mask)
         out = dict(obs=obs, mask=mask, reward=reward, done=done)
         if want_term:
             out["term_obs"] = term

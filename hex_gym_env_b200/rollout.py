@@ -89,10 +89,16 @@ class RolloutCollector(object):
         self.gen.manual_seed(seed)
         self._started = False
 
-    def collect(self, policy):
+    def collect(self, policy, opponent_fn=None):
+        """opponent_fn: only for manual_opponent batches - the learned opponent (see HexBatch.step_with_opponent)."""
         b, buf = self.batch, self.buf
+        if b.manual_opponent and opponent_fn is None:
+            raise ValueError("a manual_opponent batch needs opponent_fn")
         if not self._started:
             b.reset(obs=buf.obs[0], mask=buf.action_masks[0])
+            if b.manual_opponent:
+                b.opponent_opening(opponent_fn)
+                b.encode(0, obs=buf.obs[0], mask=buf.action_masks[0])
             buf.episode_starts[0] = 1.0
             self._started = True
         else:  # continue from where the previous rollout stopped
@@ -104,7 +110,11 @@ class RolloutCollector(object):
                 logits, values = policy(buf.obs[t].float())
                 actions, logp = masked_sample(logits, buf.action_masks[t], generator=self.gen)
                 buf.actions[t], buf.log_probs[t], buf.values[t] = actions, logp, values
-                b.step(actions, obs=buf.obs[t + 1], mask=buf.action_masks[t + 1], reward=buf.rewards[t], done=buf.dones[t])
+                if b.manual_opponent:
+                    o = b.step_with_opponent(actions, opponent_fn, obs=buf.obs[t + 1], mask=buf.action_masks[t + 1])
+                    buf.rewards[t], buf.dones[t] = o["reward"], o["done"]
+                else:
+                    b.step(actions, obs=buf.obs[t + 1], mask=buf.action_masks[t + 1], reward=buf.rewards[t], done=buf.dones[t])
                 buf.episode_starts[t + 1] = buf.dones[t].float()
             _, buf.values[buf.T] = policy(buf.obs[buf.T].float())
         buf.compute_returns_and_advantage()
