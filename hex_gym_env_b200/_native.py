@@ -65,6 +65,7 @@ SYMBOLS = {
     "hexb_import_boards": (_i32, [_vp] * 4),
     "hexb_stats": (_i32, [_vp] * 3),
     "hexb_set_opponent_buffers": (_i32, [_vp, _vp, _vp]),
+    "hexb_set_info_buffers": (_i32, [_vp, _vp, _vp]),
     "hexb_half_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "hexb_masked_sample": (_i32, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp, _vp, _vp, _i32, _vp]),
 }

@@ -160,6 +160,14 @@ class HexBatch(object):
             out["actions"] = actions_out
         return out
 
+    def enable_info(self):
+        """Also record, at every step(), the fields of the reference's info dict (HexGame.py:281-286) as device tensors:
+        self.last_move_opponent i32[G] and self.winner i8[G]; info["last_move_player"] is step(want_actions=True)["actions"]."""
+        self.last_move_opponent = torch.full((self.G,), -1, dtype=torch.int32, device=self.device)
+        self.winner = torch.full((self.G,), -1, dtype=torch.int8, device=self.device)
+        check(self._lib.hexb_set_info_buffers(self._h, _ptr(self.last_move_opponent), _ptr(self.winner)))
+        return self.last_move_opponent, self.winner
+
     def pinned_io(self):
         """Pinned host buffers for step_host: dict(actions i32[G], obs i8[G,N,N], mask u8[G,C], reward f32[G], done u8[G])."""
         if self._pinned is None:

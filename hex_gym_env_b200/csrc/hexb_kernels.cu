@@ -527,6 +527,13 @@ static View view_of(const hexb_env *e) {
 
 extern "C" {
 
+int32_t hexb_set_info_buffers(hexb_env *env, int32_t *last_move_opponent, int8_t *winner) {
+    if (!env) return HEXB_ERR_ARG;
+    env->base.info_opp = last_move_opponent;
+    env->base.info_winner = winner;
+    return HEXB_OK;
+}
+
 int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to_move) {
     if (!env) return HEXB_ERR_ARG;
     env->base.opp_index = opp_index;

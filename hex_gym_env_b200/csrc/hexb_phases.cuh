@@ -107,6 +107,7 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
     }
     const unsigned long long gid = (unsigned long long)(P.game_offset + g);
     const bool was_done = (rec.meta & M_DONE) != 0u;
+    int opp_move = -1;
     if (was_done) {
         loc.reward = P.variant == VARIANT_A ? stale_reward_A(rec.meta) : 0.f;
     } else {
@@ -146,6 +147,7 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
             const int i = select_kth_zero<N>(rec.occ_cm, choice_of(u, n));  // k-th empty cell of the opponent's view = stored column-major
             const int x = i / N, y = i - x * N;
             const bool won = place_stone<N>(L, rec, 1, y * N + x, prmB);
+            opp_move = P.variant == VARIANT_A ? y * N + x : i;  // A: transposed back to the true cell (HexGame.py:341-346); B: its own view
             loc.st[7]++;
             rec.meta ^= M_TOMOVE;
             if (won) {
@@ -171,6 +173,12 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
     if (P.reward) P.reward[g] = loc.reward;
     if (P.done) P.done[g] = is_done ? 1 : 0;
     if (P.actions_out) P.actions_out[g] = loc.action;
+    if (P.info_opp) P.info_opp[g] = opp_move;
+    if (P.info_winner) {  // HexEnv.winner (HexGame.py:251,347 / HexSingleGame.py:239): the last make_move's return value
+        const uint32_t w = (rec.meta & M_WIN_MASK) >> M_WIN_SHIFT;
+        const int tr = (rec.meta & M_TRANSPOSED) ? 1 : 0;
+        P.info_winner[g] = (int8_t)((rec.meta & M_INVALID) ? 3 : (w == 0u ? -1 : (int)((w - 1u) ^ (uint32_t)tr)));
+    }
     if (is_done) {
         if (P.auto_reset) {
             reset_game<N>(rec, P, gid, P.opp_u ? &P.opp_u[2 * g + 1] : nullptr, flg);

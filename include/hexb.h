@@ -100,6 +100,12 @@ int32_t hexb_reset(hexb_env *env, const uint8_t *reset_mask, const double *open_
 int32_t hexb_step(hexb_env *env, const int32_t *actions, const double *opp_u, int8_t *obs, uint8_t *mask, float *reward,
                   uint8_t *done, int8_t *term_obs, int32_t *actions_out, void *stream);
 
+/* Optional per-game outputs of every following hexb_step (null = off): what the reference returns in the info dict of variant-A
+ * HexEnv.step (HexGame.py:281-286) - last_move_opponent i32[G] (the opponent's move of this step as HexEnv reports it: variant A
+ * the true cell, variant B the cell in the opponent's own view; -1 if it did not move) and winner i8[G] (env.winner: -1 None,
+ * 0 BLACK, 1 WHITE, 3 illegal move). info["last_move_player"] is hexb_step's actions_out. */
+int32_t hexb_set_info_buffers(hexb_env *env, int32_t *last_move_opponent, int8_t *winner);
+
 /* The same step with HOST buffers (pinned memory recommended): copies actions_host to the device, steps, copies
  * obs/mask/reward/done back and waits for them. This is the call a host-side (CPU policy) user of the reference
  * API makes; it needs hexb_host_workspace_bytes(cfg) bytes of device scratch passed at every call. */

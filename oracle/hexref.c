@@ -235,6 +235,8 @@ typedef struct {
     int manual;         /* the opponent's moves come from the caller (an OpponentPolicy, SelfplayWrapper.py:26-35): resets do not open */
     int pool_size;      /* len(self.opponent_models) */
     int opp_index;      /* opponent chosen by setup_opponents: -1 = best_model, k = opponent_models[k] */
+    int last_opp;       /* the opponent's latest move as HexEnv reports it (A: true cell, HexGame.py:341-348; B: its own view) */
+    int info_opp, info_winner; /* info["last_move_opponent"], env.winner at the end of the latest step() (before an auto-reset) */
 } env_t;
 
 /* --- variant A */
@@ -245,6 +247,7 @@ static void A_opponent_move(env_t *e, double u) {
     invert_board(&e->g);
     a = transpose_action(a, e->g.N);
     e->env_winner = fast_move(&e->g, a);
+    e->last_opp = a;
     e->plies++; e->st[7]++;
 }
 
@@ -293,6 +296,7 @@ static void B_continue_game(env_t *e, const double *u_in, int reward[2]) {
         u = rng_random(&e->rng);      /* BaseRandomPolicy.choose_action (:20) */
     }
     int a = random_choice(&e->g, u);
+    e->last_opp = a;
     B_base_step(e, a, reward);
 }
 
@@ -421,11 +425,14 @@ static void *step_range(void *arg) {
         if (j->actions_out) j->actions_out[i] = a;
         const double *ou = j->opp_u ? &j->opp_u[2 * i] : NULL;
         float r;
+        e->last_opp = -1;
         if (was_done && e->kind == 1) r = 0.f; /* stepping a finished variant-B game: defined as a no-op here (the reference has no guard) */
         else r = e->kind == 0 ? A_step(e, a, ou) : B_step(e, a, ou);
         if (!was_done) e->st[6]++;
         if (j->reward) j->reward[i] = r;
         if (j->done) j->done[i] = (uint8_t)e->g.done;
+        e->info_opp = e->last_opp;
+        e->info_winner = e->env_winner;
         if (e->g.done && !was_done) account_episode(e);
         if (e->g.done && j->term_obs) emit_obs_mask(e, j->term_obs + i * C, NULL);
         if (e->g.done && j->auto_reset) env_reset(e, ou ? ou + 1 : NULL);
@@ -505,6 +512,14 @@ void hexref_batch_half_step(void *h, int side, const int32_t *actions, int auto_
         }
         if (to_move) to_move[i] = e->g.done ? 2 : (agent_to_move(e) ? 0 : 1);
         if (opp_index) opp_index[i] = e->opp_index;
+    }
+}
+
+void hexref_batch_info(void *h, int32_t *last_move_opponent, int8_t *winner) {
+    batch_t *b = (batch_t *)h;
+    for (int64_t i = 0; i < b->G; ++i) {
+        if (last_move_opponent) last_move_opponent[i] = b->envs[i].info_opp;
+        if (winner) winner[i] = (int8_t)b->envs[i].info_winner;
     }
 }
 

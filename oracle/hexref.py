@@ -47,6 +47,7 @@ def lib():
         L.hexref_batch_half_step.argtypes = [vp, i32, vp, i32] + [vp] * 5
         L.hexref_batch_observe.argtypes = [vp, vp, vp]
         L.hexref_batch_opp_state.argtypes = [vp, vp, vp]
+        L.hexref_batch_info.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -117,6 +118,12 @@ class RefBatch(object):
         if want_term:
             out["term_obs"] = term
         return out
+
+    def info(self):
+        opp = np.empty(self.G, np.int32)
+        winner = np.empty(self.G, np.int8)
+        lib().hexref_batch_info(self._h, _p(opp), _p(winner))
+        return opp, winner
 
     def opp_state(self):
         to_move = np.empty(self.G, np.uint8)

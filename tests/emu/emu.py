@@ -40,6 +40,7 @@ def lib():
         L.emu_stats.argtypes = [vp, vp]
         L.emu_set_manual_opponent.argtypes = [vp, i32, vp, vp]
         L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.emu_set_info.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -99,6 +100,14 @@ class EmuBatch(object):
         if want_term:
             out["term_obs"] = term
         return out
+
+    def enable_info(self):
+        self.info_opp = np.full(self.G, -1, np.int32)
+        self.info_winner = np.full(self.G, -1, np.int8)
+        lib().emu_set_info(self._h, _p(self.info_opp), _p(self.info_winner))
+
+    def info(self):
+        return self.info_opp.copy(), self.info_winner.copy()
 
     def opp_state(self):
         return self.to_move.copy(), self.opp_index.copy()

@@ -131,6 +131,10 @@ void emu_set_manual_opponent(void *h, int pool_size, int32_t *opp_index, uint8_t
     emu_env *e = (emu_env *)h;
     e->base.manual_opponent = 1; e->base.pool_size = pool_size; e->base.opp_index = opp_index; e->base.to_move = to_move;
 }
+void emu_set_info(void *h, int32_t *opp, int8_t *winner) {
+    emu_env *e = (emu_env *)h;
+    e->base.info_opp = opp; e->base.info_winner = winner;
+}
 void emu_half_step(void *h, int side, const int32_t *actions, float *reward, uint8_t *done, int8_t *term_obs) {
     emu_env *e = (emu_env *)h;
     Params P = e->base;

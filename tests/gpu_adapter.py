@@ -34,6 +34,12 @@ class GpuBatch(object):
         out["to_move"], out["opp_index"] = self.opp_state()
         return out
 
+    def enable_info(self):
+        self.b.enable_info()
+
+    def info(self):
+        return self._np(self.b.last_move_opponent), self._np(self.b.winner)
+
     def opp_state(self):
         return self._np(self.b.to_move), self._np(self.b.opp_index)
 

@@ -77,6 +77,8 @@ def versus_oracle(make, kind, N, G, T, seed=0, game_offset=0, fused=True, auto_r
     ref = hexref.RefBatch(kind, N, G, seed=seed, game_offset=game_offset, **kw)
     env = make(kind, N, G, seed=seed, game_offset=game_offset, auto_reset=auto_reset, **kw)
     rs = np.random.RandomState(seed + 17)
+    if hasattr(env, "enable_info"):
+        env.enable_info()
     ro, rm = ref.reset()
     o, m = env.reset()
     eq(o, ro, "reset obs")
@@ -101,6 +103,10 @@ def versus_oracle(make, kind, N, G, T, seed=0, game_offset=0, fused=True, auto_r
             if key == "actions" and not fused:
                 continue
             eq(o[key], r[key], w + key)
+        if hasattr(env, "enable_info"):
+            (eo, ew), (fo, fw) = env.info(), ref.info()
+            eq(eo, fo, w + "info last_move_opponent")
+            eq(ew, fw, w + "info winner")
         d = r["done"].astype(bool)
         if auto_reset or t == 0 or True:
             newly = d if auto_reset else d

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hexb.h declares; argument checking and sizing work without
+a GPU (no compute call is made here). The product has no CPU path: creating an env without a device must fail loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from hex_gym_env_b200 import _native
+from hex_gym_env_b200._native import HexbConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    return _native.lib()
+
+
+def test_header_and_library_agree(L):
+    hdr = open(os.path.join(ROOT, "include", "hexb.h")).read()
+    declared = set(re.findall(r"\b(hexb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_native.SYMBOLS), (declared ^ set(_native.SYMBOLS))
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert getattr(raw, name) is not None
+    assert L.hexb_version() >> 16 == 1
+
+
+def test_config_struct_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "hexb.h")).read()
+    body = hdr[hdr.index("typedef struct hexb_config {"):hdr.index("} hexb_config;")]
+    fields = re.findall(r"^\s*(?:u?int(?:32|64)_t)\s+([a-z_]+);", body, flags=re.M)
+    assert fields == [f[0] for f in HexbConfig._fields_]
+
+
+def test_state_bytes_and_errors(L):
+    def cfg(**kw):
+        base = dict(board_size=11, variant=1, num_games=1000, game_offset=0, seed=0, agent_mode=2, opponent_first=0, auto_reset=1,
+                    eval_state=0, raw=0, device=0, manual_opponent=0, pool_size=0)
+        base.update(kw)
+        return HexbConfig(**base)
+    c = cfg()
+    n = L.hexb_state_bytes(ctypes.byref(c))
+    chunks = (1000 + 127) // 128 * 4                       # games padded to 128, 32 per chunk
+    assert n >= chunks * 32 * (121 + 4 * 10) and n % 256 == 0
+    assert L.hexb_host_workspace_bytes(ctypes.byref(c)) >= 1000 * (4 + 121 + 121 + 4 + 1)
+    for bad in (cfg(board_size=2), cfg(board_size=20), cfg(variant=2), cfg(num_games=0), cfg(agent_mode=3),
+                cfg(variant=0, agent_mode=1), cfg(game_offset=-1), cfg(raw=1, manual_opponent=1), cfg(pool_size=-1)):
+        assert L.hexb_state_bytes(ctypes.byref(bad)) == 0
+        out = ctypes.c_void_p()
+        assert L.hexb_create(ctypes.byref(bad), None, 0, None, ctypes.byref(out)) == -1      # HEXB_ERR_ARG
+    out = ctypes.c_void_p()
+    assert L.hexb_create(ctypes.byref(c), None, 0, None, ctypes.byref(out)) == -3            # HEXB_ERR_STATE: no buffer
+    assert L.hexb_strerror(0) == b"ok" and b"argument" in L.hexb_strerror(-1) and b"unknown" in L.hexb_strerror(-99)
+    for fn, args in (("hexb_step", 10), ("hexb_reset", 6), ("hexb_ply", 4), ("hexb_stats", 3), ("hexb_destroy", 1)):
+        assert getattr(L, fn)(*([None] * args)) == -1                                         # null handle -> HEXB_ERR_ARG
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from hex_gym_env_b200 import HexBatch
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        HexBatch(5, 10)
+    from hex_gym_env_b200.rollout import masked_sample
+    with pytest.raises(RuntimeError, match="GPU only"):
+        masked_sample(torch.zeros(2, 9), torch.ones(2, 9, dtype=torch.uint8))
