@@ -126,9 +126,10 @@ def py_rate(N, seconds, procs):
 def cpu_baseline(N, budget_s=12.0):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     v, sample = py_rate(N, budget_s, cores)
+    p1, _ = py_rate(N, min(budget_s, 4.0), 1)
     c1, _ = cpu_port_rate(N, 2.0, 1)
     cn, _ = cpu_port_rate(N, 3.0, cores)
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "python_loop_1_core": p1,
             "c_port_1_thread": c1, "c_port_all_threads": cn}
 
 
@@ -201,6 +202,30 @@ def run_gpu(args):
     stats = torch.zeros(8, dtype=torch.int64, device=dev)
     for _ in range(Wm):
         env.step()
+    # The step loop is captured in a CUDA graph (GRAPH_STEPS launches per replay) so that the ~3 us launch gap of a Python
+    # loop does not sit between 110 us kernels; K steps = K kernel launches either way.
+    GRAPH_STEPS = 50
+    graph = None
+    if not args.no_graph and K >= 2 * GRAPH_STEPS:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            env.step()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(GRAPH_STEPS):
+                    env.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph.replay()      # (warm-up: these 51 steps are outside the timed region)
+
+    def run_steps(n):
+        if graph is not None:
+            for _ in range(n // GRAPH_STEPS):
+                graph.replay()
+            n %= GRAPH_STEPS
+        for _ in range(n):
+            env.step()
+
     env.stats(out=stats)
     if world > 1:
         dist.all_reduce(stats)
@@ -210,8 +235,7 @@ def run_gpu(args):
     barrier()
     sampler.start()
     e0.record()
-    for _ in range(K):
-        env.step()
+    run_steps(K)
     env.stats(out=stats)
     if world > 1:
         dist.all_reduce(stats)      # K7: the only collective of the path (64 bytes)
@@ -227,8 +251,7 @@ def run_gpu(args):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     k0.record()
-    for _ in range(K):
-        env.step()
+    run_steps(K)
     k1.record()
     torch.cuda.synchronize()
     kern_ms = k0.elapsed_time(k1) / K
@@ -305,7 +328,8 @@ def run_gpu(args):
                        if N == 11 else "%dx%d SelfPlayEnv random self-play" % (N, N),
                        "board_size": N, "games_per_gpu": G, "global_games": world * G, "parallelism": "games sharded by index x%d" % world,
                        "l2_policy": "working set %.0f MB per step > 126 MB L2" % (G * moved_bytes(N) / 1e6),
-                       "agent": "fused on-device random policy (Philox stream per game)", "seed": args.seed},
+                       "agent": "fused on-device random policy (Philox stream per game)", "seed": args.seed,
+                       "launch": ("CUDA graph of %d step launches per replay" % GRAPH_STEPS) if graph is not None else "one launch per step"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches + K + launches_e2e, "clocks": clocks,
             "plies_per_sec": ds[7] / (ms * 1e-3), "episodes_in_timed_region": ds[0],
             "episode_stats": dict(zip(("episodes", "black_wins", "white_wins", "agent_wins", "episode_plies", "invalid_ends",
@@ -330,6 +354,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -72,7 +72,7 @@ constexpr int kCtaThreads = kWarpsPerCta * kWarp;
 constexpr int min_ctas(int n) {
     const int smem = kWarpsPerCta * 32 * (n * n + 4 * (2 * ((n * n + 31) / 32) + 2)) + 64;
     const int by_smem = 220 * 1024 / smem;
-    const int want = 12 * 4 / kWarpsPerCta;   // 48 warps per SM while the record is small
+    const int want = 10 * 4 / kWarpsPerCta;   // 40 warps per SM (48 registers): measured equal to 48 warps, and no spills
     const int cap = 8 * 4 / kWarpsPerCta;
     return n <= 12 ? (want > 32 ? 32 : want) : (by_smem < 1 ? 1 : (by_smem > cap ? cap : by_smem));
 }
