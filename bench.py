@@ -330,7 +330,7 @@ def run_gpu(args):
                        "l2_policy": "working set %.0f MB per step > 126 MB L2" % (G * moved_bytes(N) / 1e6),
                        "agent": "fused on-device random policy (Philox stream per game)", "seed": args.seed,
                        "launch": ("CUDA graph of %d step launches per replay" % GRAPH_STEPS) if graph is not None else "one launch per step"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches + K + launches_e2e, "clocks": clocks,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "gpu_launches_detail": {"timed_region": "%d x hexb_step_kernel + 1 x hexb_stats_kernel" % K, "roofline_region": K, "e2e_region": launches_e2e}, "clocks": clocks,
             "plies_per_sec": ds[7] / (ms * 1e-3), "episodes_in_timed_region": ds[0],
             "episode_stats": dict(zip(("episodes", "black_wins", "white_wins", "agent_wins", "episode_plies", "invalid_ends",
                                        "env_steps", "plies"), ds))}
