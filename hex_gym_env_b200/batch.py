@@ -280,6 +280,40 @@ class HexBatch(object):
                                                                                  "winner", "agent", "draws")], self._stream()))
         return out
 
+    def export_state_host(self, ply_actions=None):
+        """export_state() for host readers (the single-game drop-in classes): ONE kernel into one packed device buffer, ONE
+        device->host copy into pinned memory, numpy views on it. The arrays are overwritten by the next call.
+        ply_actions (host ints, raw handles): first play these moves (hexb_ply) in the same round trip; the dict then also
+        holds "ret" (HexGame.make_move's return codes)."""
+        G, N = self.G, self.N
+        spec = (("board", (G, N, N), torch.float64), ("regions", (G, 2, N + 2, N + 2), torch.float64),
+                ("region_counter", (G, 2), torch.float64), ("draws", (G,), torch.int32), ("cur", (G,), torch.int8),
+                ("done", (G,), torch.uint8), ("winner", (G,), torch.int8), ("agent", (G,), torch.int8), ("ret", (G,), torch.int8))
+        if getattr(self, "_xdev", None) is None:
+            off, views = 0, []
+            for name, shape, dt in spec:
+                n = int(torch.tensor(shape).prod()) * torch.empty((), dtype=dt).element_size()
+                views.append((name, shape, dt, off, n))
+                off = (off + n + 15) // 16 * 16
+            self._xdev = torch.empty(off, dtype=torch.uint8, device=self.device)
+            self._xhost = torch.empty(off, dtype=torch.uint8).pin_memory()
+            self._xviews = views
+            self._xact_host = torch.empty(G, dtype=torch.int32).pin_memory()
+            self._xact_dev = torch.empty(G, dtype=torch.int32, device=self.device)
+            self._xd = {name: self._xdev[o:o + n].view(dt).view(shape) for name, shape, dt, o, n in views}
+            self._xh = {name: self._xhost[o:o + n].view(dt).view(shape).numpy() for name, shape, dt, o, n in views}
+        d = self._xd
+        with torch.cuda.device(self.device):
+            if ply_actions is not None:
+                self._xact_host.numpy()[:] = ply_actions
+                self._xact_dev.copy_(self._xact_host, non_blocking=True)
+                check(self._lib.hexb_ply(self._h, _ptr(self._xact_dev), _ptr(d["ret"]), self._stream()))
+            check(self._lib.hexb_export_state(self._h, *[_ptr(d[k]) for k in ("board", "regions", "region_counter", "cur", "done",
+                                                                               "winner", "agent", "draws")], self._stream()))
+        self._xhost.copy_(self._xdev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._xh
+
     def import_boards(self, board_true, to_move=None):
         b = self._in(board_true, (self.G, self.N, self.N), torch.int8, "board_true")
         tm = self._in(to_move, (self.G,), torch.int8, "to_move")

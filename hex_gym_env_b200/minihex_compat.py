@@ -65,6 +65,7 @@ player_b = {
 }
 
 _DEFAULT_DEVICE = [None]
+_HANDLE_POOL = {}   # (variant, board size, device) -> idle one-game device handles, reused across episodes
 
 
 def set_device(device):
@@ -92,7 +93,14 @@ class DeviceGame(object):
         board = np.asarray(board)
         n = board.shape[1]
         self._n = n
-        self._dev = HexBatch(n, 1, variant=self._variant, device=_DEFAULT_DEVICE[0], raw=True)
+        self._pool_key = (self._variant, n, _DEFAULT_DEVICE[0])
+        idle = _HANDLE_POOL.setdefault(self._pool_key, [])
+        self._dev = None
+        while idle and self._dev is None:
+            cand = idle.pop()
+            self._dev = cand if getattr(cand, "_h", None) else None   # never reuse a handle the garbage collector closed
+        if self._dev is None:
+            self._dev = HexBatch(n, 1, variant=self._variant, device=_DEFAULT_DEVICE[0], raw=True)
         self._dev.reset()
         if self._variant == VARIANT_A:
             true_codes = np.where(board == 0, 0, np.where(board == 1, 1, 2)).astype(np.int8)
@@ -107,15 +115,21 @@ class DeviceGame(object):
         self.empty_fields = int(np.count_nonzero(board == self._empty))
         self._done_host = False
         self._ref_flipped = bool(int(to_move)) if self._variant == VARIANT_B else False  # parity of the env's invert_board() calls
-        self.debug = debug
-        self.make_move = self.make_move_debug if debug else self.fast_move
+        self.debug = debug   # (make_move dispatches on it; no bound method is stored on the instance: that would be a reference cycle)
         self.actions = np.arange(n * n)
         self._cache = None
+
+    def __del__(self):
+        dev, key = getattr(self, "_dev", None), getattr(self, "_pool_key", None)
+        if dev is not None and key is not None and _HANDLE_POOL is not None and getattr(dev, "_h", None):
+            self._dev = None
+            if len(_HANDLE_POOL.setdefault(key, [])) < 8:
+                _HANDLE_POOL[key].append(dev)
 
     # -- state, read back from the device in the reference's layout (float64 like the reference's numpy arrays)
     def _state(self):
         if self._cache is None:
-            self._cache = {k: v.cpu().numpy() for k, v in self._dev.export_state().items()}
+            self._cache = {k: v.copy() for k, v in self._dev.export_state_host().items()}   # one kernel + one copy
         return self._cache
 
     @property
@@ -172,6 +186,10 @@ class DeviceGame(object):
     def get_possible_actions(self):
         return self.actions[self.board.flatten() == self._empty]
 
+    def make_move(self, action):
+        """HexGame.make_move: fast_move, or make_move_debug when the game was built with debug=True (HexGame.py:29-32)."""
+        return self.make_move_debug(action) if self.debug else self.fast_move(action)
+
     def make_move_debug(self, action):
         if not self.is_valid_move(action):
             raise IndexError("Illegal move %s" % (self.action_to_coordinate(action),))
@@ -182,10 +200,11 @@ class DeviceGame(object):
         y, x = self.action_to_coordinate(int(action))
         if not (0 <= int(action) < self._n * self._n):
             raise IndexError("index %d is out of bounds for a %dx%d board" % (int(action), self._n, self._n))
-        ret = int(self._dev.ply(np.array([int(action)], np.int32)).cpu()[0])
+        st = self._dev.export_state_host(ply_actions=[int(action)])   # move + fresh state in one round trip
+        ret = int(st["ret"][0])
         if ret == 3:
             return 3
-        self._cache = None
+        self._cache = {k: v.copy() for k, v in st.items()}
         self.empty_fields -= x if self._variant == VARIANT_A else 1  # variant A: sic, HexGame.py:96
         if ret < 0:
             return None
