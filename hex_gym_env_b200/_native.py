@@ -64,6 +64,7 @@ SYMBOLS = {
     "hexb_export_state": (_i32, [_vp] * 10),
     "hexb_import_boards": (_i32, [_vp] * 4),
     "hexb_stats": (_i32, [_vp] * 3),
+    "hexb_rollout": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hexb_set_opponent_buffers": (_i32, [_vp, _vp, _vp]),
     "hexb_set_info_buffers": (_i32, [_vp, _vp, _vp]),
     "hexb_half_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),

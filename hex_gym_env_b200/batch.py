@@ -160,6 +160,28 @@ class HexBatch(object):
             out["actions"] = actions_out
         return out
 
+    def rollout(self, num_steps, obs=None, mask=None, reward=None, done=None, term_obs=None, actions_out=None, outputs=True):
+        """num_steps env steps in ONE launch with the fused random agent (= step(actions=None) called num_steps times, bit for
+        bit), the state staying on chip in between. Outputs have a leading step dimension, like a rollout buffer:
+        obs i8[T,G,N,N], mask u8[T,G,C], reward f32[T,G], done u8[T,G] (+ term_obs, actions_out when given)."""
+        T, G, N, C = int(num_steps), self.G, self.N, self.C
+        if outputs:
+            obs = self._chk(obs, (T, G, N, N), torch.int8, "obs") if obs is not None else self._buf("r_obs%d" % T, (T, G, N, N), torch.int8)
+            mask = self._chk(mask, (T, G, C), torch.uint8, "mask") if mask is not None else self._buf("r_mask%d" % T, (T, G, C), torch.uint8)
+            reward = self._chk(reward, (T, G), torch.float32, "reward") if reward is not None else self._buf("r_rew%d" % T, (T, G), torch.float32)
+            done = self._chk(done, (T, G), torch.uint8, "done") if done is not None else self._buf("r_done%d" % T, (T, G), torch.uint8)
+        term_obs = self._chk(term_obs, (T, G, N, N), torch.int8, "term_obs")
+        actions_out = self._chk(actions_out, (T, G), torch.int32, "actions_out")
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_rollout(self._h, T, _ptr(obs), _ptr(mask), _ptr(reward), _ptr(done), _ptr(term_obs), _ptr(actions_out),
+                                         self._stream()))
+        out = dict(obs=obs, mask=mask, reward=reward, done=done)
+        if term_obs is not None:
+            out["term_obs"] = term_obs
+        if actions_out is not None:
+            out["actions"] = actions_out
+        return out
+
     def enable_info(self):
         """Also record, at every step(), the fields of the reference's info dict (HexGame.py:281-286) as device tensors:
         self.last_move_opponent i32[G] and self.winner i8[G]; info["last_move_player"] is step(want_actions=True)["actions"]."""

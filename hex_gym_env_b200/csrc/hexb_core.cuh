@@ -102,6 +102,7 @@ struct Params {
     unsigned long long seed;
     int variant, auto_reset, eval_state, opponent_first, agent_mode, mode;
     int raw;  // 1: bare HexGame batch (hexb_ply): reset draws nothing and nobody opens
+    int steps;            // MODE_STEP: env steps per launch (hexb_rollout: T > 1 keeps the state on chip between steps; outputs [T,G,..])
     int manual_opponent;  // 1: the opponent's moves come from the caller (hexb_half_step); resets never play the opening move
     int half_side;        // MODE_HALF: 0 = the agent's ply, 1 = the opponent's ply
     int pool_size;        // setup_opponents: size of the opponent pool the index is drawn from

@@ -85,14 +85,14 @@ struct SmemLayout {
 };
 
 template <int N>
-__device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params &P, long long g0, int lane) {
+__device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params &P, long long g0, int t, int lane) {
     constexpr int C = Geo<N>::C;
-    const long long out0 = g0 * C;        // byte offset of the chunk in obs / mask (multiple of 16)
-    const long long limit = P.G * C;      // bytes that exist in the caller's buffers
+    const long long out0 = (g0 + (long long)t * P.G) * C;   // byte offset of the chunk in obs / mask (row t of [T,G,C])
+    const long long limit = ((long long)t + 1) * P.G * C;   // bytes of that row that exist in the caller's buffers
     const uint4 *src = reinterpret_cast<const uint4 *>(chunk);
     uint8_t *obs = reinterpret_cast<uint8_t *>(P.obs);
     uint8_t *msk = P.mask;
-    const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)msk)) & 15) == 0;
+    const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)msk) | (uintptr_t)out0) & 15) == 0;
     if (vec_ok && obs && msk && out0 + Chunk<N>::BYTES <= limit) {
         // the common case (warp-uniform): whole chunk inside the buffers, both outputs wanted, 16-byte aligned
         uint4 *po = reinterpret_cast<uint4 *>(obs + out0), *pm = reinterpret_cast<uint4 *>(msk + out0);
@@ -164,105 +164,93 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     const long long g = g0 + lane;          // this lane's game
     uint8_t *gl = P.state + wglobal * SL::CHUNK;
 
-    // ---- chunk in (asynchronous: labels and records in ONE bulk copy); meanwhile the two draws of the step, which only need
-    //      the game's meta and stream-position words (two plain loads of lines the bulk copy is fetching anyway)
+    // ---- chunk in (asynchronous: labels and records in ONE bulk copy); meanwhile the two draws of the (first) step, which
+    //      only need the game's meta and stream-position words (two plain loads of lines the bulk copy is fetching anyway)
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, SL::CHUNK);
         bulk_g2s(chunk, gl, SL::CHUNK, bar);
     }
     uint32_t *recw = reinterpret_cast<uint32_t *>(chunk + Geo<N>::CHUNK_LAB) + lane;   // this lane's record word 0 (shared memory)
+    uint32_t *lab32 = reinterpret_cast<uint32_t *>(chunk);
     double u_agent = 0.0, u_opp = 0.0;
-#if defined(HEXB_EXP_NO_PHILOX)     // timing experiment only: a cheap hash instead of the two Philox draws
-    if (STEP_ONLY && g < P.G) {
-        uint32_t h = (uint32_t)g * 2654435761u + rec.draws * 40503u;
-        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-        u_agent = (double)(h >> 8) * (1.0 / 16777216.0);
-        h *= 3266489917u; h ^= h >> 16;
-        u_opp = (double)(h >> 8) * (1.0 / 16777216.0);
-    }
-#else
     if (STEP_ONLY && g < P.G) {
         const uint32_t *grec = reinterpret_cast<const uint32_t *>(gl + Geo<N>::CHUNK_LAB) + lane;
         pre_draws(P, grec[(2 * Geo<N>::W) * kRecStride], grec[(2 * Geo<N>::W + 1) * kRecStride],
                   (unsigned long long)(P.game_offset + g), u_agent, u_opp);
     }
-#endif
     __syncwarp();  // the barrier's initialisation is visible to the other lanes
     mbar_wait(bar, 0);
     Rec<N> rec;
     load_rec<N>(recw, rec);
-
-    // ---- thread-per-game phase
-    uint32_t prmA = 0, prmB = 0, flg = 0;
     uint8_t *L = chunk + lane * C;
-    if (STEP_ONLY) {
-        Loc loc;
-#if defined(HEXB_EXP_NO_COMPUTE)   // timing experiment only: memory pipeline without the plies
-        loc.reward = 0.f; loc.action = 0;
-        for (int i = 0; i < 8; ++i) loc.st[i] = 0;
-        rec.draws++;
-#else
-        game_step<N>(L, P, g, rec, u_agent, u_opp, loc, prmA, prmB, flg);
-#endif
-#if defined(HEXB_EXP_NO_ROWJOBS)   // timing experiment only
-        flg &= ~F_ROWJOB;
-#endif
-        // K7: episode statistics - the eight per-game increments are packed into two words (fields wide enough for the
-        // sum over 32 lanes), reduced with two redux.sync, and lane 0 adds the non-zero counters to this warp's stripe
-        const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) | ((uint32_t)loc.st[3] << 18) |
-                            ((uint32_t)loc.st[5] << 24);
-        const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
-        add_stats(P, wglobal, lane, __reduce_add_sync(FULL, pa), __reduce_add_sync(FULL, pb));
-    } else if (P.mode == MODE_RESET) {
-        game_reset<N>(P, g, rec, flg);
-    } else if (P.mode == MODE_HALF) {
-        Loc loc;
-        game_half<N>(L, P, g, rec, loc, prmA, prmB, flg);
-        const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) | ((uint32_t)loc.st[3] << 18) |
-                            ((uint32_t)loc.st[5] << 24);
-        const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
-        add_stats(P, wglobal, lane, __reduce_add_sync(FULL, pa), __reduce_add_sync(FULL, pb));
-    } else {
-        game_ply<N>(L, P, g, rec, prmA, flg);
-    }
-    if (g < P.G) store_rec<N>(recw, rec);
-    __syncwarp();  // every game's new stones and record are in shared memory
 
-    // ---- warp-per-game row jobs, part 1 (rare): games that finished - terminal observation, clear, opening stone
-    uint32_t pending = __ballot_sync(FULL, (flg & (F_RESET | F_TERM)) != 0u);
-    while (pending) {
-        const int r = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const uint32_t rf = __shfl_sync(FULL, flg, r);
-        row_job_lane<N>(chunk, r, 0u, 0u, rf & ~F_RELABEL, P, g0 + r, lane, [] { __syncwarp(); });
-        __syncwarp();
-    }
+    // One env step per iteration. hexb_step launches with steps == 1; hexb_rollout runs T steps with the chunk staying in
+    // shared memory and the records in registers: the state crosses HBM once per launch instead of once per step.
+    const int steps = STEP_ONLY ? P.steps : 1;
+    for (int t = 0; t < steps; ++t) {
+        // ---- thread-per-game phase
+        uint32_t prmA = 0, prmB = 0, flg = 0;
+        if (STEP_ONLY) {
+            if (t > 0 && g < P.G) pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+            Loc loc;
+            game_step<N>(L, P, g, t, rec, u_agent, u_opp, loc, prmA, prmB, flg);
+            // K7: episode statistics - the eight per-game increments are packed into two words (fields wide enough for the
+            // sum over 32 lanes), reduced with two redux.sync, and lane 0 adds the non-zero counters to this warp's stripe
+            const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) |
+                                ((uint32_t)loc.st[3] << 18) | ((uint32_t)loc.st[5] << 24);
+            const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
+            add_stats(P, wglobal, lane, __reduce_add_sync(FULL, pa), __reduce_add_sync(FULL, pb));
+        } else if (P.mode == MODE_RESET) {
+            game_reset<N>(P, g, rec, flg);
+        } else if (P.mode == MODE_HALF) {
+            Loc loc;
+            game_half<N>(L, P, g, rec, loc, prmA, prmB, flg);
+            const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) |
+                                ((uint32_t)loc.st[3] << 18) | ((uint32_t)loc.st[5] << 24);
+            const uint32_t pb = (uint32_t)loc.st[4] | ((uint32_t)loc.st[6] << 14) | ((uint32_t)loc.st[7] << 20);
+            add_stats(P, wglobal, lane, __reduce_add_sync(FULL, pa), __reduce_add_sync(FULL, pb));
+        } else {
+            game_ply<N>(L, P, g, rec, prmA, flg);
+        }
+        __syncwarp();  // every game's new stones are in shared memory
 
-    // ---- observation + mask. They depend on emptiness and owner bits only, not on the labels, so they are issued BEFORE
-    //      the relabel sweeps: the output stores drain to HBM while the warp works through its relabel rows.
-    if ((STEP_ONLY || (P.mode != MODE_PLY && P.mode != MODE_HALF)) && (P.obs || P.mask)) {
-        encode_chunk<N>(chunk, P, g0, lane);
-        uint32_t views = __ballot_sync(FULL, (flg & F_VIEW_OPP) != 0u);  // only without auto-reset: finished by the agent's own ply
-        if (views) __syncwarp();
-        while (views) {
-            const int r = __ffs(views) - 1;
-            views &= views - 1;
-            view_row_lane<N>(chunk, r, P, g0 + r, lane);
+        // ---- warp-per-game row jobs, part 1 (rare): games that finished - terminal observation, clear, opening stone
+        uint32_t pending = __ballot_sync(FULL, (flg & (F_RESET | F_TERM)) != 0u);
+        while (pending) {
+            const int r = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t rf = __shfl_sync(FULL, flg, r);
+            row_job_lane<N>(chunk, r, 0u, 0u, rf & ~F_RELABEL, P, g0 + r + (long long)t * P.G, lane, [] { __syncwarp(); });
+            __syncwarp();
+        }
+
+        // ---- observation + mask. They depend on emptiness and owner bits only, not on the labels, so they are issued
+        //      BEFORE the relabel sweeps: the output stores drain to HBM while the warp works through its relabel rows.
+        if ((STEP_ONLY || (P.mode != MODE_PLY && P.mode != MODE_HALF)) && (P.obs || P.mask)) {
+            encode_chunk<N>(chunk, P, g0, t, lane);
+            uint32_t views = __ballot_sync(FULL, (flg & F_VIEW_OPP) != 0u);  // only without auto-reset: finished by the agent's own ply
+            if (views) __syncwarp();
+            while (views) {
+                const int r = __ffs(views) - 1;
+                views &= views - 1;
+                view_row_lane<N>(chunk, r, P, g0 + r + (long long)t * P.G, lane);
+            }
+        }
+
+        // ---- warp-per-game row jobs, part 2: relabel sweeps (regions[regions == label] = new label, both plies at once)
+        pending = __ballot_sync(FULL, (flg & (F_RELABEL | F_RESET)) == F_RELABEL);
+        while (pending) {
+            const int r = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r);
+            relabel_row_lane<N>(lab32, r, ra, rb, lane, P.one);
+            __syncwarp();   // (sweeping two non-adjacent rows per iteration for ILP was measured: slower, 114 vs 111 us)
         }
     }
 
-    // ---- warp-per-game row jobs, part 2: relabel sweeps (regions[regions == label] = new label, both plies at once)
-    pending = __ballot_sync(FULL, (flg & (F_RELABEL | F_RESET)) == F_RELABEL);
-    while (pending) {
-        const int r = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r);
-        relabel_row_lane<N>(reinterpret_cast<uint32_t *>(chunk), r, ra, rb, lane, P.one);
-        __syncwarp();   // (sweeping two non-adjacent rows per iteration for ILP was measured: slower, 114 vs 111 us)
-    }
-
     // ---- chunk out
+    if (g < P.G) store_rec<N>(recw, rec);
     fence_async_smem();  // generic-proxy writes to shared memory -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
@@ -573,8 +561,25 @@ int32_t hexb_step(hexb_env *env, const int32_t *actions, const double *opp_u, in
     CK(cudaSetDevice(env->cfg.device));
     Params P = env->base;
     P.mode = MODE_STEP;
+    P.steps = 1;
     P.actions = actions;
     P.opp_u = opp_u;
+    P.obs = obs;
+    P.mask = mask;
+    P.reward = reward;
+    P.done = done;
+    P.term_obs = term_obs;
+    P.actions_out = actions_out;
+    return dispatch_tile(env, P, (cudaStream_t)stream);
+}
+
+int32_t hexb_rollout(hexb_env *env, int32_t num_steps, int8_t *obs, uint8_t *mask, float *reward, uint8_t *done, int8_t *term_obs,
+                     int32_t *actions_out, void *stream) {
+    if (!env || env->cfg.raw || env->cfg.manual_opponent || num_steps < 1 || num_steps > 65536) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    Params P = env->base;
+    P.mode = MODE_STEP;
+    P.steps = num_steps;
     P.obs = obs;
     P.mask = mask;
     P.reward = reward;

@@ -90,9 +90,10 @@ HEXB_HD void pre_draws(const Params &P, uint32_t meta, uint32_t draws, unsigned 
 // game's stream first, exactly like the reference loop  a = BaseRandomPolicy().choose_action(obs); env.step(a).
 // L = this game's C label bytes. prmA / prmB = relabel requests of the two plies, flg = row job for the warp.
 template <int N>
-HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, double u_agent, double u_opp, Loc &loc, uint32_t &prmA,
-                       uint32_t &prmB, uint32_t &flg) {
+HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &rec, double u_agent, double u_opp, Loc &loc,
+                       uint32_t &prmA, uint32_t &prmB, uint32_t &flg) {
     constexpr int C = Geo<N>::C;
+    const long long o = g + (long long)t * P.G;  // output slot: step t of a multi-step launch (hexb_rollout) writes row t of [T,G]
     loc.reward = 0.f;
     loc.action = -1;
 #pragma unroll
@@ -100,9 +101,9 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
     prmA = 0; prmB = 0; flg = 0;
     if (g >= P.G) return;
     if (!(rec.meta & M_LIVE)) {  // never reset: nothing to play
-        if (P.reward) P.reward[g] = 0.f;
-        if (P.done) P.done[g] = 1;
-        if (P.actions_out) P.actions_out[g] = -1;
+        if (P.reward) P.reward[o] = 0.f;
+        if (P.done) P.done[o] = 1;
+        if (P.actions_out) P.actions_out[o] = -1;
         return;
     }
     const unsigned long long gid = (unsigned long long)(P.game_offset + g);
@@ -170,9 +171,9 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, Rec<N> &rec, do
         loc.st[5] = (rec.meta & M_INVALID) != 0u;
         if (P.term_obs) flg |= F_TERM | (((rec.meta & M_AGENT_ENDED) && P.variant == VARIANT_B) ? F_TERM_OPP : 0u);
     }
-    if (P.reward) P.reward[g] = loc.reward;
-    if (P.done) P.done[g] = is_done ? 1 : 0;
-    if (P.actions_out) P.actions_out[g] = loc.action;
+    if (P.reward) P.reward[o] = loc.reward;
+    if (P.done) P.done[o] = is_done ? 1 : 0;
+    if (P.actions_out) P.actions_out[o] = loc.action;
     if (P.info_opp) P.info_opp[g] = opp_move;
     if (P.info_winner) {  // HexEnv.winner (HexGame.py:251,347 / HexSingleGame.py:239): the last make_move's return value
         const uint32_t w = (rec.meta & M_WIN_MASK) >> M_WIN_SHIFT;

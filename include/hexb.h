@@ -100,6 +100,15 @@ int32_t hexb_reset(hexb_env *env, const uint8_t *reset_mask, const double *open_
 int32_t hexb_step(hexb_env *env, const int32_t *actions, const double *opp_u, int8_t *obs, uint8_t *mask, float *reward,
                   uint8_t *done, int8_t *term_obs, int32_t *actions_out, void *stream);
 
+/* T env steps in ONE launch with the fused random agent (the reference's random-vs-random rollout loop,
+ *   for t in range(T): a = BaseRandomPolicy().choose_action(obs); obs, r, done, _, _ = env.step(a); reset on done,
+ * i.e. hexb_step(actions = null) called T times) with the packed state staying on chip between steps: a warp keeps its 32 games
+ * in shared memory and registers and the state crosses HBM once per launch instead of once per step. Bit-identical to T calls
+ * of hexb_step. Every output gets a leading step dimension: obs i8[T,G,N,N], mask u8[T,G,N*N], reward f32[T,G], done u8[T,G],
+ * term_obs i8[T,G,N,N], actions_out i32[T,G] (each nullable) - the layout of a rollout buffer. */
+int32_t hexb_rollout(hexb_env *env, int32_t num_steps, int8_t *obs, uint8_t *mask, float *reward, uint8_t *done, int8_t *term_obs,
+                     int32_t *actions_out, void *stream);
+
 /* Optional per-game outputs of every following hexb_step (null = off): what the reference returns in the info dict of variant-A
  * HexEnv.step (HexGame.py:281-286) - last_move_opponent i32[G] (the opponent's move of this step as HexEnv reports it: variant A
  * the true cell, variant B the cell in the opponent's own view; -1 if it did not move) and winner i8[G] (env.winner: -1 None,

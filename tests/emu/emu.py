@@ -41,6 +41,7 @@ def lib():
         L.emu_set_manual_opponent.argtypes = [vp, i32, vp, vp]
         L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
         L.emu_set_info.argtypes = [vp, vp, vp]
+        L.emu_rollout.argtypes = [vp, i32] + [vp] * 6
         _LIB = L
     return _LIB
 
@@ -99,6 +100,14 @@ class EmuBatch(object):
         out = dict(reward=reward, done=done, to_move=self.to_move.copy(), opp_index=self.opp_index.copy())
         if want_term:
             out["term_obs"] = term
+        return out
+
+    def rollout(self, T, want_term=False):
+        G, N, C = self.G, self.N, self.C
+        out = dict(obs=np.empty((T, G, N, N), np.int8), mask=np.empty((T, G, C), np.uint8), reward=np.empty((T, G), np.float32),
+                   done=np.empty((T, G), np.uint8), term_obs=np.zeros((T, G, N, N), np.int8), actions=np.empty((T, G), np.int32))
+        lib().emu_rollout(self._h, T, _p(out["obs"]), _p(out["mask"]), _p(out["reward"]), _p(out["done"]),
+                          _p(out["term_obs"]) if want_term else None, _p(out["actions"]))
         return out
 
     def enable_info(self):

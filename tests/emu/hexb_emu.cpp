@@ -32,52 +32,55 @@ static void run_tiles(Params P) {
     std::vector<Rec<N>> recs(kWarp);
     std::vector<Loc> locs(kWarp);
     uint32_t prmA[kWarp], prmB[kWarp], flg[kWarp];
+    const int steps = P.mode == MODE_STEP ? P.steps : 1;
     for (long long g0 = 0; g0 < P.Gpad; g0 += kWarp) {   // one "warp" = one chunk of 32 games at a time
         uint8_t *gl = P.state + (g0 / kWarp) * Geo<N>::CHUNK_STATE;
         memcpy(chunk, gl, Geo<N>::CHUNK_STATE);
         uint32_t *recw = reinterpret_cast<uint32_t *>(chunk + Geo<N>::CHUNK_LAB);
-        for (int t = 0; t < kWarp; ++t) {
-            load_rec<N>(recw + t, recs[t]);
-            prmA[t] = prmB[t] = flg[t] = 0;
-        }
-        for (int t = 0; t < kWarp; ++t) {   // thread-per-game phase
-            const long long g = g0 + t;
-            uint8_t *L = chunk + t * C;
-            if (P.mode == MODE_STEP) {
-                double ua = 0.0, uo = 0.0;
-                if (g < P.G) pre_draws(P, recs[t].meta, recs[t].draws, (unsigned long long)(P.game_offset + g), ua, uo);
-                game_step<N>(L, P, g, recs[t], ua, uo, locs[t], prmA[t], prmB[t], flg[t]);
-                for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
-            } else if (P.mode == MODE_RESET) {
-                game_reset<N>(P, g, recs[t], flg[t]);
-            } else if (P.mode == MODE_HALF) {
-                game_half<N>(L, P, g, recs[t], locs[t], prmA[t], prmB[t], flg[t]);
-                for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
-            } else {
-                game_ply<N>(L, P, g, recs[t], prmA[t], flg[t]);
+        for (int t = 0; t < kWarp; ++t) load_rec<N>(recw + t, recs[t]);
+        for (int st = 0; st < steps; ++st) {   // hexb_rollout: several env steps on the resident chunk
+            const long long so = (long long)st * P.G;
+            for (int t = 0; t < kWarp; ++t) {   // thread-per-game phase
+                const long long g = g0 + t;
+                uint8_t *L = chunk + t * C;
+                prmA[t] = prmB[t] = flg[t] = 0;
+                if (P.mode == MODE_STEP) {
+                    double ua = 0.0, uo = 0.0;
+                    if (g < P.G) pre_draws(P, recs[t].meta, recs[t].draws, (unsigned long long)(P.game_offset + g), ua, uo);
+                    game_step<N>(L, P, g, st, recs[t], ua, uo, locs[t], prmA[t], prmB[t], flg[t]);
+                    for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
+                } else if (P.mode == MODE_RESET) {
+                    game_reset<N>(P, g, recs[t], flg[t]);
+                } else if (P.mode == MODE_HALF) {
+                    game_half<N>(L, P, g, recs[t], locs[t], prmA[t], prmB[t], flg[t]);
+                    for (int i = 0; i < 8; ++i) P.stats[i] += locs[t].st[i];
+                } else {
+                    game_ply<N>(L, P, g, recs[t], prmA[t], flg[t]);
+                }
             }
-            if (g < P.G) store_rec<N>(recw + t, recs[t]);
-        }
-        for (int r = 0; r < kWarp; ++r) {   // warp-per-game row jobs; a lane-level barrier = finish the loop over lanes
-            if (!(flg[r] & F_ROWJOB)) continue;
-            if (flg[r] & F_TERM)
-                for (int lane = 0; lane < kWarp; ++lane) term_row_lane<N>(chunk, r, flg[r], P, g0 + r, lane);
-            for (int lane = 0; lane < kWarp; ++lane)
-                row_job_lane<N>(chunk, r, prmA[r], prmB[r], flg[r] & ~F_TERM, P, g0 + r, lane, [] {});
-        }
-        if (P.mode != MODE_PLY && P.mode != MODE_HALF && (P.obs || P.mask)) {   // elementwise encode, then the rare opponent-view rows
-            const long long out0 = g0 * C, limit = P.G * C;
-            for (int i = 0; i < Chunk<N>::VECS; ++i) {
-                Vec4 in, o, m;
-                memcpy(&in, chunk + 16 * i, 16);
-                encode_vec<N>(in, P.variant, o, m);
-                if (P.obs) store_tail(reinterpret_cast<uint8_t *>(P.obs), out0 + 16ll * i, limit, o);
-                if (P.mask) store_tail(P.mask, out0 + 16ll * i, limit, m);
+            for (int r = 0; r < kWarp; ++r) {   // warp-per-game row jobs; a lane-level barrier = finish the loop over lanes
+                if (!(flg[r] & F_ROWJOB)) continue;
+                if (flg[r] & F_TERM)
+                    for (int lane = 0; lane < kWarp; ++lane) term_row_lane<N>(chunk, r, flg[r], P, g0 + r + so, lane);
+                for (int lane = 0; lane < kWarp; ++lane)
+                    row_job_lane<N>(chunk, r, prmA[r], prmB[r], flg[r] & ~F_TERM, P, g0 + r + so, lane, [] {});
             }
-            for (int r = 0; r < kWarp; ++r)
-                if (flg[r] & F_VIEW_OPP)
-                    for (int lane = 0; lane < kWarp; ++lane) view_row_lane<N>(chunk, r, P, g0 + r, lane);
+            if (P.mode != MODE_PLY && P.mode != MODE_HALF && (P.obs || P.mask)) {   // elementwise encode, then the rare opponent-view rows
+                const long long out0 = (g0 + so) * C, limit = (so + P.G) * C;
+                for (int i = 0; i < Chunk<N>::VECS; ++i) {
+                    Vec4 in, o, m;
+                    memcpy(&in, chunk + 16 * i, 16);
+                    encode_vec<N>(in, P.variant, o, m);
+                    if (P.obs) store_tail(reinterpret_cast<uint8_t *>(P.obs), out0 + 16ll * i, limit, o);
+                    if (P.mask) store_tail(P.mask, out0 + 16ll * i, limit, m);
+                }
+                for (int r = 0; r < kWarp; ++r)
+                    if (flg[r] & F_VIEW_OPP)
+                        for (int lane = 0; lane < kWarp; ++lane) view_row_lane<N>(chunk, r, P, g0 + r + so, lane);
+            }
         }
+        for (int t = 0; t < kWarp; ++t)
+            if (g0 + t < P.G) store_rec<N>(recw + t, recs[t]);
         memcpy(gl, chunk, Geo<N>::CHUNK_STATE);
     }
 }
@@ -152,7 +155,14 @@ void emu_step(void *h, const int32_t *actions, const double *opp_u, int8_t *obs,
               int8_t *term_obs, int32_t *actions_out) {
     emu_env *e = (emu_env *)h;
     Params P = e->base;
-    P.mode = MODE_STEP; P.actions = actions; P.opp_u = opp_u; P.obs = obs; P.mask = mask; P.reward = reward; P.done = done;
+    P.mode = MODE_STEP; P.steps = 1; P.actions = actions; P.opp_u = opp_u; P.obs = obs; P.mask = mask; P.reward = reward; P.done = done;
+    P.term_obs = term_obs; P.actions_out = actions_out;
+    dispatch(e, P);
+}
+void emu_rollout(void *h, int steps, int8_t *obs, uint8_t *mask, float *reward, uint8_t *done, int8_t *term_obs, int32_t *actions_out) {
+    emu_env *e = (emu_env *)h;
+    Params P = e->base;
+    P.mode = MODE_STEP; P.steps = steps; P.obs = obs; P.mask = mask; P.reward = reward; P.done = done;
     P.term_obs = term_obs; P.actions_out = actions_out;
     dispatch(e, P);
 }

@@ -34,6 +34,13 @@ class GpuBatch(object):
         out["to_move"], out["opp_index"] = self.opp_state()
         return out
 
+    def rollout(self, T, want_term=False):
+        G, N = self.G, self.N
+        term = torch.zeros((T, G, N, N), dtype=torch.int8, device="cuda") if want_term else None
+        acts = torch.empty((T, G), dtype=torch.int32, device="cuda")
+        o = self.b.rollout(T, term_obs=term, actions_out=acts)
+        return {k: self._np(v) for k, v in o.items()}
+
     def enable_info(self):
         self.b.enable_info()
 

@@ -212,3 +212,26 @@ def golden_oppmodel(make, name):
         eq(e["region_counter"], z["counter"][t].astype(np.float64), w + "counter")
         eq(e["cur"], z["sim_cur"][t], w + "cur")
         eq(e["draws"], z["draws"][t], w + "draws")
+
+
+def rollout_equals_steps(make, kind, N, G, T, seed=0, **kw):
+    """hexb_rollout(T) is bit-identical to T calls of hexb_step(actions=None), and both match the oracle."""
+    a = make(kind, N, G, seed=seed, **kw)
+    b = make(kind, N, G, seed=seed, **kw)
+    ref = hexref.RefBatch(kind, N, G, seed=seed, **kw)
+    a.reset(); b.reset(); ref.reset()
+    for rep in range(2):    # two launches back to back: the state carried between launches is right too
+        ro = a.rollout(T, want_term=True)
+        for t in range(T):
+            so = b.step(want_term=True)
+            r = ref.step(want_term=True)
+            w = "rollout rep=%d t=%d " % (rep, t)
+            for key, okey in (("obs", "obs"), ("mask", "mask"), ("reward", "reward"), ("done", "done"), ("actions", "actions")):
+                eq(ro[okey][t], so[key], w + key + " vs steps")
+                eq(ro[okey][t], r[key], w + key + " vs oracle")
+            d = r["done"].astype(bool)
+            eq(ro["term_obs"][t][d], r["term_obs"][d], w + "term_obs")
+        ea, eb = a.export(), b.export()
+        for key in STATE_KEYS:
+            eq(ea[key], eb[key], "rollout state " + key)
+        eq(a.stats(), b.stats(), "rollout stats")

@@ -85,3 +85,9 @@ def test_preset_board_rebuild(N):
 def test_half_step_vs_oracle(N, kind):
     from test_gpu_parity import test_half_step_vs_oracle as driver
     driver(make, N, kind)
+
+
+@pytest.mark.parametrize("N,kind,kw", [(5, hexref.KIND_SELFPLAY_B, dict(agent_mode=2)), (11, hexref.KIND_SELFPLAY_B, dict(agent_mode=1)),
+                                       (6, hexref.KIND_ENV_A, dict(opponent_first=True))])
+def test_rollout_equals_steps(N, kind, kw):
+    parity.rollout_equals_steps(make, kind, N, 100, N * N // 2 + 3, seed=N, **kw)

@@ -217,3 +217,9 @@ def test_step_with_opponent_on_device():
         assert torch.equal(out["obs"], obs) and torch.equal(out["mask"], mask) and torch.equal(out["reward"], rew) and torch.equal(out["done"], done)
         assert bool((a.to_move == 0).all())
     assert int(a.stats()[0]) > 0 and int(a.stats()[5]) == 0
+
+
+@pytest.mark.parametrize("N,kind,kw", [(5, hexref.KIND_SELFPLAY_B, dict(agent_mode=2)), (11, hexref.KIND_SELFPLAY_B, dict(agent_mode=2)),
+                                       (7, hexref.KIND_ENV_A, dict(opponent_first=True)), (19, hexref.KIND_SELFPLAY_B, dict(agent_mode=0))])
+def test_rollout_equals_steps(make, N, kind, kw):
+    parity.rollout_equals_steps(make, kind, N, 1000 if N < 19 else 300, min(N * N // 2 + 3, 64), seed=N, **kw)

@@ -45,3 +45,16 @@ for _ in range(K):
 e1.record()
 torch.cuda.synchronize()
 print("no-output: %.1f us/step device" % (1e3 * e0.elapsed_time(e1) / K))
+# multi-step launches (hexb_rollout): state stays on chip, outputs [T,G,..]
+for T in (4, 16, 32):
+    if T * G * (2 * N * N + 5) > 40e9:
+        continue
+    env.rollout(T)
+    torch.cuda.synchronize()
+    reps = max(1, 320 // T)
+    e0.record()
+    for _ in range(reps):
+        env.rollout(T)
+    e1.record()
+    torch.cuda.synchronize()
+    print("rollout T=%d: %.1f us/step device" % (T, 1e3 * e0.elapsed_time(e1) / (reps * T)))
