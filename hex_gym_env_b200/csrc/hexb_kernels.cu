@@ -148,10 +148,13 @@ __device__ __forceinline__ void add_stats(const Params &P, long long wglobal, in
     if (sb >> 20) atomicAdd(stripe + 7, (unsigned long long)(sb >> 20));
 }
 
-// STEP_ONLY = true: the instantiation the timed path launches (MODE_STEP only, nothing else compiled in);
-// STEP_ONLY = false: reset / raw ply / half step, selected at run time by P.mode.
-template <int N, bool STEP_ONLY>
+// KIND_STEP: the instantiation the timed path launches (one env step, nothing else compiled in, step index folded to 0);
+// KIND_ROLLOUT: P.steps env steps per launch on the resident chunk (hexb_rollout);
+// KIND_OTHER: reset / raw ply / half step, selected at run time by P.mode.
+enum : int { KIND_OTHER = 0, KIND_STEP = 1, KIND_ROLLOUT = 2 };
+template <int N, int KIND>
 __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(const Params P) {
+    constexpr bool STEP_ONLY = KIND != KIND_OTHER;
     extern __shared__ __align__(128) uint8_t smem[];
     using SL = SmemLayout<N>;
     constexpr int C = Geo<N>::C;
@@ -187,8 +190,9 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
 
     // One env step per iteration. hexb_step launches with steps == 1; hexb_rollout runs T steps with the chunk staying in
     // shared memory and the records in registers: the state crosses HBM once per launch instead of once per step.
-    const int steps = STEP_ONLY ? P.steps : 1;
-    for (int t = 0; t < steps; ++t) {
+    const int steps = KIND == KIND_ROLLOUT ? P.steps : 1;
+    for (int tt = 0; tt < steps; ++tt) {
+        const int t = KIND == KIND_ROLLOUT ? tt : 0;   // a compile-time 0 on the single-step path
         // ---- thread-per-game phase
         uint32_t prmA = 0, prmB = 0, flg = 0;
         if (STEP_ONLY) {
@@ -213,7 +217,8 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         } else {
             game_ply<N>(L, P, g, rec, prmA, flg);
         }
-        __syncwarp();  // every game's new stones are in shared memory
+        if ((KIND != KIND_ROLLOUT || tt == steps - 1) && g < P.G) store_rec<N>(recw, rec);
+        __syncwarp();  // every game's new stones (and record) are in shared memory
 
         // ---- warp-per-game row jobs, part 1 (rare): games that finished - terminal observation, clear, opening stone
         uint32_t pending = __ballot_sync(FULL, (flg & (F_RESET | F_TERM)) != 0u);
@@ -250,7 +255,6 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     }
 
     // ---- chunk out
-    if (g < P.G) store_rec<N>(recw, rec);
     fence_async_smem();  // generic-proxy writes to shared memory -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
@@ -476,16 +480,19 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     constexpr int smem = SmemLayout<N>::BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_STEP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_ROLLOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_ROLLOUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_OTHER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done = true;
     }
     const unsigned grid = (unsigned)(P.Gpad / kCtaThreads);
     (void)e;
-    if (P.mode == MODE_STEP) hexb_step_kernel<N, true><<<grid, kCtaThreads, smem, s>>>(P);
-    else hexb_step_kernel<N, false><<<grid, kCtaThreads, smem, s>>>(P);
+    if (P.mode == MODE_STEP && P.steps == 1) hexb_step_kernel<N, KIND_STEP><<<grid, kCtaThreads, smem, s>>>(P);
+    else if (P.mode == MODE_STEP) hexb_step_kernel<N, KIND_ROLLOUT><<<grid, kCtaThreads, smem, s>>>(P);
+    else hexb_step_kernel<N, KIND_OTHER><<<grid, kCtaThreads, smem, s>>>(P);
     CK(cudaGetLastError());
     return HEXB_OK;
 }
