@@ -62,7 +62,7 @@ SYMBOLS = {
     "hexb_encode": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "hexb_sample_actions": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "hexb_export_state": (_i32, [_vp] * 10),
-    "hexb_import_boards": (_i32, [_vp] * 4),
+    "hexb_import_boards": (_i32, [_vp] * 5),
     "hexb_stats": (_i32, [_vp] * 3),
     "hexb_rollout": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hexb_set_opponent_buffers": (_i32, [_vp, _vp, _vp]),

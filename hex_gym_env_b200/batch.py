@@ -223,7 +223,7 @@ class HexBatch(object):
         """One ply of `side` (0 agent, 1 opponent) in every game whose turn it is; actions i32[G] in the mover's own view.
         Returns dict(reward, done [, term_obs]); self.to_move / self.opp_index are updated in place."""
         G, N = self.G, self.N
-        a = self._in(actions, (G,), torch.int32, "actions")
+        a = self._in(actions, (G,), torch.int32, "actions")   # None (side 1 only): the built-in random opponent moves
         reward = self._chk(reward, (G,), torch.float32, "reward") if reward is not None else self._buf("h_reward%d" % side, (G,), torch.float32)
         done = self._chk(done, (G,), torch.uint8, "done") if done is not None else self._buf("h_done%d" % side, (G,), torch.uint8)
         if term_obs is not None:
@@ -336,11 +336,35 @@ class HexBatch(object):
         torch.cuda.current_stream(self.device).synchronize()
         return self._xh
 
-    def import_boards(self, board_true, to_move=None):
+    def state_dict(self):
+        """Checkpoint of the whole shard: the packed device state (labels, records, statistics) plus the configuration it
+        belongs to. The reference never saves env state; this is the batched equivalent of pickling the env."""
+        torch.cuda.current_stream(self.device).synchronize()
+        off = self._state_ptr - self._state.data_ptr()
+        cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
+        return {"config": cfg, "state": self._state[off:off + self.state_bytes].clone()}
+
+    def load_state_dict(self, sd):
+        cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
+        if sd["config"] != cfg:
+            raise ValueError("checkpoint belongs to a different configuration: %r vs %r" % (sd["config"], cfg))
+        off = self._state_ptr - self._state.data_ptr()
+        self._state[off:off + self.state_bytes].copy_(sd["state"].to(self.device))
+
+    def import_boards(self, board_true, to_move=None, import_mask=None):
+        """Overwrite games with preset positions (true coordinates, 0 BLACK / 1 WHITE / 2 EMPTY); labels are rebuilt in raster
+        order like HexGame.__init__ does. On an env handle this is reset(sample_board=True) for the masked games."""
         b = self._in(board_true, (self.G, self.N, self.N), torch.int8, "board_true")
         tm = self._in(to_move, (self.G,), torch.int8, "to_move")
+        im = self._in(import_mask, (self.G,), torch.uint8, "import_mask")
         with torch.cuda.device(self.device):
-            check(self._lib.hexb_import_boards(self._h, _ptr(b), _ptr(tm), self._stream()))
+            check(self._lib.hexb_import_boards(self._h, _ptr(b), _ptr(tm), _ptr(im), self._stream()))
+
+    def opponent_catch_up(self):
+        """Let the built-in random opponent move in every game where it is to move (after import_boards on an env handle):
+        SelfPlayEnv.reset -> continue_game (SelfplayWrapper.py:79-80)."""
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_half_step(self._h, 1, None, None, None, None, self._stream()))
 
     def stats(self, out=None):
         """Episode statistics since creation as a device int64[8] tensor (see STAT_NAMES)."""

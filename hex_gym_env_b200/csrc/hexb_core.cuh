@@ -347,7 +347,7 @@ HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) 
 // one byte, optionally seen from the opponent's side (sign swap; the caller transposes the cell index)
 HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &msk) {
     msk = (b == 0u);
-    if (variant == VARIANT_A) return b == 0u ? 2u : (b >> 7);
+    if (variant == VARIANT_A) return b == 0u ? 2u : ((b >> 7) ^ (opp_view ? 1u : 0u));  // invert_board swaps 0 <-> 1 (HexGame.py:297-303)
     if (b == 0u) return 0u;
     const bool own = ((b >> 7) != 0u) == opp_view;  // R is "own" in the agent's view, C in the opponent's
     return own ? 0xffu : 0x01u;

@@ -279,9 +279,9 @@ __global__ void hexb_export_kernel(View V, double *board, double *regions, doubl
     if (i < V.G * 2 * (V.N + 2) * (V.N + 2)) export_at(V, i, board, regions, counter, cur, done, winner, agent, draws);
 }
 template <int N>
-__global__ void hexb_import_kernel(Params P, const int8_t *board_true, const int8_t *to_move) {
+__global__ void hexb_import_kernel(Params P, const int8_t *board_true, const int8_t *to_move, const uint8_t *import_mask) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < P.G) import_game<N>(P, g, board_true, to_move);
+    if (g < P.G) import_game<N>(P, g, board_true, to_move, import_mask);
 }
 
 __global__ void hexb_stats_kernel(const long long *src, int64_t *dst) {
@@ -538,7 +538,9 @@ int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to
 
 int32_t hexb_half_step(hexb_env *env, int32_t side, const int32_t *actions, float *reward, uint8_t *done, int8_t *term_obs,
                        void *stream) {
-    if (!env || !actions || env->cfg.raw || !env->cfg.manual_opponent || (side != 0 && side != 1)) return HEXB_ERR_ARG;
+    // actions == null is allowed for side 1 only: the built-in random opponent moves (positions imported with the opponent to move)
+    if (!env || env->cfg.raw || (side != 0 && side != 1) || (!actions && side != 1)) return HEXB_ERR_ARG;
+    if (!env->cfg.manual_opponent) return HEXB_ERR_ARG;   // fused handles step with hexb_step; their resets already open
     CK(cudaSetDevice(env->cfg.device));
     Params P = env->base;
     P.mode = MODE_HALF;
@@ -673,14 +675,14 @@ int32_t hexb_export_state(hexb_env *env, double *board, double *regions, double 
     return HEXB_OK;
 }
 
-int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, void *stream) {
-    if (!env || !board_true || !env->cfg.raw) return HEXB_ERR_ARG;
+int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, const uint8_t *import_mask, void *stream) {
+    if (!env || !board_true) return HEXB_ERR_ARG;
     CK(cudaSetDevice(env->cfg.device));
     const Params P = env->base;
     const unsigned grid = (unsigned)((P.G + 127) / 128);
     switch (env->cfg.board_size) {
 #define X(n) \
-    case n: hexb_import_kernel<n><<<grid, 128, 0, (cudaStream_t)stream>>>(P, board_true, to_move); break;
+    case n: hexb_import_kernel<n><<<grid, 128, 0, (cudaStream_t)stream>>>(P, board_true, to_move, import_mask); break;
         HEXB_FOR_N(X)
 #undef X
     }

@@ -217,10 +217,15 @@ HEXB_HD void game_half(uint8_t *L, const Params &P, long long g, Rec<N> &rec, Lo
     const bool was_done = (rec.meta & M_DONE) != 0u;
     const bool my_turn = (((rec.meta & M_TOMOVE) != 0u) == (side != 0));
     if (!was_done && my_turn) {
-        const int a = P.actions[g];
+        if (side != 0 && P.variant == VARIANT_B) rec.draws++;           // rv = random.uniform(0,1), unused (SelfplayWrapper.py:159)
+        int a;
+        if (P.actions) a = P.actions[g];
+        else {  // the built-in random opponent (BaseRandomPolicy / random_policy): k-th empty cell of ITS view
+            const double u = draw01(P.seed, gid, rec.draws++);
+            a = select_kth_zero<N>(rec.occ_cm, choice_of(u, count_empty<N>(rec.occ_cm)));
+        }
         loc.action = a;
         if (side == 0) loc.st[6] = 1;                                   // an env step starts with the agent's ply
-        else if (P.variant == VARIANT_B) rec.draws++;                   // rv = random.uniform(0,1), unused (SelfplayWrapper.py:159)
         int cell = a;
         if (side != 0 && (unsigned)a < (unsigned)C) {                   // the opponent's view is the transpose of the stored board
             const int x = a / N;

@@ -31,6 +31,8 @@ HEXB_HD void encode_at(const View &V, int view, long long i, int8_t *obs, uint8_
     if (V.variant == VARIANT_B) {
         if (view == 1 || V.raw) opp = (meta & M_TOMOVE) != 0u;
         else opp = (meta & M_DONE) && (meta & M_AGENT_ENDED);
+    } else if (view == 1 && !V.raw) {
+        opp = (meta & M_TOMOVE) != 0u;  // what HexEnv.opponent_move shows its policy: invert_board (HexGame.py:333-334)
     }
     const int y = c / V.N, x = c - y * V.N;
     const uint32_t b = view_labels(V, g)[opp ? x * V.N + y : c];
@@ -46,7 +48,7 @@ HEXB_HD void sample_at(const View &V, int view, long long g, const double *u, in
     constexpr int W = Geo<N>::W;
     const uint32_t *rw = view_rec(V, g);
     const uint32_t meta = rw[(2 * W) * kRecStride];
-    const bool opp = V.variant == VARIANT_B && (view == 1 || V.raw) && (meta & M_TOMOVE);
+    const bool opp = (V.variant == VARIANT_B ? (view == 1 || V.raw) : (view == 1 && !V.raw)) && (meta & M_TOMOVE);
     uint32_t occ[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) occ[w] = rw[((opp ? W : 0) + w) * kRecStride];
@@ -109,25 +111,34 @@ HEXB_HD void export_at(const View &V, long long i, double *board, double *region
 
 // K6b: HexGame.__init__ with a preset board: raster-order flood_fill rebuild (HexGame.py:53-61, HexSingleGame.py:57-65).
 template <int N>
-HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true, const int8_t *to_move) {
+// On an env handle (not raw) the game keeps its agent colour and its position in the random stream: the board is given in TRUE
+// coordinates and colours, stones are visited in TRUE raster order (the labels depend on it) and mapped into the stored
+// (agent's) orientation. `import_mask` (nullable) selects the games to overwrite.
+HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true, const int8_t *to_move, const uint8_t *import_mask) {
     constexpr int C = Geo<N>::C;
+    if (import_mask && !import_mask[g]) return;
     uint8_t *L = P.state + labels_offset(g, C);
+    uint32_t *recw = reinterpret_cast<uint32_t *>(P.state + rec_offset(g, C));
     Rec<N> rec;
+    load_rec<N>(recw, rec);
+    const bool env_game = !P.raw && (rec.meta & M_COLOUR_SET);
+    const uint32_t keep = env_game ? (rec.meta & (M_TRANSPOSED | M_COLOUR_SET)) : M_COLOUR_SET;
+    const int tr = (keep & M_TRANSPOSED) ? 1 : 0;
+    if (!env_game) rec.draws = 0;
 #pragma unroll
     for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
-    rec.meta = M_LIVE | M_COLOUR_SET | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
-    rec.draws = 0;
+    rec.meta = keep | M_LIVE | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
     for (int c = 0; c < C; ++c) L[c] = 0;
     for (int c = 0; c < C; ++c) {
         const int v = board_true[g * C + c];
         if (v != 0 && v != 1) continue;
         uint32_t prm;
-        place_stone<N>(L, rec, v, c, prm);
+        place_stone<N>(L, rec, v ^ tr, tr ? transpose_cell<N>(c) : c, prm);
         if (prm & P_NEED)
             for (int k = 0; k < C; ++k) L[k] = (uint8_t)relabel_byte(L[k], prm);
     }
-    if (to_move && to_move[g]) rec.meta |= M_TOMOVE;
-    store_rec<N>(reinterpret_cast<uint32_t *>(P.state + rec_offset(g, C)), rec);
+    if (((to_move && to_move[g]) ? 1 : 0) ^ tr) rec.meta |= M_TOMOVE;   // stored "C to move" = the side that is not the agent
+    store_rec<N>(recw, rec);
 }
 
 }  // namespace hexb

@@ -42,9 +42,34 @@ class _LazyInfos(object):
         return (self[i] for i in range(self._n))
 
 
+def random_start_boards(num_games, board_size, generator, device):
+    """Batched stand-in for HexEnv.random_board (HexSingleGame.py:300-331): per game a random rectangle (sides in
+    [N//4, N-2], uniform position) of the empty board receives an even number of stones, about 50-100 % of its cells, half
+    BLACK and half WHITE, at random cells of the rectangle - so BLACK is to move. The reference draws from the global
+    np.random; this generator is torch's (keyed by `generator`), i.e. the same distribution family, not the same numbers.
+    Returns int8[G,N,N] in true coordinates: 0 BLACK, 1 WHITE, 2 EMPTY."""
+    G, N = num_games, board_size
+    lo, hi = N // 4, max(N - 1, N // 4 + 1)
+    r = lambda a, b: torch.randint(a, b, (G,), generator=generator, device=device)
+    rows, cols = r(lo, hi), r(lo, hi)
+    top = (torch.rand(G, generator=generator, device=device) * (N - rows + 1).float()).long()
+    left = (torch.rand(G, generator=generator, device=device) * (N - cols + 1).float()).long()
+    frac = 0.5 + 0.5 * torch.rand(G, generator=generator, device=device)
+    stones = ((rows * cols).float() * frac / 2).floor().long() * 2
+    yy = torch.arange(N, device=device).view(1, N, 1)
+    xx = torch.arange(N, device=device).view(1, 1, N)
+    inside = (yy >= top.view(G, 1, 1)) & (yy < (top + rows).view(G, 1, 1)) & (xx >= left.view(G, 1, 1)) & (xx < (left + cols).view(G, 1, 1))
+    keys = torch.rand((G, N, N), generator=generator, device=device).masked_fill(~inside, 2.0).view(G, -1)
+    rank = keys.argsort(dim=1).argsort(dim=1)
+    board = torch.full((G, N * N), 2, dtype=torch.int8, device=device)
+    board[rank < (stones // 2).view(G, 1)] = 0
+    board[(rank >= (stones // 2).view(G, 1)) & (rank < stones.view(G, 1))] = 1
+    return board.view(G, N, N)
+
+
 class HexVecEnv(object):
     def __init__(self, board_size=5, num_envs=1024, variant="selfplay", agent_player_num=None, opponent_first=False,
-                 seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0):
+                 seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0, sample_board=False):
         if variant in ("selfplay", "B", VARIANT_B):
             v = VARIANT_B
             agent_mode = AGENT_RANDOM if agent_player_num is None else (AGENT_WHITE if int(agent_player_num) else AGENT_BLACK)
@@ -56,9 +81,17 @@ class HexVecEnv(object):
         if output not in ("numpy", "torch"):
             raise ValueError("output must be 'numpy' or 'torch'")
         self.num_envs, self.board_size, self.output = int(num_envs), int(board_size), output
+        self.sample_board = bool(sample_board)
+        if sample_board and v != VARIANT_B:
+            raise ValueError("sample_board is a SelfPlayEnv (variant B) option (HexSingleGame.py:171)")
+        # sample_board: episodes start from random positions. The fused step kernel restarts games on the empty board, so this
+        # mode runs the split step instead (agent ply / built-in random opponent ply as separate launches around the import).
         self.batch = HexBatch(board_size, num_envs, variant=v, device=device, seed=seed, game_offset=game_offset,
-                              agent_mode=agent_mode, opponent_first=opponent_first, auto_reset=True)
+                              agent_mode=agent_mode, opponent_first=opponent_first, auto_reset=True,
+                              manual_opponent=self.sample_board)
         self.device = self.batch.device
+        self._bgen = torch.Generator(device=self.device)
+        self._bgen.manual_seed(int(seed) + 0x5EED)
         self.obs_dtype = obs_dtype or (np.float32 if output == "numpy" else torch.float32)
         self.observation_space = _spaces.Box(low=low, high=high, shape=(board_size, board_size),
                                              dtype=np.int64 if v == VARIANT_B else np.uint8)
@@ -88,10 +121,34 @@ class HexVecEnv(object):
         return h.numpy().astype(self.obs_dtype)
 
     # ------------------------------------------------------------------ VecEnv API
+    def _restart_on_sampled_boards(self, which=None):
+        boards = random_start_boards(self.num_envs, self.board_size, self._bgen, self.device)
+        self.batch.import_boards(boards, import_mask=which)
+
     def reset(self):
         obs, mask = self.batch.reset()
+        if self.sample_board:
+            self._restart_on_sampled_boards()
+            self.batch.opponent_catch_up()      # SelfPlayEnv.reset -> continue_game where the opponent moves first
+            obs, mask = self.batch.encode(0)
         self._mask = mask
         return self._obs_out(obs)
+
+    def _step_sampled(self, actions):
+        """One env step in sample_board mode, in the reference's order: agent ply -> (finished: new sampled board) ->
+        opponent reply / opening -> (finished: new sampled board) -> opening."""
+        b = self.batch
+        term = b._buf("sb_term", (b.G, b.N, b.N), torch.int8)
+        h = b.half_step(0, actions, term_obs=term)
+        reward, done = h["reward"].clone(), h["done"].clone()
+        self._restart_on_sampled_boards(h["done"])
+        h = b.half_step(1, None, term_obs=term)
+        reward += h["reward"]
+        done |= h["done"]
+        self._restart_on_sampled_boards(h["done"])
+        b.opponent_catch_up()
+        obs, mask = b.encode(0)
+        return dict(obs=obs, mask=mask, reward=reward, done=done, term_obs=term)
 
     def step_async(self, actions):
         if isinstance(actions, np.ndarray):
@@ -99,7 +156,7 @@ class HexVecEnv(object):
         self._actions = actions
 
     def step_wait(self):
-        o = self.batch.step(self._actions, want_term=True)
+        o = self._step_sampled(self._actions) if self.sample_board else self.batch.step(self._actions, want_term=True)
         self._mask = o["mask"]
         if self.output == "torch":
             infos = _LazyInfos(o["done"], o["term_obs"], self.num_envs)

@@ -129,7 +129,8 @@ int32_t hexb_ply(hexb_env *env, const int32_t *actions, int8_t *ret, void *strea
 
 /* Observation + mask of the current state without stepping (get_action_mask HexGame.py:203-204, legal_actions
  * HexSingleGame.py:205-206, the live simulator.board). view 0 = the agent's (what step/reset return), view 1 = the
- * side to move's (variant-B HexEnv one-ply loop: board after invert_board, HexSingleGame.py:259-262). */
+ * side to move's (variant-B HexEnv one-ply loop: board after invert_board, HexSingleGame.py:259-262; variant A: the transposed,
+ * colour-swapped board HexEnv.opponent_move hands its policy when the opponent is to move, HexGame.py:333-334). */
 int32_t hexb_encode(hexb_env *env, int32_t view, int8_t *obs, uint8_t *mask, void *stream);
 
 /* k-th-empty-cell sampler, standalone (BaseRandomPolicy.choose_action SelfplayWrapper.py:17-22; random_policy
@@ -145,9 +146,14 @@ int32_t hexb_export_state(hexb_env *env, double *board, double *regions, double 
                           int8_t *winner, int8_t *agent, uint32_t *draws, void *stream);
 
 /* HexGame.__init__ with a preset board and connected_stones=None (HexGame.py:53-61, HexSingleGame.py:57-65): stones are
- * inserted in raster order through flood_fill. board_true i8[G,N,N] in {0 BLACK, 1 WHITE, 2 EMPTY}, true coordinates;
- * to_move i8[G] (0/1). Only on raw=1 handles. */
-int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, void *stream);
+ * inserted in raster order through flood_fill. board_true i8[G,N,N] in {0 BLACK, 1 WHITE, 2 EMPTY}, true coordinates and
+ * colours; to_move i8[G] (true colour to move, null = BLACK); import_mask u8[G] (null = every game). On a raw=1 handle this is
+ * the constructor; on an env handle (after hexb_reset) it is HexEnv.reset with sample_board=True (HexSingleGame.py:217-222,
+ * random_board :300-331): the game keeps its agent colour and stream position. If the opponent is then to move, call
+ * hexb_half_step(side 1, actions) with the caller's opponent, or with actions = null for the built-in random opponent
+ * (SelfPlayEnv.reset -> continue_game, SelfplayWrapper.py:79-80); env handles used this way are manual_opponent=1 ones, whose
+ * resets leave the opening move to that call. */
+int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, const uint8_t *import_mask, void *stream);
 
 /* Episode statistics accumulated by hexb_step since creation, int64[8] on the device:
  * [0] episodes finished, [1] BLACK wins, [2] WHITE wins, [3] agent wins, [4] plies of finished episodes,
@@ -159,6 +165,7 @@ int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream);
  *   hexb_half_step(side 0, agent actions)  ->  hexb_encode(view 1) for the games with to_move == 1  ->  opponent network  ->
  *   hexb_half_step(side 1, opponent actions)  [twice: a game the opponent just won restarts, and if the opponent also opens the
  *   new episode it needs the opening move]
+ * (hexb_half_step(side 1, actions = null) lets the built-in random opponent move instead of the caller's.)
  * hexb_half_step plays ONE ply of `side` (0 agent, 1 opponent) in every live, unfinished game whose turn it is: the agent's half
  * of SelfPlayEnv.step (SelfplayWrapper.py:174-176, HexSingleGame.py:233-263) or continue_game (:146-172) with the action supplied
  * by the caller in the mover's own perspective (exactly what OpponentPolicy.choose_action returns). Other games are untouched.

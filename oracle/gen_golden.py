@@ -15,6 +15,7 @@ Fixture families
   envA_N*_of*.npz        variant-A HexEnv(opponent_policy=minihex.random_policy) rollouts, same two agent modes
   oppmodel_N*_a*.npz     SelfPlayEnv with OpponentPolicy opponents (scripted stand-ins for SB3 models, oracle/scripted.py): the
                          learned-opponent path incl. the 80/20 best/pool choice of setup_opponents and the opponent's observation
+  preset_N*.npz          HexGame.__init__ on preset boards (raster-order region rebuild), both variants
   kat.npz                the four hand-checked known-answer tests of SURVEY.md section 8c
 """
 import os
@@ -170,6 +171,23 @@ def rollout_scripted_opponent(N, G, T, seed, agent_mode, pool, illegal_rate=0.04
     return out
 
 
+def gen_preset_boards(N, n, seed):
+    """HexGame.__init__ with a preset board and connected_stones=None (HexGame.py:53-61, HexSingleGame.py:57-65): the planes
+    are rebuilt by flood_fill in raster order. Random boards (true coordinates), both variants."""
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed)
+    true_codes = rs.choice([0, 1, 2], size=(n, N, N), p=[0.3, 0.3, 0.4]).astype(np.int8)
+    out = dict(board_true=true_codes, regions_A=np.zeros((n, 2, N + 2, N + 2), np.uint8), counter_A=np.zeros((n, 2), np.int16),
+               regions_B=np.zeros((n, 2, N + 2, N + 2), np.uint8), counter_B=np.zeros((n, 2), np.int16))
+    for i in range(n):
+        ga = A.HexGame(A.player.BLACK, true_codes[i].astype(np.float64), A.player.BLACK)
+        bb = np.where(true_codes[i] == 0, -1.0, np.where(true_codes[i] == 1, 1.0, 0.0))
+        gb = B.HexGame(0, bb)
+        out["regions_A"][i], out["counter_A"][i] = ga.regions, ga.region_counter
+        out["regions_B"][i], out["counter_B"][i] = gb.regions, gb.region_counter
+    np.savez_compressed(os.path.join(OUT, "preset_N%d.npz" % N), N=N, **out)
+
+
 def gen_kats():
     """SURVEY.md section 8c KAT-1..4, re-derived from the reference here and stored verbatim."""
     minihex, A, B, S = rh.load()
@@ -228,6 +246,8 @@ def main():
                 o = rollout("A", N, G, T, seed=2000 + N, agent_mode=0, fused=bool(fused), opponent_first=bool(of))
                 np.savez_compressed(os.path.join(OUT, "envA_N%d_of%d_f%d.npz" % (N, of, fused)), N=N, seed=2000 + N,
                                     opponent_first=of, fused=fused, **o)
+    for N, n in [(4, 30), (7, 20), (11, 12)]:
+        gen_preset_boards(N, n, 400 + N)
     for N, G, T, pool in [(4, 16, 30, 3), (7, 10, 70, 5), (11, 6, 120, 20)]:
         for agent_mode in (0, 1, 2):
             o = rollout_scripted_opponent(N, G, T, seed=3000 + N, agent_mode=agent_mode, pool=pool)

@@ -482,11 +482,18 @@ void hexref_batch_half_step(void *h, int side, const int32_t *actions, int auto_
         const int was_done = e->g.done;
         float r = 0.f;
         if (!was_done && ((side == 0) == (agent_to_move(e) != 0))) {
-            int a = actions[i];
             if (side == 0) e->st[6]++;
+            if (side == 1 && e->kind == 1) (void)rng_uniform01(&e->rng);   /* continue_game's unused draw (:159) */
+            int a;
+            if (actions) a = actions[i];
+            else if (e->kind == 1) a = random_choice(&e->g, rng_random(&e->rng));   /* BaseRandomPolicy on the mover's view */
+            else {                                                                   /* random_policy on the inverted board */
+                invert_board(&e->g);
+                a = random_choice(&e->g, rng_random(&e->rng));
+                invert_board(&e->g);
+            }
             if (e->kind == 1) {
                 int rw[2];
-                if (side == 1) (void)rng_uniform01(&e->rng);
                 B_base_step(e, a, rw);
                 r = (float)rw[e->agent];
             } else {
@@ -573,6 +580,25 @@ void hexref_batch_stats(void *h, int64_t out[8]) {
     for (int k = 0; k < 8; ++k) out[k] = 0;
     for (int64_t i = 0; i < b->G; ++i)
         for (int k = 0; k < 8; ++k) out[k] += b->envs[i].st[k];
+}
+
+/* HexEnv.reset with sample_board=True (HexSingleGame.py:217-222) for the masked envs: a new simulator on the given board
+ * (true coordinates; B codes -1 BLACK / +1 WHITE / 0 empty, A codes 0/1/2), BLACK to move. The agent colour and the random
+ * stream carry on; the opponent's catch-up move (SelfPlayEnv.reset -> continue_game) is a separate half step. */
+void hexref_batch_env_set_board(void *h, const int8_t *boards, const uint8_t *mask) {
+    batch_t *b = (batch_t *)h;
+    const int C = b->N * b->N;
+    for (int64_t i = 0; i < b->G; ++i) {
+        if (mask && !mask[i]) continue;
+        env_t *e = &b->envs[i];
+        int tmp[MAXC], stones = 0;
+        const int E = e->kind == 1 ? 0 : 2;
+        for (int c = 0; c < C; ++c) { tmp[c] = boards[i * C + c]; stones += (tmp[c] != E); }
+        game_init(&e->g, b->N, e->kind == 1 ? 1 : 0, BLACK, tmp);
+        e->env_cur = BLACK;
+        e->plies = stones;
+        e->env_winner = NONE;
+    }
 }
 
 /* Raw game from a preset board (HexGame.__init__ with connected_stones=None: raster-order flood_fill rebuild). */

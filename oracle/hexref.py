@@ -48,6 +48,7 @@ def lib():
         L.hexref_batch_observe.argtypes = [vp, vp, vp]
         L.hexref_batch_opp_state.argtypes = [vp, vp, vp]
         L.hexref_batch_info.argtypes = [vp, vp, vp]
+        L.hexref_batch_env_set_board.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -112,7 +113,7 @@ class RefBatch(object):
         to_move = np.empty(self.G, np.uint8)
         opp_index = np.empty(self.G, np.int32)
         term = np.zeros((self.G, self.N, self.N), np.int8) if want_term else None
-        a = np.ascontiguousarray(actions, np.int32)
+        a = None if actions is None else np.ascontiguousarray(actions, np.int32)
         lib().hexref_batch_half_step(self._h, side, _p(a), int(auto_reset), _p(reward), _p(done), _p(to_move), _p(opp_index), _p(term))
         out = dict(reward=reward, done=done, to_move=to_move, opp_index=opp_index)
         if want_term:
@@ -145,6 +146,12 @@ class RefBatch(object):
         a = np.ascontiguousarray(actions, np.int32)
         lib().hexref_batch_ply(self._h, _p(a), _p(ret))
         return ret
+
+    def env_set_board(self, boards, mask=None):
+        """boards in the variant's own codes, true coordinates; BLACK to move."""
+        b = np.ascontiguousarray(boards, np.int8)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().hexref_batch_env_set_board(self._h, _p(b), _p(m))
 
     def set_board(self, boards, cur=0):
         b = np.ascontiguousarray(boards, np.int8)

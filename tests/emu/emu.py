@@ -36,7 +36,7 @@ def lib():
         L.emu_encode.argtypes = [vp, i32, vp, vp]
         L.emu_sample_actions.argtypes = [vp, i32, vp, vp]
         L.emu_export_state.argtypes = [vp] * 9
-        L.emu_import_boards.argtypes = [vp] * 3
+        L.emu_import_boards.argtypes = [vp] * 4
         L.emu_stats.argtypes = [vp, vp]
         L.emu_set_manual_opponent.argtypes = [vp, i32, vp, vp]
         L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -95,7 +95,7 @@ class EmuBatch(object):
         reward = np.empty(self.G, np.float32)
         done = np.empty(self.G, np.uint8)
         term = np.zeros((self.G, self.N, self.N), np.int8) if want_term else None
-        a = np.ascontiguousarray(actions, np.int32)
+        a = None if actions is None else np.ascontiguousarray(actions, np.int32)
         lib().emu_half_step(self._h, side, _p(a), _p(reward), _p(done), _p(term))
         out = dict(reward=reward, done=done, to_move=self.to_move.copy(), opp_index=self.opp_index.copy())
         if want_term:
@@ -142,10 +142,14 @@ class EmuBatch(object):
         lib().emu_sample_actions(self._h, view, _p(uu), _p(out))
         return out
 
-    def import_boards(self, board_true, to_move=None):
+    def import_boards(self, board_true, to_move=None, import_mask=None):
         b = np.ascontiguousarray(board_true, np.int8)
         tm = None if to_move is None else np.ascontiguousarray(to_move, np.int8)
-        lib().emu_import_boards(self._h, _p(b), _p(tm))
+        im = None if import_mask is None else np.ascontiguousarray(import_mask, np.uint8)
+        lib().emu_import_boards(self._h, _p(b), _p(tm), _p(im))
+
+    def opponent_catch_up(self):
+        lib().emu_half_step(self._h, 1, None, None, None, None)
 
     def export(self):
         N, G = self.N, self.G

@@ -194,11 +194,11 @@ void emu_export_state(void *h, double *board, double *regions, double *counter, 
     const long long n = V.G * 2 * (V.N + 2) * (V.N + 2);
     for (long long i = 0; i < n; ++i) export_at(V, i, board, regions, counter, cur, done, winner, agent, draws);
 }
-void emu_import_boards(void *h, const int8_t *board_true, const int8_t *to_move) {
+void emu_import_boards(void *h, const int8_t *board_true, const int8_t *to_move, const uint8_t *import_mask) {
     emu_env *e = (emu_env *)h;
     for (long long g = 0; g < e->base.G; ++g) switch (e->N) {
 #define X(n) \
-    case n: import_game<n>(e->base, g, board_true, to_move); break;
+    case n: import_game<n>(e->base, g, board_true, to_move, import_mask); break;
             HEXB_FOR_N(X)
 #undef X
         }

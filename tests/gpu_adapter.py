@@ -63,8 +63,11 @@ class GpuBatch(object):
     def sample_actions(self, u, view=0):
         return self._np(self.b.sample_actions(u, view))
 
-    def import_boards(self, board_true, to_move=None):
-        self.b.import_boards(board_true, to_move)
+    def import_boards(self, board_true, to_move=None, import_mask=None):
+        self.b.import_boards(board_true, to_move, import_mask)
+
+    def opponent_catch_up(self):
+        self.b.opponent_catch_up()
 
     def export(self):
         e = {k: self._np(v) for k, v in self.b.export_state().items()}

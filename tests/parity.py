@@ -235,3 +235,63 @@ def rollout_equals_steps(make, kind, N, G, T, seed=0, **kw):
         for key in STATE_KEYS:
             eq(ea[key], eb[key], "rollout state " + key)
         eq(a.stats(), b.stats(), "rollout stats")
+
+
+def random_start_boards(rs, G, N, variant_b=True):
+    """Random positions with equally many stones of both colours (BLACK to move), like HexEnv.random_board produces."""
+    true_codes = np.full((G, N * N), 2, np.int8)
+    for g in range(G):
+        k = int(rs.randint(0, N * N // 3)) * 2
+        cells = rs.permutation(N * N)[:k]
+        true_codes[g, cells[:k // 2]] = 0
+        true_codes[g, cells[k // 2:]] = 1
+    true_codes = true_codes.reshape(G, N, N)
+    own = np.where(true_codes == 0, -1, np.where(true_codes == 1, 1, 0)).astype(np.int8) if variant_b else true_codes
+    return true_codes, own
+
+
+def sample_board_flow(make, N, G, T, seed=0, agent_mode=2):
+    """SelfPlayEnv with sample_board=True and the random opponent, as a split-step flow: agent ply, opponent reply, finished
+    games restart from random positions (import) and the opponent catches up where it is to move. Implementation vs oracle."""
+    env = make(hexref.KIND_SELFPLAY_B, N, G, seed=seed, agent_mode=agent_mode, manual_opponent=True)
+    ref = hexref.RefBatch(hexref.KIND_SELFPLAY_B, N, G, seed=seed, agent_mode=agent_mode, manual_opponent=True)
+    rs = np.random.RandomState(seed + 5)
+    env.reset(); ref.reset()
+    tc, own = random_start_boards(rs, G, N)
+    env.import_boards(tc); ref.env_set_board(own)
+    env.half_step(1, None); ref.half_step(1, None)
+    for t in range(T):
+        obs, mask = env.view1()
+        robs, rmask = ref.view1()
+        eq(obs, robs, "sample_board obs t=%d" % t)
+        eq(mask, rmask, "sample_board mask t=%d" % t)
+        cnt = np.maximum(mask.sum(1), 1)
+        k = (rs.rand(G) * cnt).astype(np.int64)
+        acts = np.argsort(-mask.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
+        done = np.zeros(G, bool)
+        for side, a in ((0, acts), (1, None)):
+            o, r = env.half_step(side, a), ref.half_step(side, a)
+            for key in ("reward", "done", "to_move"):
+                eq(o[key], r[key], "sample_board %s t=%d side=%d" % (key, t, side))
+            done |= r["done"].astype(bool)
+        tc, own = random_start_boards(rs, G, N)
+        env.import_boards(tc, import_mask=done.astype(np.uint8)); ref.env_set_board(own, done.astype(np.uint8))
+        o, r = env.half_step(1, None), ref.half_step(1, None)
+        eq(o["to_move"], r["to_move"], "sample_board to_move after catch-up t=%d" % t)
+        if t % 4 == 0:
+            e, re_ = env.export(), ref.export()
+            for key in ("regions", "region_counter", "cur", "done", "winner", "agent", "draws"):
+                eq(e[key], re_[key], "sample_board %s t=%d" % (key, t))
+    eq(env.stats(), ref.stats(), "sample_board stats")
+
+
+def golden_preset(make_raw, name):
+    """Preset-board construction (raster-order label rebuild) against the reference's own HexGame.__init__."""
+    z = np.load(os.path.join(GOLDEN, name))
+    N = int(z["N"])
+    tc = z["board_true"]
+    for variant, kind in (("A", hexref.KIND_GAME_A), ("B", hexref.KIND_GAME_B)):
+        env = make_raw(kind, N, tc.shape[0])
+        e = env.export()
+        eq(e["regions"], z["regions_" + variant].astype(np.float64), "%s %s regions" % (name, variant))
+        eq(e["region_counter"], z["counter_" + variant].astype(np.float64), "%s %s counter" % (name, variant))

@@ -1,11 +1,13 @@
 """CPU: the kernel's phase code (hex_gym_env_b200/csrc/hexb_phases.cuh), replayed serially by the host emulator
 (tests/emu), against the golden vectors of the unmodified reference and against the oracle. This is a check of the
 device LOGIC in a container without a GPU; the -m gpu tests repeat the same drivers through libhexb.so on the B200."""
+import os
+
 import numpy as np
 import pytest
 
 import parity
-from conftest import golden_files
+from conftest import GOLDEN, golden_files
 from oracle import hexref
 from emu.emu import EmuBatch
 
@@ -91,3 +93,19 @@ def test_half_step_vs_oracle(N, kind):
                                        (6, hexref.KIND_ENV_A, dict(opponent_first=True))])
 def test_rollout_equals_steps(N, kind, kw):
     parity.rollout_equals_steps(make, kind, N, 100, N * N // 2 + 3, seed=N, **kw)
+
+
+@pytest.mark.parametrize("N", [5, 8])
+def test_sample_board_flow(N):
+    parity.sample_board_flow(make, N, 150, 40, seed=N)
+
+
+@pytest.mark.parametrize("name", golden_files("preset_"))
+def test_golden_preset_boards(name):
+    def make_raw(kind, N, G):
+        z = np.load(os.path.join(GOLDEN, name))
+        env = EmuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True)
+        env.reset()
+        env.import_boards(z["board_true"], np.zeros(G, np.int8))
+        return env
+    parity.golden_preset(make_raw, name)

@@ -167,8 +167,14 @@ def test_half_step_vs_oracle(make, N, variant_kind):
                     live = tm != 2
                     parity.eq(obs1[live], robs1[live], "side-to-move obs t=%d" % t)
                     parity.eq(mask1[live], rmask1[live], "side-to-move mask t=%d" % t)
-                else:   # variant A keeps the true board; the opponent's action index is the transposed cell
-                    mask1 = mask1.reshape(G, N, N).transpose(0, 2, 1).reshape(G, C) if side == 1 else mask1
+                else:   # variant A: the oracle keeps the true board; the opponent sees it transposed with colours swapped
+                    robs1, rmask1 = ref.view1()
+                    oppv = tm == 1
+                    robs1[oppv] = np.where(robs1[oppv] == 2, 2, 1 - robs1[oppv]).transpose(0, 2, 1)
+                    rmask1[oppv] = rmask1[oppv].reshape(-1, N, N).transpose(0, 2, 1).reshape(-1, C)
+                    live = tm != 2
+                    parity.eq(obs1[live], robs1[live], "side-to-move obs (A) t=%d" % t)
+                    parity.eq(mask1[live], rmask1[live], "side-to-move mask (A) t=%d" % t)
                 cnt = np.maximum(mask1.sum(1), 1)
                 k = (rs.rand(G) * cnt).astype(np.int64)
                 acts = np.argsort(-mask1.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
@@ -223,3 +229,78 @@ def test_step_with_opponent_on_device():
                                        (7, hexref.KIND_ENV_A, dict(opponent_first=True)), (19, hexref.KIND_SELFPLAY_B, dict(agent_mode=0))])
 def test_rollout_equals_steps(make, N, kind, kw):
     parity.rollout_equals_steps(make, kind, N, 1000 if N < 19 else 300, min(N * N // 2 + 3, 64), seed=N, **kw)
+
+
+def test_checkpoint_roundtrip():
+    """state_dict / load_state_dict: a restored shard continues bit-identically (state, random streams, statistics)."""
+    import torch
+    from hex_gym_env_b200 import HexBatch, VARIANT_B
+    a = HexBatch(7, 777, variant=VARIANT_B, device=0, seed=8, agent_mode=2)
+    a.reset()
+    for _ in range(25):
+        a.step()
+    sd = a.state_dict()
+    ref = [{k: v.clone() for k, v in a.step().items()} for _ in range(20)]
+    b = HexBatch(7, 777, variant=VARIANT_B, device=0, seed=8, agent_mode=2)
+    b.load_state_dict(sd)
+    for t in range(20):
+        o = b.step()
+        for k in ("obs", "mask", "reward", "done"):
+            assert torch.equal(o[k], ref[t][k]), (k, t)
+    assert torch.equal(a.stats(), b.stats())
+    with pytest.raises(ValueError):
+        HexBatch(7, 778, variant=VARIANT_B, device=0, seed=8, agent_mode=2).load_state_dict(sd)
+
+
+@pytest.mark.parametrize("N,agent_mode", [(5, 2), (11, 1), (11, 2)])
+def test_sample_board_flow(make, N, agent_mode):
+    """Batched sample_board=True (random start positions + random opponent) through import + split steps, GPU vs oracle."""
+    parity.sample_board_flow(make, N, 600, 50, seed=N + agent_mode, agent_mode=agent_mode)
+
+
+@pytest.mark.parametrize("name", golden_files("preset_"))
+def test_golden_preset_boards(name):
+    """hexb_import_boards on raw handles against the reference's HexGame.__init__ with a preset board."""
+    import os
+    from conftest import GOLDEN
+    from gpu_adapter import GpuBatch
+
+    def make_raw(kind, N, G):
+        z = np.load(os.path.join(GOLDEN, name))
+        env = GpuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True)
+        env.reset()
+        env.import_boards(z["board_true"], np.zeros(G, np.int8))
+        return env
+    parity.golden_preset(make_raw, name)
+
+
+def test_vec_env_sample_board():
+    """HexVecEnv(sample_board=True): episodes start from random even positions; invariants of the reference's random_board."""
+    import torch
+    from hex_gym_env_b200.vec_env import HexVecEnv, random_start_boards
+    N, G = 8, 500
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    bd = random_start_boards(4000, N, gen, torch.device("cuda", 0))
+    nb, nw = (bd == 0).flatten(1).sum(1), (bd == 1).flatten(1).sum(1)
+    assert bool((nb == nw).all()) and int(nb.max()) > 3 and int(nb.min()) >= 0           # equal stones -> BLACK to move
+    occ = bd != 2
+    rows, cols = occ.any(2).sum(1), occ.any(1).sum(1)
+    assert int(rows.max()) <= N - 1 and int(cols.max()) <= N - 1                           # inside a rectangle of side <= N-2(+)
+    venv = HexVecEnv(board_size=N, num_envs=G, variant="selfplay", seed=3, output="torch", sample_board=True)
+    obs = venv.reset()
+    stones0 = (obs != 0).flatten(1).sum(1)
+    assert int(stones0.max()) > 2 and bool(((obs == 0).flatten(1) == venv.action_masks()).all())
+    agent_white = venv.batch.export_state()["agent"] == 1
+    own, opp = (obs == -1).flatten(1).sum(1), (obs == 1).flatten(1).sum(1)
+    assert bool((opp - own == agent_white.long()).all())       # the opponent opened exactly where the agent plays WHITE
+    total_done = 0
+    for t in range(40):
+        masks = venv.action_masks()
+        acts = torch.argmax(masks.to(torch.uint8), dim=1).to(torch.int32)
+        obs, rew, done, infos = venv.step(acts)
+        total_done += int(done.sum())
+        assert bool(((obs == 0).flatten(1) == venv.action_masks()).all())
+        own, opp = (obs == -1).flatten(1).sum(1), (obs == 1).flatten(1).sum(1)
+        assert bool((opp - own == agent_white.long()).all())   # always the agent's turn, on consistent positions
+        assert bool((rew[~done] == 0).all()) and bool((rew[done].abs() == 1).all())
+    assert total_done > G // 4 and venv.episode_stats()["invalid_ends"] == 0

@@ -82,6 +82,19 @@ def test_scripted_opponent_rollouts(name):
     parity.golden_oppmodel(lambda kind, N, G, **kw: hexref.RefBatch(kind, N, G, **kw), name)
 
 
+@pytest.mark.parametrize("name", golden_files("preset_"))
+def test_preset_boards(name):
+    import parity
+
+    def make_raw(kind, N, G):
+        z = load(name)
+        tc = z["board_true"]
+        b = hexref.RefBatch(kind, N, G)
+        b.set_board(tc if kind == hexref.KIND_GAME_A else np.where(tc == 0, -1, np.where(tc == 1, 1, 0)).astype(np.int8), cur=0)
+        return b
+    parity.golden_preset(make_raw, name)
+
+
 def test_kats():
     """SURVEY.md section 8c KAT-1..4 (values stored from the reference in kat.npz)."""
     k = load("kat.npz")
