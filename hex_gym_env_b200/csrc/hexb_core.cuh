@@ -3,7 +3,7 @@
 // Everything here is written against the REFERENCE SEMANTICS (MBPrdctns/hex_gym_env), cited as
 // file:line relative to the reference root, but in a representation chosen for the B200:
 //
-//   * one TAGGED LABEL BYTE per cell, [G][C] u8, in the AGENT'S PERSPECTIVE ("stored") coordinates:
+//   * one TAGGED LABEL BYTE per cell, C bytes per game, in the AGENT'S PERSPECTIVE ("stored") coordinates:
 //       0 = empty, else (region label & 0x7f) | (player << 7), player 0 = "R" (connects stored row 0
 //       to row N-1; the agent), player 1 = "C" (connects stored col 0 to col N-1; the opponent).
 //     It replaces the reference's board f64[N,N] plus regions f64[2,N+2,N+2] (HexGame.py:23,38-45,
@@ -14,9 +14,11 @@
 //   * "stored" = true coordinates when the agent is BLACK, the transpose when the agent is WHITE
 //     (the hex neighbourhood is symmetric under transposition), so the agent's observation, mask and
 //     action index are the stored row-major order and never need a transpose on the hot path.
-//   * a small per-game record (SoA u32 words): occupancy bitboards in row-major and column-major
+//   * a small per-game record (u32 words): occupancy bitboards in row-major and column-major
 //     order (the random opponent picks the k-th empty cell of ITS perspective = stored column-major
 //     order, SelfplayWrapper.py:17-22, minihex/__init__.py:8-12), counters, flags, RNG draw index.
+//   * games are stored chunk-major, 32 games (one warp) per contiguous block: their label bytes
+//     [32][C], then their record words [word][lane] (see chunk_state_bytes below).
 //
 // The same source compiles for the device (hexb_kernels.cu) and, with HEXB_HOST_EMU defined, for the
 // host-side emulator under tests/emu/ that replays the kernel phases serially. The emulator is test

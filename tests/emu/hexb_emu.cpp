@@ -1,8 +1,8 @@
-// TEST INFRASTRUCTURE ONLY - host-side emulator of the CUDA tile kernel.
+// TEST INFRASTRUCTURE ONLY - host-side emulator of the CUDA step kernel.
 //
 // Compiles the SAME phase code the device runs (hex_gym_env_b200/csrc/hexb_phases.cuh, hexb_views.cuh) with
-// HEXB_HOST_EMU and replays one CTA at a time: every phase is run for all 128 "threads" before the next one,
-// which is what the __syncthreads() between phases guarantees on the GPU. It lets the CPU test-suite check the
+// HEXB_HOST_EMU and replays one warp (chunk of 32 games) at a time: every phase is run for all 32 "lanes" before the
+// next one, which is what the __syncwarp() between phases guarantees on the GPU. It lets the CPU test-suite check the
 // device logic against the oracle in a container without a GPU. It is not a CPU fallback: the product package
 // never loads it, and it is far too slow to be one.
 #define HEXB_HOST_EMU 1
