@@ -304,3 +304,33 @@ def test_vec_env_sample_board():
         assert bool((opp - own == agent_white.long()).all())   # always the agent's turn, on consistent positions
         assert bool((rew[~done] == 0).all()) and bool((rew[done].abs() == 1).all())
     assert total_done > G // 4 and venv.episode_stats()["invalid_ends"] == 0
+
+
+@pytest.mark.parametrize("N", list(range(3, 20)))
+def test_every_board_size_instantiation(make, N):
+    """Every template instantiation (N = 3..19), both variants, short fused rollouts against the oracle."""
+    parity.versus_oracle(make, hexref.KIND_SELFPLAY_B, N, 97, min(N * N // 2 + 4, 40), seed=100 + N, fused=True, agent_mode=2,
+                         check_state_every=7)
+    parity.versus_oracle(make, hexref.KIND_ENV_A, N, 65, min(N * N // 2 + 4, 30), seed=200 + N, fused=True, opponent_first=bool(N % 2),
+                         check_state_every=7)
+
+
+def test_misaligned_output_buffers():
+    """Caller buffers that are not 16-byte aligned (slices of a larger buffer) take the byte-wise store path: same bytes."""
+    import torch
+    from hex_gym_env_b200 import HexBatch, VARIANT_B
+    N, G = 11, 333
+    a = HexBatch(N, G, variant=VARIANT_B, device=0, seed=2, agent_mode=2)
+    b = HexBatch(N, G, variant=VARIANT_B, device=0, seed=2, agent_mode=2)
+    big_o = torch.zeros(G * N * N + 7, dtype=torch.int8, device="cuda")
+    big_m = torch.zeros(G * N * N + 7, dtype=torch.uint8, device="cuda")
+    obs_u = big_o[3:3 + G * N * N].view(G, N, N)
+    mask_u = big_m[5:5 + G * N * N].view(G, N * N)
+    assert obs_u.data_ptr() % 16 != 0 and mask_u.data_ptr() % 16 != 0
+    a.reset(); b.reset(obs=obs_u, mask=mask_u)
+    for t in range(40):
+        o = a.step()
+        b.step(obs=obs_u, mask=mask_u)
+        assert torch.equal(o["obs"], obs_u) and torch.equal(o["mask"], mask_u), t
+    assert int(big_o[:3].abs().sum()) == 0 and int(big_o[3 + G * N * N:].abs().sum()) == 0      # nothing written outside the slice
+    assert int(big_m[:5].sum()) == 0 and int(big_m[5 + G * N * N:].sum()) == 0
