@@ -67,7 +67,13 @@ def random_start_boards(num_games, board_size, generator, device):
     return board.view(G, N, N)
 
 
-class HexVecEnv(object):
+try:  # subclass the real VecEnv when stable-baselines3 is installed, so that isinstance checks inside SB3 pass
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv as _VecEnvBase
+except Exception:  # pragma: no cover - SB3 is absent in the build image
+    _VecEnvBase = object
+
+
+class HexVecEnv(_VecEnvBase):
     def __init__(self, board_size=5, num_envs=1024, variant="selfplay", agent_player_num=None, opponent_first=False,
                  seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0, sample_board=False):
         if variant in ("selfplay", "B", VARIANT_B):
@@ -96,6 +102,8 @@ class HexVecEnv(object):
         self.observation_space = _spaces.Box(low=low, high=high, shape=(board_size, board_size),
                                              dtype=np.int64 if v == VARIANT_B else np.uint8)
         self.action_space = _spaces.Discrete(board_size ** 2)
+        if _VecEnvBase is not object:
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self.render_mode = None
         self._actions = None
         self._mask = None
