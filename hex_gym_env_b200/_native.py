@@ -25,14 +25,24 @@ def _nvcc():
 
 def build(force=False, verbose=False):
     """Compile libhexb.so for sm_100a if it is missing or older than its sources. Returns the library path."""
-    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES)
-    if force or stale:
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
-        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if proc.returncode != 0:
-            raise RuntimeError("building libhexb.so failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))
-        if verbose:
-            print(proc.stdout)
+    def stale():
+        return (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES)
+
+    if force or stale():
+        import fcntl
+        with open(LIB_PATH + ".lock", "w") as lock:     # one builder at a time (torchrun starts several ranks at once)
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or stale():                        # another rank may have built it while we waited
+                tmp = "%s.%d.tmp" % (LIB_PATH, os.getpid())
+                cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, SOURCES[0]]
+                proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                if proc.returncode != 0:
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
+                    raise RuntimeError("building libhexb.so failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))
+                os.replace(tmp, LIB_PATH)               # atomic: a concurrent loader never sees a half-written library
+                if verbose:
+                    print(proc.stdout)
     return LIB_PATH
 
 
