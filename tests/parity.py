@@ -108,9 +108,8 @@ def versus_oracle(make, kind, N, G, T, seed=0, game_offset=0, fused=True, auto_r
             eq(eo, fo, w + "info last_move_opponent")
             eq(ew, fw, w + "info winner")
         d = r["done"].astype(bool)
-        if auto_reset or t == 0 or True:
-            newly = d if auto_reset else d
-            eq(o["term_obs"][newly] if auto_reset else o["obs"][newly], r["term_obs"][newly], w + "term_obs")
+        # with auto-reset the terminal observation comes through term_obs; without it, it is the observation itself
+        eq(o["term_obs"][d] if auto_reset else o["obs"][d], r["term_obs"][d], w + "term_obs")
         rm = r["mask"]
         if check_state_every and t % check_state_every == 0:
             re_, e = ref.export(), env.export()
