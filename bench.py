@@ -179,6 +179,14 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = "unchanged"
+    try:  # run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU: the end-to-end leg is PCIe / host-memory bound
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = "nvmlDeviceSetCpuAffinity(gpu %d): %d cpus" % (local, len(os.sched_getaffinity(0)))
+    except Exception as exc:
+        numa = "not set (%s)" % (str(exc)[:60],)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N, G, K, Wm = args.board, args.games_per_gpu, args.steps, args.warmup
@@ -324,7 +332,7 @@ def run_gpu(args):
     invalid = int(env.stats().cpu()[5])
     e2e = {"value": world * G * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * G,
            "d2h_bytes_per_step": G * (2 * N * N + 5), "steps": E, "ms_per_step": e2e_ms / E, "wall_ms_per_step": wall_ms / E,
-           "api": "hexb_step_host (C ABI, pinned host buffers)", "illegal_moves_in_replay": invalid}
+           "api": "hexb_step_host (C ABI, pinned host buffers)", "illegal_moves_in_replay": invalid, "cpu_affinity": numa}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
