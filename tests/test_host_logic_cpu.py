@@ -1,0 +1,42 @@
+"""CPU: host-side pieces that need no GPU - the random start-board generator of HexVecEnv(sample_board=True), the bench
+byte accounting, the scripted opponent stand-in."""
+import numpy as np
+import torch
+
+import bench
+from hex_gym_env_b200.vec_env import random_start_boards
+from oracle.scripted import scripted_choice
+
+
+def test_random_start_boards_invariants():
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(7)
+    for N in (5, 8, 11):
+        b = random_start_boards(3000, N, gen, torch.device("cpu"))
+        assert b.shape == (3000, N, N) and b.dtype == torch.int8 and set(b.unique().tolist()) <= {0, 1, 2}
+        nb, nw = (b == 0).flatten(1).sum(1), (b == 1).flatten(1).sum(1)
+        assert bool((nb == nw).all())                                   # even stone count, BLACK to move (HexSingleGame.py:312)
+        occ = b != 2
+        h = occ.any(2).sum(1)
+        w = occ.any(1).sum(1)
+        assert int(h.max()) <= max(N - 2, N // 4) and int(w.max()) <= max(N - 2, N // 4)   # rectangle sides in [N//4, N-2]
+        assert int((nb + nw).max()) >= (N // 4) ** 2 // 2 and float((nb + nw).float().mean()) > 1.0
+
+
+def test_contract_and_moved_bytes():
+    # SURVEY.md section 8(d) table
+    assert [bench.contract_bytes(N) for N in (5, 6, 7, 11, 19)] == [207, 289, 367, 831, 2399]
+    # this implementation: 2 * (C + 4 * (2W + 2)) + 2C + 5
+    assert bench.moved_bytes(11) == 2 * (121 + 40) + 242 + 5 == 569
+    assert bench.moved_bytes(11, sampled=False) == 573
+
+
+def test_scripted_choice_is_legal_and_deterministic():
+    rs = np.random.RandomState(0)
+    for _ in range(50):
+        board = rs.choice([-1, 0, 1], size=(6, 6))
+        mask = (board == 0).reshape(-1)
+        if not mask.any():
+            continue
+        a = scripted_choice(board, mask)
+        assert mask[a] and a == scripted_choice(board.astype(np.float64), mask.astype(np.uint8))
