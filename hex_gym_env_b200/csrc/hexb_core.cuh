@@ -335,12 +335,17 @@ HEXB_HD uint32_t flags_to_ones(uint32_t f) { return mulhi32(f, 1u << 25); }
 
 template <int VARIANT>
 HEXB_HD void encode_word_v(uint32_t x, uint32_t one, uint32_t &obs, uint32_t &msk) {
+    // 4 ALU-pipe ops (three LOP3 for t's operand, z, c and one for r1) + 4 FMA-pipe ops (the add, two multiply-highs, one IMAD)
     const uint32_t t = fma_add(x & 0x7f7f7f7fu, 0x7f7f7f7fu, one);
     const uint32_t z = ~(t | x) & 0x80808080u;        // 0x80 per EMPTY cell
-    const uint32_t c = x & 0x80808080u;               // 0x80 per C stone
+    const uint32_t c1 = flags_to_ones(x & 0x80808080u);  // 0x01 per C stone
     msk = flags_to_ones(z);                           // legal == empty
-    if (VARIANT == VARIANT_B) obs = sign_fill(~(z | x) & 0x80808080u) | flags_to_ones(c);   // R -> 0xff, C -> 0x01
-    else obs = flags_to_ones(c) | (msk << 1);         // BLACK 0 (= R), WHITE 1 (= C), EMPTY 2
+    if (VARIANT == VARIANT_B) {
+        const uint32_t r1 = (msk | c1) ^ 0x01010101u; // 0x01 per R stone
+        obs = r1 * 0xffu + c1;                        // R -> 0xff, C -> 0x01 (disjoint bytes: the multiply-add cannot carry)
+    } else {
+        obs = msk * 2u + c1;                          // BLACK 0 (= R), WHITE 1 (= C), EMPTY 2
+    }
 }
 HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) {
     if (variant == VARIANT_B) encode_word_v<VARIANT_B>(x, 1u, obs, msk);
