@@ -56,14 +56,14 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ step kernel
-// One warp = one chunk of 32 games; a CTA is 4 independent warps (no __syncthreads anywhere). Per warp:
+// One warp = one chunk of 32 games; a CTA is HEXB_WARPS_PER_CTA independent warps (default 1; no __syncthreads anywhere). Per warp:
 //   lane 0 starts ONE bulk asynchronous copy (cp.async.bulk = the 1-D TMA path, completion on the warp's own mbarrier)
 //   of the chunk (32 games' label bytes + record words, one contiguous block) into shared memory; meanwhile every lane
 //   fetches its game's meta / stream-position words and runs the Philox rounds of the step's two draws; then the
 //   thread-per-game plies, the rare finished-game rows, the elementwise obs/mask encode with 16-byte coalesced stores, the
 //   warp-per-game relabel sweeps, and one bulk copy of the chunk back to global memory.
 #ifndef HEXB_WARPS_PER_CTA
-#define HEXB_WARPS_PER_CTA 4
+#define HEXB_WARPS_PER_CTA 1   // measured: 1 warp per CTA 102.2 us, 2: 104.0 us, 4: 104.4 us per 1 Mi-game step (finer-grained tail)
 #endif
 constexpr int kWarpsPerCta = HEXB_WARPS_PER_CTA;   // Gpad is a multiple of kTile = 128 games, so 1, 2 and 4 all divide it
 constexpr int kCtaThreads = kWarpsPerCta * kWarp;
