@@ -18,7 +18,7 @@ Reference lines (paths relative to the reference root):
   HexEnvB                minihex/HexSingleGame.py:156-331
   selfplay_wrapper       minihex/SelfplayWrapper.py:37-208
   BaseRandomPolicy / OpponentPolicy / random_policy   SelfplayWrapper.py:16-35, minihex/__init__.py:8-12
-Not carried over (out of scope): render(), the pygame GUI (play_gui / show_board / "interactive"),
+Not carried over (out of scope): the pygame GUI (play_gui / show_board / "interactive"),
 player_color=WHITE of variant A (corrupt in the reference, HexGame.py:245-248).
 """
 import random  # noqa: F401  (module attribute on purpose: the reference draws from the global `random`; tests swap it)
@@ -263,6 +263,17 @@ class OpponentPolicy(object):
 
 
 # ---------------------------------------------------------------------------------------------------- variant-A env
+def _print_board(board, empty, black):
+    """ANSI rendering in the reference's rhombus layout (HexGame.py:305-330 / HexSingleGame.py:273-298): O empty, B / W stones."""
+    n = board.shape[1]
+    print(" " * 6 + "".join("  %d  |" % (j + 1) for j in range(n)))
+    print(" " * 5 + "-" * (n * 6 - 1))
+    for i in range(n):
+        cells = "".join("  %s  |" % ("O" if board[i, j] == empty else ("B" if board[i, j] == black else "W")) for j in range(n))
+        print(" " * (1 + i * 3) + "%d  |" % (i + 1) + cells)
+        print(" " * (i * 3 + 1) + "-" * (n * 7 - 1))
+
+
 class HexEnvA(_EnvBase):
     """minihex.HexGame.HexEnv ('hex-v0'): the agent plays BLACK against `opponent_policy` inside step()."""
 
@@ -352,7 +363,7 @@ class HexEnvA(_EnvBase):
         return action
 
     def render(self, mode="ansi", close=False):
-        raise NotImplementedError("render() is out of scope (UI)")
+        _print_board(self.simulator.board, player.EMPTY, player.BLACK)
 
 
 # ---------------------------------------------------------------------------------------------------- variant-B env
@@ -438,7 +449,7 @@ class HexEnvB(_EnvBase):
         self.simulator._ref_flipped = not self.simulator._ref_flipped
 
     def render(self, mode="ansi", close=False):
-        raise NotImplementedError("render() is out of scope (UI)")
+        _print_board(self.simulator.board, 0, -1)
 
 
 # ---------------------------------------------------------------------------------------------------- self-play wrapper
