@@ -324,6 +324,17 @@ HEXB_HD uint32_t sign_fill(uint32_t f) {
     return ((f >> 7) & 0x01010101u) * 0xffu;
 #endif
 }
+// byte k (0..2) of a relabel request replicated into all four bytes: one PRMT on the device
+template <int K>
+HEXB_HD uint32_t splat_byte(uint32_t prm) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(prm), "r"(0u), "r"(0x1111u * K));
+    return d;
+#else
+    return ((prm >> (8 * K)) & 0xffu) * 0x01010101u;
+#endif
+}
 // a + b issued as a multiply-add (IMAD, FMA pipe) instead of an add (IADD3 / VIADD, ALU pipe). `one` is Params::one: the
 // step kernel is bound by the ALU pipe (LOP3 / SHF / PRMT / ISETP, rt 2 cycles per warp instruction and SMSP) while the FMA
 // pipe idles, so the adds and shifts of the byte-SIMD loops are steered there.

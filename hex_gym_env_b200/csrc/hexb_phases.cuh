@@ -338,9 +338,9 @@ struct RowSpan {
 
 // one relabel request applied to one word: every byte equal to o1 (or o2) becomes m; zf = 0x80 flags of the bytes to change
 HEXB_HD uint32_t relabel_flags(uint32_t x, uint32_t prm, uint32_t one) {
-    const uint32_t o1 = prm & 0xffu, o2 = (prm >> 8) & 0xffu;
-    uint32_t zf = zero_flags(x ^ splat(o1), one);
-    if (o2 != o1) zf |= zero_flags(x ^ splat(o2), one);  // a third adjacent group is rare; the branch is warp-uniform
+    const uint32_t s1 = splat_byte<0>(prm), s2 = splat_byte<1>(prm);
+    uint32_t zf = zero_flags(x ^ s1, one);
+    if (s2 != s1) zf |= zero_flags(x ^ s2, one);  // a third adjacent group is rare; the branch is warp-uniform
     return zf;
 }
 
@@ -351,21 +351,24 @@ template <int N>
 HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t prmB, int lane, uint32_t one) {
     constexpr int C = Geo<N>::C;
     const int rs = r * C, re = rs + C;
-    const int wl = (re - 1) >> 2;
+    const int w0 = rs >> 2, wl = (re - 1) >> 2;
+    // row_mask() of the row's first and last word, computed once per row (warp-uniform); every word in between is all ones
+    const uint32_t first = Chunk<N>::ALIGNED_ROWS ? 0xffffffffu : 0xffffffffu << (8 * (rs & 3));
+    const uint32_t last = Chunk<N>::ALIGNED_ROWS ? 0xffffffffu : 0xffffffffu >> (8 * (3 - ((re - 1) & 3)));
 #pragma unroll
     for (int it = 0; it < RowSpan<N>::SWEEPS; ++it) {
-        const int w = (rs >> 2) + lane + it * kWarp;
+        const int w = w0 + lane + it * kWarp;
         if (w > wl) break;
         const uint32_t x = lab32[w];
-        const uint32_t rm = row_mask<N>(rs, re, w);
+        const uint32_t rm = (w == w0 ? first : 0xffffffffu) & (w == wl ? last : 0xffffffffu);
         uint32_t x2 = x;
         if (prmA & P_NEED) {
             const uint32_t mk = sign_fill(relabel_flags(x, prmA, one)) & rm;
-            x2 = (x2 & ~mk) | (splat((prmA >> 16) & 0xffu) & mk);
+            x2 = (x2 & ~mk) | (splat_byte<2>(prmA) & mk);
         }
         if (prmB & P_NEED) {
             const uint32_t mk = sign_fill(relabel_flags(x, prmB, one)) & rm;
-            x2 = (x2 & ~mk) | (splat((prmB >> 16) & 0xffu) & mk);
+            x2 = (x2 & ~mk) | (splat_byte<2>(prmB) & mk);
         }
         if (x2 != x) lab32[w] = x2;
     }
