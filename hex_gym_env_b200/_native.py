@@ -64,6 +64,7 @@ SYMBOLS = {
     "hexb_state_bytes": (_sz, [_cfgp]),
     "hexb_create": (_i32, [_cfgp, _vp, _sz, _vp, ctypes.POINTER(_vp)]),
     "hexb_destroy": (_i32, [_vp]),
+    "hexb_get_config": (_i32, [_vp, _cfgp]),
     "hexb_reset": (_i32, [_vp] * 6),
     "hexb_step": (_i32, [_vp] * 10),
     "hexb_host_workspace_bytes": (_sz, [_cfgp]),

@@ -75,6 +75,11 @@ class HexBatch(object):
         self._pinned = None
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def handle(self):
+        """The hexb_env* as an int: the first argument of the torch.ops.hexb.* operators (torch_ops.py)."""
+        return int(self._h.value)
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

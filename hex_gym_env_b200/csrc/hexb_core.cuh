@@ -37,7 +37,7 @@ namespace hexb {
 // ----------------------------------------------------------------------------------------------
 // constants
 // ----------------------------------------------------------------------------------------------
-constexpr int kTile = 128;  // games per CTA == threads per CTA (4 warps, each owning a chunk of 32 games)
+constexpr int kTile = 128;  // a shard's game count is padded to a multiple of this (4 chunks of 32 games), so 1, 2 or 4 warps per CTA all divide it
 
 enum : int { VARIANT_A = 0, VARIANT_B = 1 };
 enum : int { MODE_STEP = 0, MODE_RESET = 1, MODE_PLY = 2, MODE_HALF = 3 };

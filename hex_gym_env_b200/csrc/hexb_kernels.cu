@@ -1,9 +1,10 @@
 // hexb_kernels.cu - sm_100a kernels and the C ABI (include/hexb.h) of the batched Hex simulator.
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (see build.py).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC (hex_gym_env_b200/_native.py: build).
 //
 // Kernel inventory:
-//   K1/K2/K3  hexb_step_kernel<N>  one warp per chunk of 32 games, 4 warps per CTA; MODE_RESET / MODE_STEP / MODE_PLY
+//   K1/K2/K3  hexb_step_kernel<N>  one warp per chunk of 32 games, HEXB_WARPS_PER_CTA (default 1) warps per CTA;
+//             MODE_RESET / MODE_STEP / MODE_PLY / MODE_HALF, and T steps per launch for hexb_rollout
 //   K4        hexb_sample_kernel   standalone k-th-empty-cell sampler
 //   K5        hexb_encode_kernel   standalone observation + mask encoder (either view)
 //   K6        hexb_export_kernel / hexb_import_kernel   reference-layout dump / preset boards
@@ -402,16 +403,12 @@ static bool cfg_ok(const hexb_config *c) {
 
 struct Layout {
     long long Gpad;
-    size_t labels_off, rec_off, stats_off, total;
+    size_t stats_off, total;   // the chunks (labels + records of 32 games each) start at offset 0; the statistics follow
 };
 static Layout layout_of(const hexb_config *c) {
     Layout L;
     const long long C = (long long)c->board_size * c->board_size;
-    const long long W = (C + 31) / 32, R = 2 * W + 2;
     L.Gpad = (c->num_games + kTile - 1) / kTile * kTile;
-    L.labels_off = 0;
-    L.rec_off = 0;   // chunk-major: records follow the labels inside every chunk
-    (void)W; (void)R;
     L.stats_off = align256((size_t)(L.Gpad / 32 * chunk_state_bytes((int)C)));
     L.total = L.stats_off + align256((size_t)kStatStripes * 8 * 8);
     return L;
@@ -470,6 +467,12 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
 int32_t hexb_destroy(hexb_env *env) {
     if (!env) return HEXB_ERR_ARG;
     free(env);
+    return HEXB_OK;
+}
+
+int32_t hexb_get_config(const hexb_env *env, hexb_config *out) {
+    if (!env || !out) return HEXB_ERR_ARG;
+    *out = env->cfg;
     return HEXB_OK;
 }
 

@@ -78,6 +78,9 @@ size_t hexb_state_bytes(const hexb_config *cfg);
  * (SelfplayWrapper.py:39-67). Games are not playable until hexb_reset. */
 int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, void *stream, hexb_env **out);
 int32_t hexb_destroy(hexb_env *env);
+/* The configuration the handle was created with (the attribute reads .board_size etc. of the reference's env objects); bindings
+ * use it to validate the sizes of the buffers they are handed. */
+int32_t hexb_get_config(const hexb_env *env, hexb_config *out);
 
 /* reset(): HexGame.__init__ on an empty board (HexGame.py:21-68, HexSingleGame.py:26-71), HexEnv.reset
  * (HexGame.py:206-242, HexSingleGame.py:208-231), SelfPlayEnv.reset + setup_opponents + opening continue_game
