@@ -1,0 +1,87 @@
+"""Per-source-line hot spots of one profiled kernel launch.
+
+    python tools/ncu_source_hotspots.py gpurun_out/prof.ncu-rep hex_gym_env_b200/libhexb.so \
+        _Z16hexb_step_kernelILi11ELi1EEvN4hexb6ParamsE [source_dir] [top_n]
+
+Joins `ncu -i <rep> --page source --csv` (per-SASS-instruction executed-instruction counts and warp-stall samples; the report
+must come from `ncu --set full --import-source on`) with the line table `nvdisasm -g` prints for the same kernel of the same
+library build (-lineinfo), and aggregates by source line and by enclosing function. source_dir holds the .cu/.cuh files the
+library was built from (default hex_gym_env_b200/csrc)."""
+import collections
+import csv
+import glob
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep, so, kernel = sys.argv[1:4]
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+srcdir = sys.argv[4] if len(sys.argv) > 4 else os.path.join(root, "hex_gym_env_b200", "csrc")
+top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+
+with tempfile.TemporaryDirectory() as tmp:
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+    cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True, check=True).stdout.split("\n")
+start = next(i for i, l in enumerate(dis) if l.startswith(kernel + ":"))
+loc, seq = None, []
+for l in dis[start + 1:]:
+    if l.startswith("//--------------------- "):
+        break
+    m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
+    if m:
+        loc = (os.path.basename(m.group(1)), int(m.group(2)))
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+    if m:
+        seq.append((int(m.group(1), 16), loc))
+
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, data = rows[1], rows[2:]
+ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
+assert len(seq) == len(data), "the library is not the build that was profiled (%d vs %d SASS instructions)" % (len(seq), len(data))
+base = int(data[0][0], 16)
+byline = collections.defaultdict(lambda: [0, 0, 0])
+tot_i = tot_s = 0
+for (off, lc), r in zip(seq, data):
+    assert int(r[0], 16) - base == off
+    byline[lc][0] += int(r[ia])
+    byline[lc][1] += int(r[isamp])
+    byline[lc][2] += 1
+    tot_i += int(r[ia])
+    tot_s += int(r[isamp])
+src = {}
+for f in os.listdir(srcdir):
+    if f.endswith((".cu", ".cuh")):
+        src[f] = open(os.path.join(srcdir, f)).read().split("\n")
+
+
+def func_of(f, ln):
+    if f not in src:
+        return f
+    L = src[f]
+    for i in range(ln - 1, -1, -1):
+        if re.match(r"^(HEXB_HD|__device__|__global__|static)", L[i]) and "(" in L[i]:
+            m = re.search(r"(\w+)\s*\(", L[i].replace("__launch_bounds__(kCtaThreads, min_ctas(N))", ""))
+            return m.group(1) if m else L[i]
+    return "?"
+
+
+print("%s: %d SASS instructions, %d warp instructions executed, %d stall samples" % (kernel, len(seq), tot_i, tot_s))
+print("\n-- by source line (share of stall samples, share of executed warp instructions, SASS instructions on the line)")
+for (f, ln), (ie, s, cnt) in sorted(byline.items(), key=lambda kv: -kv[1][1])[:top]:
+    text = src[f][ln - 1].strip()[:110] if f in src and ln <= len(src[f]) else ""
+    print("%6.2f%% samp %6.2f%% instr  n=%3d  %s:%d  %s" % (100.0 * s / tot_s, 100.0 * ie / tot_i, cnt, f, ln, text))
+fn = collections.defaultdict(lambda: [0, 0])
+for (f, ln), (ie, s, cnt) in byline.items():
+    k = func_of(f, ln)
+    fn[k][0] += ie
+    fn[k][1] += s
+print("\n-- by enclosing function")
+for k, (ie, s) in sorted(fn.items(), key=lambda kv: -kv[1][1]):
+    if s or ie:
+        print("%6.2f%% samp %6.2f%% instr  %s" % (100.0 * s / tot_s, 100.0 * ie / tot_i, k))
