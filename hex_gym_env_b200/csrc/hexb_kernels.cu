@@ -153,7 +153,7 @@ __device__ __forceinline__ void add_stats(const Params &P, long long wglobal, in
 // KIND_ROLLOUT: P.steps env steps per launch on the resident chunk (hexb_rollout);
 // KIND_OTHER: reset / raw ply / half step, selected at run time by P.mode.
 enum : int { KIND_OTHER = 0, KIND_STEP = 1, KIND_ROLLOUT = 2 };
-template <int N, int KIND>
+template <int N, int KIND, bool BATCHED>
 __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(const Params P) {
     constexpr bool STEP_ONLY = KIND != KIND_OTHER;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -244,14 +244,39 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
             }
         }
 
-        // ---- warp-per-game row jobs, part 2: relabel sweeps (regions[regions == label] = new label, both plies at once)
-        pending = __ballot_sync(FULL, (flg & (F_RELABEL | F_RESET)) == F_RELABEL);
-        while (pending) {
-            const int r = __ffs(pending) - 1;
-            pending &= pending - 1;
-            const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r);
-            relabel_row_lane<N>(lab32, r, ra, rb, lane, P.one);
-            __syncwarp();   // (sweeping two non-adjacent rows per iteration for ILP was measured: slower, 114 vs 111 us)
+        // ---- row jobs, part 2: relabel sweeps (regions[regions == label] = new label, both plies of the step at once)
+        if (!BATCHED) {
+            // one row per pass, one word per lane: the faster form when the launch is several waves deep (HBM-bound regime)
+            uint32_t pending = __ballot_sync(FULL, (flg & (F_RELABEL | F_RESET)) == F_RELABEL);
+            while (pending) {
+                const int r = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r);
+                relabel_row_lane<N>(lab32, r, ra, rb, lane, P.one);
+                __syncwarp();
+            }
+        } else {
+            // RPS rows per pass (Sweep<N>): fewer, wider passes shorten a warp's dependent chain - the faster form when the
+            // launch is at most about one wave of warps and the step time is a single warp's latency (small batches, rollouts)
+            using SW = Sweep<N>;
+            const bool need = (flg & (F_RELABEL | F_RESET)) == F_RELABEL;
+            uint32_t olds_l = 0, news_l = 0, n_l = 0;
+            if (need) canon_request(prmA, prmB, olds_l, news_l, n_l);
+            const uint32_t pend_all = __ballot_sync(FULL, need);
+            const int sg = lane / SW::LPR, sl = lane % SW::LPR;
+            constexpr int CLASSES = (Chunk<N>::ALIGNED_ROWS || SW::RPS == 1) ? 1 : 2;
+#pragma unroll
+            for (int cls = 0; cls < CLASSES; ++cls) {
+                uint32_t pp = CLASSES == 1 ? pend_all : (pend_all & (cls ? 0xaaaaaaaau : 0x55555555u));
+                while (pp) {
+                    const int row = pick_row<N>(pp, sg);
+                    const int srcl = row & 31;
+                    const uint32_t o = __shfl_sync(FULL, olds_l, srcl), nw = __shfl_sync(FULL, news_l, srcl);
+                    const uint32_t n = __shfl_sync(FULL, n_l, srcl);
+                    relabel_rows_lane<N>(lab32, row, sl, o, nw, (int)n, P.one);
+                    __syncwarp();
+                }
+            }
         }
     }
 
@@ -478,24 +503,42 @@ int32_t hexb_get_config(const hexb_env *env, hexb_config *out) {
 
 }  // extern "C"
 
+// number of chunk-warps one wave of the step kernel holds on this device (SMs x resident CTAs per SM x warps per CTA)
+static long long wave_warps(int device) {
+    static long long cached[64] = {0};
+    if (device < 0 || device >= 64) return 148ll * 32;
+    if (!cached[device]) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+        cached[device] = (long long)sms * 32;
+    }
+    return cached[device];
+}
+
 template <int N>
 static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     constexpr int smem = SmemLayout<N>::BYTES;
     static bool attr_done = false;
     if (!attr_done) {
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_STEP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_ROLLOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_ROLLOUT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_OTHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CK(cudaFuncSetAttribute(hexb_step_kernel<N, KIND_OTHER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define HEXB_ATTR(K, B)                                                                                                        \
+    CK(cudaFuncSetAttribute(hexb_step_kernel<N, K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+    CK(cudaFuncSetAttribute(hexb_step_kernel<N, K, B>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        HEXB_ATTR(KIND_STEP, false) HEXB_ATTR(KIND_STEP, true) HEXB_ATTR(KIND_ROLLOUT, true) HEXB_ATTR(KIND_OTHER, false)
+#undef HEXB_ATTR
         attr_done = true;
     }
     const unsigned grid = (unsigned)(P.Gpad / kCtaThreads);
-    (void)e;
-    if (P.mode == MODE_STEP && P.steps == 1) hexb_step_kernel<N, KIND_STEP><<<grid, kCtaThreads, smem, s>>>(P);
-    else if (P.mode == MODE_STEP) hexb_step_kernel<N, KIND_ROLLOUT><<<grid, kCtaThreads, smem, s>>>(P);
-    else hexb_step_kernel<N, KIND_OTHER><<<grid, kCtaThreads, smem, s>>>(P);
+    // at most about one wave of warps: the step time is one warp's latency -> the batched relabel sweep; deeper launches are
+    // HBM-bound and run the one-row-per-pass sweep (measured on 1 Mi games 11x11: 99.5 us vs 105.0 us; on 4,096 games 6x6: 6.7 vs 6.0 us)
+    const bool small = P.Gpad / kWarp <= wave_warps(e->cfg.device);
+    if (P.mode == MODE_STEP && P.steps == 1) {
+        if (small) hexb_step_kernel<N, KIND_STEP, true><<<grid, kCtaThreads, smem, s>>>(P);
+        else hexb_step_kernel<N, KIND_STEP, false><<<grid, kCtaThreads, smem, s>>>(P);
+    } else if (P.mode == MODE_STEP) {
+        hexb_step_kernel<N, KIND_ROLLOUT, true><<<grid, kCtaThreads, smem, s>>>(P);
+    } else {
+        hexb_step_kernel<N, KIND_OTHER, false><<<grid, kCtaThreads, smem, s>>>(P);
+    }
     CK(cudaGetLastError());
     return HEXB_OK;
 }

@@ -374,6 +374,92 @@ HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t pr
     }
 }
 
+// ---- batched relabel sweep: several rows per warp pass.
+// A row of label bytes spans at most RowSpan<N>::WORDS words; a group of LPR lanes takes one row, WPL words per lane, so one
+// pass of the warp relabels RPS = 32 / LPR rows (4 rows of an 11x11 board, 8 of a 7x7 one) instead of one, with WPL independent
+// words in flight per lane. Rows handled in the same pass must not share an edge word (odd N): the caller batches rows of equal
+// parity, which are never adjacent.
+template <int N>
+struct Sweep {
+    static constexpr int WPL = 4;
+    static constexpr int NEED = (RowSpan<N>::WORDS + WPL - 1) / WPL;
+    static constexpr int LPR = NEED <= 4 ? 4 : (NEED <= 8 ? 8 : (NEED <= 16 ? 16 : 32));
+    static constexpr int RPS = kWarp / LPR;
+};
+
+// The step's two relabel requests (prm words of place_stone) as up to four (old byte -> new byte) pairs: olds / news hold
+// pair p in byte p, n = number of pairs; unused slots repeat pair 0 (applying a pair twice is a no-op).
+HEXB_HD void canon_request(uint32_t prmA, uint32_t prmB, uint32_t &olds, uint32_t &news, uint32_t &n) {
+    olds = 0; news = 0; n = 0;
+    const uint32_t prm[2] = {prmA, prmB};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t o1 = prm[i] & 0xffu, o2 = (prm[i] >> 8) & 0xffu, m = (prm[i] >> 16) & 0xffu;
+        if (prm[i] & P_NEED) {
+            olds |= o1 << (8 * n); news |= m << (8 * n); n++;
+            if (o2 != o1) { olds |= o2 << (8 * n); news |= m << (8 * n); n++; }
+        }
+    }
+    if (n < 4u) {
+        const uint32_t keep = (1u << (8 * n)) - 1u;
+        olds = (olds & keep) | (splat(olds & 0xffu) & ~keep);
+        news = (news & keep) | (splat(news & 0xffu) & ~keep);
+    }
+}
+
+// The sg-th (0-based) lowest set bit of *pp for each of the RPS lane groups, -1 if there are fewer; clears the RPS lowest bits.
+template <int N>
+HEXB_HD int pick_row(uint32_t &pp, int sg) {
+    int mine = -1;
+#pragma unroll
+    for (int k = 0; k < Sweep<N>::RPS; ++k) {
+        int r = -1;
+        if (pp) {
+#if defined(__CUDA_ARCH__)
+            r = __ffs(pp) - 1;
+#else
+            r = __builtin_ctz(pp);
+#endif
+        }
+        if (k == sg) mine = r;
+        pp &= pp - 1u;   // stays 0 once empty
+    }
+    return mine;
+}
+
+// One lane's share of one pass: sub-lane sl of the group that owns `row` applies the row's n pairs to its WPL words
+// (regions[regions == label] = new_region_label, HexGame.py:141-142, HexSingleGame.py:152-153, for both plies of the step).
+template <int N>
+HEXB_HD void relabel_rows_lane(uint32_t *lab32, int row, int sl, uint32_t olds, uint32_t news, int n, uint32_t one) {
+    constexpr int C = Geo<N>::C, WPL = Sweep<N>::WPL, LPR = Sweep<N>::LPR;
+    if (row < 0) return;
+    const int rs = row * C, re = rs + C;
+    const int w0 = rs >> 2, wl = (re - 1) >> 2;
+    const uint32_t first = Chunk<N>::ALIGNED_ROWS ? 0xffffffffu : 0xffffffffu << (8 * (rs & 3));
+    const uint32_t last = Chunk<N>::ALIGNED_ROWS ? 0xffffffffu : 0xffffffffu >> (8 * (3 - ((re - 1) & 3)));
+    uint32_t x[WPL], y[WPL], rm[WPL];
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) {
+        const int w = w0 + sl + j * LPR;
+        x[j] = w <= wl ? lab32[w] : 0u;   // a word outside the row holds nothing to relabel (labels are never 0)
+        y[j] = x[j];
+        rm[j] = (w == w0 ? first : 0xffffffffu) & (w == wl ? last : 0xffffffffu);
+    }
+    for (int p = 0; p < n; ++p) {
+        const uint32_t so = splat_byte_dyn(olds, p), sn = splat_byte_dyn(news, p);
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) {
+            const uint32_t mk = sign_fill(zero_flags(y[j] ^ so, one)) & rm[j];
+            y[j] = (y[j] & ~mk) | (sn & mk);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) {
+        const int w = w0 + sl + j * LPR;
+        if (y[j] != x[j]) lab32[w] = y[j];
+    }
+}
+
 // Games that restart get an empty board (HexSingleGame.py:208-231 / HexGame.py:206-220) plus the opponent's opening stone
 // when it moves first (flg bits 8-15 = its byte, 16-31 = its cell).
 template <int N>

@@ -42,12 +42,18 @@ def lib():
         L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
         L.emu_set_info.argtypes = [vp, vp, vp]
         L.emu_rollout.argtypes = [vp, i32] + [vp] * 6
+        L.emu_force_sweep.argtypes = [i32]
         _LIB = L
     return _LIB
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def force_sweep(form):
+    """-1: the relabel sweep the device would pick for a small batch; 0: one row per pass; 1: several rows per pass."""
+    lib().emu_force_sweep(int(form))
 
 
 class EmuBatch(object):

@@ -24,6 +24,11 @@ struct emu_env {
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Which relabel sweep to replay: the device picks the batched form (several rows per warp pass) for single steps of at most
+// one wave of warps and for rollouts, the one-row-per-pass form for deeper launches and for reset / ply / half step.
+// -1 = like the device for a small batch, 0 / 1 = force one form (so that CPU tests cover both).
+static int g_force_sweep = -1;
+
 template <int N>
 static void run_tiles(Params P) {
     constexpr int C = Geo<N>::C;
@@ -63,7 +68,39 @@ static void run_tiles(Params P) {
                 if (flg[r] & F_TERM)
                     for (int lane = 0; lane < kWarp; ++lane) term_row_lane<N>(chunk, r, flg[r], P, g0 + r + so, lane);
                 for (int lane = 0; lane < kWarp; ++lane)
-                    row_job_lane<N>(chunk, r, prmA[r], prmB[r], flg[r] & ~F_TERM, P, g0 + r + so, lane, [] {});
+                    row_job_lane<N>(chunk, r, 0u, 0u, flg[r] & ~(F_TERM | F_RELABEL), P, g0 + r + so, lane, [] {});
+            }
+            const bool batched = g_force_sweep < 0 ? (P.mode == MODE_STEP) : (g_force_sweep != 0);
+            if (!batched) {
+                for (int r = 0; r < kWarp; ++r)
+                    if ((flg[r] & (F_RELABEL | F_RESET)) == F_RELABEL)
+                        for (int lane = 0; lane < kWarp; ++lane)
+                            relabel_row_lane<N>(reinterpret_cast<uint32_t *>(chunk), r, prmA[r], prmB[r], lane, 1u);
+            } else {   // batched relabel sweeps, as the device kernel runs them: lane group sg takes the sg-th pending row of a parity class
+                using SW = Sweep<N>;
+                uint32_t olds[kWarp], news[kWarp], cnt[kWarp], pend_all = 0;
+                for (int r = 0; r < kWarp; ++r) {
+                    olds[r] = news[r] = cnt[r] = 0;
+                    if ((flg[r] & (F_RELABEL | F_RESET)) == F_RELABEL) {
+                        canon_request(prmA[r], prmB[r], olds[r], news[r], cnt[r]);
+                        pend_all |= 1u << r;
+                    }
+                }
+                const int classes = (Chunk<N>::ALIGNED_ROWS || SW::RPS == 1) ? 1 : 2;
+                for (int cls = 0; cls < classes; ++cls) {
+                    uint32_t pp = classes == 1 ? pend_all : (pend_all & (cls ? 0xaaaaaaaau : 0x55555555u));
+                    while (pp) {
+                        uint32_t next = pp;
+                        for (int lane = 0; lane < kWarp; ++lane) {
+                            uint32_t q = pp;
+                            const int row = pick_row<N>(q, lane / SW::LPR);
+                            next = q;
+                            relabel_rows_lane<N>(reinterpret_cast<uint32_t *>(chunk), row, lane % SW::LPR, olds[row & 31], news[row & 31],
+                                                 row >= 0 ? (int)cnt[row] : 0, 1u);
+                        }
+                        pp = next;
+                    }
+                }
             }
             if (P.mode != MODE_PLY && P.mode != MODE_HALF && (P.obs || P.mask)) {   // elementwise encode, then the rare opponent-view rows
                 const long long out0 = (g0 + so) * C, limit = (so + P.G) * C;
@@ -130,6 +167,7 @@ void *emu_create(int N, int variant, long long G, long long game_offset, unsigne
     return e;
 }
 void emu_destroy(void *h) { delete (emu_env *)h; }
+void emu_force_sweep(int form) { g_force_sweep = form; }
 void emu_set_manual_opponent(void *h, int pool_size, int32_t *opp_index, uint8_t *to_move) {
     emu_env *e = (emu_env *)h;
     e->base.manual_opponent = 1; e->base.pool_size = pool_size; e->base.opp_index = opp_index; e->base.to_move = to_move;

@@ -109,3 +109,17 @@ def test_golden_preset_boards(name):
         env.import_boards(z["board_true"], np.zeros(G, np.int8))
         return env
     parity.golden_preset(make_raw, name)
+
+
+@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("N", [3, 4, 7, 8, 11, 13, 16, 19])
+def test_both_relabel_sweep_forms(N, form):
+    """The device runs the one-row-per-pass sweep on deep launches and the several-rows-per-pass sweep on small ones; the CPU
+    batches here are all small, so force each form in turn (odd and even boards: rows with and without shared edge words)."""
+    from emu import emu
+    emu.force_sweep(form)
+    try:
+        parity.versus_oracle(make, hexref.KIND_SELFPLAY_B, N, 97, N * N // 2 + 8, seed=100 + N, fused=True, agent_mode=2, check_state_every=2)
+        parity.snake_chain(make, N) if N in (7, 11) else None
+    finally:
+        emu.force_sweep(-1)
