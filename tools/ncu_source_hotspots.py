@@ -41,7 +41,16 @@ for l in dis[start + 1:]:
 
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, data = rows[1], rows[2:]
+# the page holds one section per profiled launch ("Kernel Name" row, header row, one row per SASS instruction): sum the sections
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+hdr = rows[starts[0] + 1]
+sections = [[r for r in rows[a + 2:b] if len(r) == len(hdr) and r[0].startswith("0x")] for a, b in zip(starts, starts[1:])]
+sections = [sec for sec in sections if len(sec) == len(sections[0])]
+data = [list(r) for r in sections[0]]
+for col in (hdr.index("Instructions Executed"), hdr.index("# Samples")):
+    for k in range(len(data)):
+        data[k][col] = str(sum(int(sec[k][col]) for sec in sections))
+print("%d profiled launch(es) summed" % len(sections))
 ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 assert len(seq) == len(data), "the library is not the build that was profiled (%d vs %d SASS instructions)" % (len(seq), len(data))
 base = int(data[0][0], 16)
