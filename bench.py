@@ -163,7 +163,7 @@ def run_reference(args):
                              "c_port_all_threads": c_all, "c_port_sample": c_sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -349,9 +349,18 @@ def run_gpu(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(N, args.cpu_budget)
-        print(json.dumps(line))
+        print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints "NCCL version ..." there when NCCL_DEBUG is set) write to
+    file descriptor 1, so point descriptor 1 at stderr and return a private handle to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -368,6 +377,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
+    args.out = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
