@@ -187,6 +187,25 @@ class HexBatch(object):
             out["actions"] = actions_out
         return out
 
+    def capture_steps(self, num_steps, **step_kwargs):
+        """Capture `num_steps` calls of step(**step_kwargs) into a CUDA graph and return it (torch.cuda.CUDAGraph; .replay()
+        runs the steps on the current stream). For launch-bound batches: a 65,536-game 7x7 step is 8 us on the device but
+        12 us to issue from Python. The graph reads and writes the tensors passed in step_kwargs (or this object's default
+        output tensors): refill an `actions` tensor in place between replays. One eager step runs first (outside the graph)."""
+        dev = self.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            self.step(**step_kwargs)          # allocates the default output tensors and loads the kernel before the capture
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(int(num_steps)):
+                    out = self.step(**step_kwargs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph.outputs = out
+        return graph
+
     def enable_info(self):
         """Also record, at every step(), the fields of the reference's info dict (HexGame.py:281-286) as device tensors:
         self.last_move_opponent i32[G] and self.winner i8[G]; info["last_move_player"] is step(want_actions=True)["actions"]."""

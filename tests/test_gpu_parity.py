@@ -334,3 +334,30 @@ def test_misaligned_output_buffers():
         assert torch.equal(o["obs"], obs_u) and torch.equal(o["mask"], mask_u), t
     assert int(big_o[:3].abs().sum()) == 0 and int(big_o[3 + G * N * N:].abs().sum()) == 0      # nothing written outside the slice
     assert int(big_m[:5].sum()) == 0 and int(big_m[5 + G * N * N:].sum()) == 0
+
+
+def test_capture_steps_graph():
+    """HexBatch.capture_steps: K steps replayed from a CUDA graph == K eager steps (fused agent and external actions)."""
+    import torch
+    from hex_gym_env_b200 import HexBatch
+    N, G, K = 7, 3000, 8
+    a = HexBatch(N, G, variant=1, device=0, seed=12, agent_mode=2)
+    b = HexBatch(N, G, variant=1, device=0, seed=12, agent_mode=2)
+    a.reset(); b.reset()
+    g = a.capture_steps(K)
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    for _ in range(1 + 2 * K):
+        o = b.step()
+    for k in ("obs", "mask", "reward", "done"):
+        assert torch.equal(g.outputs[k], o[k]), k
+    assert torch.equal(a.stats(), b.stats())
+    acts = torch.zeros(G, dtype=torch.int32, device="cuda")
+    g1 = a.capture_steps(1, actions=acts)          # the eager step inside plays cell 0 everywhere
+    b.step(acts)
+    for t in range(5):
+        acts.copy_(a.sample_actions(torch.full((G,), 0.37, dtype=torch.float64, device="cuda")))
+        g1.replay()
+        o = b.step(acts)
+        for k in ("obs", "mask", "reward", "done"):
+            assert torch.equal(g1.outputs[k], o[k]), (k, t)
