@@ -46,6 +46,7 @@ def main():
                     help="random: BaseRandomPolicy inside the fused step kernel; self: a frozen copy of the policy, refreshed every "
                          "--refresh iterations, played through the split step (hexb_half_step), like the reference's OpponentPolicy pool")
     ap.add_argument("--refresh", type=int, default=4)
+    ap.add_argument("--graph", action="store_true", help="replay the whole rollout (policy forward + sampling + env step + GAE) as one CUDA graph")
     args = ap.parse_args()
     torch.manual_seed(args.seed)
     dev = torch.device("cuda", 0)
@@ -62,34 +63,67 @@ def main():
             logits, _ = frozen(obs.float())
             return masked_sample(logits, mask, generator=ogen)[0]
 
-    opt = torch.optim.Adam(policy.parameters(), lr=args.lr, eps=1e-5)
-    col = RolloutCollector(env, args.n_steps, gamma=0.99, gae_lambda=0.95, seed=args.seed)
+    opt = torch.optim.Adam(policy.parameters(), lr=args.lr, eps=1e-5, capturable=args.graph)
+    col = RolloutCollector(env, args.n_steps, gamma=0.99, gae_lambda=0.95, seed=args.seed, extra_generators=[ogen])
+    buf = col.buf
+    n = buf.T * buf.G
+    flat = dict(obs=buf.obs[:-1].reshape(n, *buf.obs.shape[2:]), action_masks=buf.action_masks[:-1].reshape(n, -1),
+                actions=buf.actions.reshape(n), log_probs=buf.log_probs.reshape(n), advantages=buf.advantages.reshape(n),
+                returns=buf.returns.reshape(n))                              # views of the collector's (static) tensors
+    idx = torch.zeros(min(args.minibatch, n), dtype=torch.long, device=dev)  # the minibatch's sample indices
+    loss_out = torch.zeros((), device=dev)
+
+    def update_minibatch():
+        """One clipped-PPO optimizer step on the samples idx points at (sb3_contrib MaskablePPO.train, one minibatch)."""
+        mb = {k: v[idx] for k, v in flat.items()}
+        logits, values = policy(mb["obs"].float())
+        logits = logits.masked_fill(mb["action_masks"] == 0, -1e8)          # sb3_contrib's HUGE_NEG masking
+        logp_all = torch.log_softmax(logits, dim=-1)
+        logp = logp_all.gather(1, mb["actions"].long().unsqueeze(1)).squeeze(1)
+        adv = mb["advantages"]
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        ratio = torch.exp(logp - mb["log_probs"])
+        pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+        vloss = torch.nn.functional.mse_loss(values, mb["returns"])
+        ent = -(torch.exp(logp_all) * logp_all.masked_fill(mb["action_masks"] == 0, 0.0)).sum(-1).mean()
+        loss = pg + 0.5 * vloss - 0.0 * ent
+        loss.backward()
+        nn.utils.clip_grad_norm_(policy.parameters(), 0.5)
+        opt.step()
+        loss_out.copy_(loss.detach())
+
+    update_graph = None
+    pgen = torch.Generator(device=dev)
+    pgen.manual_seed(args.seed + 7)
     prev = env.stats().cpu()
     for it in range(args.iters):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if args.opponent == "self" and it and it % args.refresh == 0:
             frozen.load_state_dict(policy.state_dict())
-        buf = col.collect(policy, opponent_fn if args.opponent == "self" else None)
+        col.collect(policy, opponent_fn if args.opponent == "self" else None, use_graph=args.graph)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if args.graph and it == 1 and n % idx.numel() == 0:
+            # the first iteration's 320 eager optimizer steps were the warm-up; from now on one minibatch step = one graph replay
+            update_graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(update_graph):
+                update_minibatch()
         for _ in range(args.epochs):
-            for mb in buf.minibatches(args.minibatch):
-                logits, values = policy(mb["obs"].float())
-                logits = logits.masked_fill(mb["action_masks"] == 0, -1e8)      # sb3_contrib's HUGE_NEG masking
-                logp_all = torch.log_softmax(logits, dim=-1)
-                logp = logp_all.gather(1, mb["actions"].long().unsqueeze(1)).squeeze(1)
-                adv = mb["advantages"]
-                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                ratio = torch.exp(logp - mb["log_probs"])
-                pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 0.8, 1.2)).mean()
-                vloss = torch.nn.functional.mse_loss(values, mb["returns"])
-                ent = -(torch.exp(logp_all) * logp_all.masked_fill(mb["action_masks"] == 0, 0.0)).sum(-1).mean()
-                loss = pg + 0.5 * vloss - 0.0 * ent
-                opt.zero_grad(set_to_none=True)
-                loss.backward()
-                nn.utils.clip_grad_norm_(policy.parameters(), 0.5)
-                opt.step()
+            perm = torch.randperm(n, device=dev, generator=pgen)
+            for s0 in range(0, n, idx.numel()):
+                if update_graph is not None:
+                    idx.copy_(perm[s0:s0 + idx.numel()])
+                    update_graph.replay()
+                else:
+                    cur = perm[s0:s0 + idx.numel()]
+                    if cur.numel() != idx.numel():
+                        continue                                              # (ragged tail: dropped, like drop_last)
+                    idx.copy_(cur)
+                    opt.zero_grad(set_to_none=True)
+                    update_minibatch()
+        loss = loss_out
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         st = env.stats().cpu()

@@ -66,7 +66,7 @@ class RolloutBuffer(object):
             delta = self.rewards[t] + self.gamma * self.values[t + 1] * nonterminal - self.values[t]
             last = delta + self.gamma * self.gae_lambda * nonterminal * last
             self.advantages[t] = last
-        self.returns = self.advantages + self.values[:-1]
+        torch.add(self.advantages, self.values[:-1], out=self.returns)
 
     def minibatches(self, batch_size, generator=None):
         n = self.T * self.G
@@ -83,14 +83,24 @@ class RolloutCollector(object):
     """collect(): T fused env steps of all games with actions sampled from `policy` under the legal-action mask.
     `policy(obs_f32[G,N,N]) -> (logits f32[G,C], values f32[G])` is any torch callable living on the same GPU."""
 
-    def __init__(self, batch: HexBatch, n_steps, gamma=0.99, gae_lambda=0.95, seed=0):
+    def __init__(self, batch: HexBatch, n_steps, gamma=0.99, gae_lambda=0.95, seed=0, extra_generators=()):
+        """extra_generators: torch.Generator objects that policy / opponent_fn draw from (needed for use_graph=True: a CUDA
+        graph can only advance generators registered with it)."""
         self.batch, self.buf = batch, RolloutBuffer(n_steps, batch, gamma, gae_lambda)
+        self.extra_generators = list(extra_generators)
         self.gen = torch.Generator(device=batch.device)
         self.gen.manual_seed(seed)
         self._started = False
+        self._graph, self._graph_key = None, None
 
-    def collect(self, policy, opponent_fn=None):
-        """opponent_fn: only for manual_opponent batches - the learned opponent (see HexBatch.step_with_opponent)."""
+    def collect(self, policy, opponent_fn=None, use_graph=False):
+        """opponent_fn: only for manual_opponent batches - the learned opponent (see HexBatch.step_with_opponent).
+
+        use_graph=True: the whole rollout (T x [policy forward, masked sampling, env step] + GAE) is captured into ONE CUDA
+        graph the second time it is collected and replayed from then on - at 4,096 games a step is a handful of 5-10 us
+        kernels, so issuing them from Python costs several times their run time. The graph reads the policy's parameters in
+        place (optimizer steps and load_state_dict update them in place), draws from this collector's generator, and
+        writes the same buffer tensors every time. `policy` / `opponent_fn` must be the same objects on every call."""
         b, buf = self.batch, self.buf
         if b.manual_opponent and opponent_fn is None:
             raise ValueError("a manual_opponent batch needs opponent_fn")
@@ -101,7 +111,26 @@ class RolloutCollector(object):
                 b.encode(0, obs=buf.obs[0], mask=buf.action_masks[0])
             buf.episode_starts[0] = 1.0
             self._started = True
-        else:  # continue from where the previous rollout stopped
+            self._rollout(policy, opponent_fn, carry=False)      # the first rollout always runs eagerly (it also warms cuBLAS up)
+            return buf
+        if not use_graph:
+            self._rollout(policy, opponent_fn, carry=True)
+            return buf
+        key = (id(policy), id(opponent_fn))
+        if self._graph is None or self._graph_key != key:
+            g = torch.cuda.CUDAGraph()
+            for gen in [self.gen] + self.extra_generators:
+                g.register_generator_state(gen)
+            torch.cuda.synchronize(b.device)
+            with torch.cuda.graph(g):
+                self._rollout(policy, opponent_fn, carry=True)
+            self._graph, self._graph_key = g, key
+        self._graph.replay()
+        return buf
+
+    def _rollout(self, policy, opponent_fn, carry):
+        b, buf = self.batch, self.buf
+        if carry:  # continue from where the previous rollout stopped
             buf.obs[0].copy_(buf.obs[-1])
             buf.action_masks[0].copy_(buf.action_masks[-1])
             buf.episode_starts[0].copy_(buf.episode_starts[-1])
@@ -118,4 +147,3 @@ class RolloutCollector(object):
                 buf.episode_starts[t + 1] = buf.dones[t].float()
             _, buf.values[buf.T] = policy(buf.obs[buf.T].float())
         buf.compute_returns_and_advantage()
-        return buf

@@ -80,3 +80,43 @@ def test_collector_invariants():
             adv[t] = last
         assert np.allclose(adv, buf.advantages[:, g].cpu().numpy(), atol=1e-5)
     assert int(env.stats()[6]) == 2 * T * G
+
+
+def test_collector_cuda_graph_rollout():
+    """collect(use_graph=True): the rollout replayed from one CUDA graph keeps every invariant of the eager rollout, advances
+    the environment by exactly T steps per call, follows in-place parameter updates, and never plays an illegal move."""
+    import torch
+    from hex_gym_env_b200 import HexBatch, VARIANT_B, AGENT_RANDOM
+    from hex_gym_env_b200.rollout import RolloutCollector
+    N, G, T = 6, 1024, 16
+    env = HexBatch(N, G, variant=VARIANT_B, device=0, seed=3, agent_mode=AGENT_RANDOM)
+    lin = torch.nn.Linear(N * N, N * N + 1).cuda()
+
+    def policy(obs):
+        y = lin(obs.flatten(1))
+        return y[:, :-1], y[:, -1]
+
+    col = RolloutCollector(env, T, seed=4)
+    last_obs = None
+    for it in range(5):
+        buf = col.collect(policy, use_graph=True)
+        torch.cuda.synchronize()
+        if last_obs is not None:
+            assert torch.equal(buf.obs[0], last_obs)                           # continues where the previous rollout stopped
+        last_obs = buf.obs[-1].clone()
+        taken = buf.action_masks[:-1].gather(2, buf.actions.long().unsqueeze(-1)).squeeze(-1)
+        assert bool((taken == 1).all()) and int(env.stats()[5]) == 0
+        assert bool(((buf.obs[:-1] == 0).flatten(2) == (buf.action_masks[:-1] == 1)).all())
+        assert bool((buf.episode_starts[1:] == buf.dones.float()).all())
+        assert int(env.stats()[6]) == (it + 1) * T * G
+        logits, values = policy(buf.obs[3].float())
+        assert torch.allclose(values, buf.values[3], atol=1e-5)                # the graph reads the CURRENT parameters
+        assert torch.allclose(buf.returns, buf.advantages + buf.values[:-1], atol=1e-6)
+        with torch.no_grad():
+            lin.weight.mul_(0.5).add_(0.01 * (it + 1))                         # an "optimizer step", in place
+    # different rollouts really were sampled (the generator advances across replays)
+    assert col._graph is not None
+    a1 = buf.actions.clone()
+    buf = col.collect(policy, use_graph=True)
+    torch.cuda.synchronize()
+    assert not torch.equal(a1, buf.actions)
