@@ -247,12 +247,22 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         // ---- row jobs, part 2: relabel sweeps (regions[regions == label] = new label, both plies of the step at once)
         if (!BATCHED) {
             // one row per pass, one word per lane: the faster form when the launch is several waves deep (HBM-bound regime)
-            uint32_t pending = __ballot_sync(FULL, (flg & (F_RELABEL | F_RESET)) == F_RELABEL);
+            const bool need = (flg & (F_RELABEL | F_RESET)) == F_RELABEL;
+            RelabelReq q = {0u, 0u, 0u, 0u, 0u};
+            if (need) prep_request(prmA, prmB, q);   // each game's own lane decodes its requests once
+            uint32_t pending = __ballot_sync(FULL, need);
+            const uint32_t extra = __ballot_sync(FULL, need && q.nx != 0u);
             while (pending) {
                 const int r = __ffs(pending) - 1;
                 pending &= pending - 1;
-                const uint32_t ra = __shfl_sync(FULL, prmA, r), rb = __shfl_sync(FULL, prmB, r);
-                relabel_row_lane<N>(lab32, r, ra, rb, lane, P.one);
+                const uint32_t so = __shfl_sync(FULL, q.so0, r), sn = __shfl_sync(FULL, q.sn0, r);
+                uint32_t xo = 0u, xn = 0u, nx = 0u;
+                if ((extra >> r) & 1u) {   // warp-uniform: more than one (old -> new) pair in this row
+                    xo = __shfl_sync(FULL, q.xo, r);
+                    xn = __shfl_sync(FULL, q.xn, r);
+                    nx = __shfl_sync(FULL, q.nx, r);
+                }
+                relabel_row_lane2<N>(lab32, row_desc<N>(r), lane, so, sn, xo, xn, (int)nx, P.one);
                 __syncwarp();
             }
         } else {

@@ -374,6 +374,78 @@ HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t pr
     }
 }
 
+// ---- relabel sweep, one row per warp pass (the form for deep launches). Everything that depends only on the row index
+// (first / last word, edge masks) comes from a per-board-size table in constant memory, and the step's relabel requests are
+// prepared once per game by its own lane (thread-per-game, all lanes in parallel) instead of being decoded by every lane in
+// every pass: the sweeps are the largest consumer of the ALU pipe, which bounds the step kernel in the steady state.
+struct RowDesc {
+    int w0, wl;            // first and last word of the row's label bytes
+    uint32_t first, last;  // row_mask() of those two words (all ones when rows are word aligned)
+};
+template <int N>
+HEXB_HD constexpr RowDesc make_row_desc(int r) {
+    constexpr int C = Geo<N>::C;
+    const int rs = r * C, re = rs + C;
+    return RowDesc{rs >> 2, (re - 1) >> 2, (C % 4 == 0) ? 0xffffffffu : 0xffffffffu << (8 * (rs & 3)),
+                   (C % 4 == 0) ? 0xffffffffu : 0xffffffffu >> (8 * (3 - ((re - 1) & 3)))};
+}
+#if defined(__CUDACC__) && !defined(HEXB_HOST_EMU)
+template <int N>
+struct RowTable {
+    RowDesc d[kWarp];
+    constexpr RowTable() : d{} {
+        for (int r = 0; r < kWarp; ++r) d[r] = make_row_desc<N>(r);
+    }
+};
+template <int N>
+__constant__ RowTable<N> c_rowtab{};
+#endif
+template <int N>
+HEXB_HD RowDesc row_desc(int r) {
+#if defined(__CUDA_ARCH__)
+    return c_rowtab<N>.d[r];
+#else
+    return make_row_desc<N>(r);
+#endif
+}
+
+// A game's relabel work of one step: pair 0 (old byte -> new byte) splatted over a word, the other pairs (a second group merged
+// by the same ply, the other ply's merges: the rarer cases) packed one per byte in xo / xn, nx = their number (0..3).
+struct RelabelReq {
+    uint32_t so0, sn0, xo, xn, nx;
+};
+HEXB_HD void canon_request(uint32_t prmA, uint32_t prmB, uint32_t &olds, uint32_t &news, uint32_t &n);
+HEXB_HD void prep_request(uint32_t prmA, uint32_t prmB, RelabelReq &q) {
+    uint32_t olds, news, n;
+    canon_request(prmA, prmB, olds, news, n);
+    q.so0 = splat(olds & 0xffu);
+    q.sn0 = splat(news & 0xffu);
+    q.xo = olds >> 8;
+    q.xn = news >> 8;
+    q.nx = n - 1u;
+}
+template <int N>
+HEXB_HD void relabel_row_lane2(uint32_t *lab32, const RowDesc &d, int lane, uint32_t so0, uint32_t sn0, uint32_t xo, uint32_t xn, int nx,
+                               uint32_t one) {
+#pragma unroll
+    for (int it = 0; it < RowSpan<N>::SWEEPS; ++it) {
+        const int w = d.w0 + lane + it * kWarp;
+        if (w > d.wl) break;
+        const uint32_t x = lab32[w];
+        // bytes of the neighbouring games in the row's first / last word are blanked before the compare (labels are never 0)
+        const uint32_t rm = ((it == 0 && lane == 0) ? d.first : 0xffffffffu) & (w == d.wl ? d.last : 0xffffffffu);
+        uint32_t mk = sign_fill(zero_flags((x & rm) ^ so0, one));
+        uint32_t x2 = (x & ~mk) | (sn0 & mk);
+#pragma unroll 1
+        for (int p = 0; p < nx; ++p) {   // warp-uniform trip count (0 for most rows)
+            const uint32_t so = splat_byte_dyn(xo, p), sn = splat_byte_dyn(xn, p);
+            mk = sign_fill(zero_flags((x2 & rm) ^ so, one));
+            x2 = (x2 & ~mk) | (sn & mk);
+        }
+        if (x2 != x) lab32[w] = x2;
+    }
+}
+
 // ---- batched relabel sweep: several rows per warp pass.
 // A row of label bytes spans at most RowSpan<N>::WORDS words; a group of LPR lanes takes one row, WPL words per lane, so one
 // pass of the warp relabels RPS = 32 / LPR rows (4 rows of an 11x11 board, 8 of a 7x7 one) instead of one, with WPL independent

@@ -73,9 +73,12 @@ static void run_tiles(Params P) {
             const bool batched = g_force_sweep < 0 ? (P.mode == MODE_STEP) : (g_force_sweep != 0);
             if (!batched) {
                 for (int r = 0; r < kWarp; ++r)
-                    if ((flg[r] & (F_RELABEL | F_RESET)) == F_RELABEL)
+                    if ((flg[r] & (F_RELABEL | F_RESET)) == F_RELABEL) {
+                        RelabelReq q;
+                        prep_request(prmA[r], prmB[r], q);
                         for (int lane = 0; lane < kWarp; ++lane)
-                            relabel_row_lane<N>(reinterpret_cast<uint32_t *>(chunk), r, prmA[r], prmB[r], lane, 1u);
+                            relabel_row_lane2<N>(reinterpret_cast<uint32_t *>(chunk), row_desc<N>(r), lane, q.so0, q.sn0, q.xo, q.xn, (int)q.nx, 1u);
+                    }
             } else {   // batched relabel sweeps, as the device kernel runs them: lane group sg takes the sg-th pending row of a parity class
                 using SW = Sweep<N>;
                 uint32_t olds[kWarp], news[kWarp], cnt[kWarp], pend_all = 0;
