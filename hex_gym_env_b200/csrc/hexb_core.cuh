@@ -300,17 +300,6 @@ HEXB_HD bool place_stone(uint8_t *L, Rec<N> &rec, int p, int cell, uint32_t &prm
 // ----------------------------------------------------------------------------------------------
 // byte-SIMD helpers for the cooperative passes (4 cells per 32-bit word)
 // ----------------------------------------------------------------------------------------------
-// 0x80 in every byte of x that is non-zero (exact, no cross-byte carries)
-HEXB_HD uint32_t nz_flags(uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
-// 0xff in every byte of x equal to the byte s
-HEXB_HD uint32_t eq_mask(uint32_t x, uint32_t s) {
-    const uint32_t z = (~nz_flags(x ^ splat(s))) & 0x80808080u;
-    return (z >> 7) * 0xffu;
-}
-HEXB_HD uint32_t relabel_word(uint32_t x, uint32_t prm) {
-    const uint32_t mk = eq_mask(x, prm & 0xffu) | eq_mask(x, (prm >> 8) & 0xffu);
-    return (x & ~mk) | (splat((prm >> 16) & 0xffu) & mk);
-}
 HEXB_HD uint32_t relabel_byte(uint32_t b, uint32_t prm) {
     return ((prm & P_NEED) && (b == (prm & 0xffu) || b == ((prm >> 8) & 0xffu))) ? ((prm >> 16) & 0xffu) : b;
 }
@@ -325,17 +314,6 @@ HEXB_HD uint32_t sign_fill(uint32_t f) {
     return d;
 #else
     return ((f >> 7) & 0x01010101u) * 0xffu;
-#endif
-}
-// byte k (0..2) of a relabel request replicated into all four bytes: one PRMT on the device
-template <int K>
-HEXB_HD uint32_t splat_byte(uint32_t prm) {
-#if defined(__CUDA_ARCH__)
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(prm), "r"(0u), "r"(0x1111u * K));
-    return d;
-#else
-    return ((prm >> (8 * K)) & 0xffu) * 0x01010101u;
 #endif
 }
 // byte p (0..3, run-time) of v replicated into all four bytes: one PRMT with a register selector on the device
@@ -370,10 +348,6 @@ HEXB_HD void encode_word_v(uint32_t x, uint32_t one, uint32_t &obs, uint32_t &ms
     } else {
         obs = msk * 2u + c1;                          // BLACK 0 (= R), WHITE 1 (= C), EMPTY 2
     }
-}
-HEXB_HD void encode_word(uint32_t x, int variant, uint32_t &obs, uint32_t &msk) {
-    if (variant == VARIANT_B) encode_word_v<VARIANT_B>(x, 1u, obs, msk);
-    else encode_word_v<VARIANT_A>(x, 1u, obs, msk);
 }
 // one byte, optionally seen from the opponent's side (sign swap; the caller transposes the cell index)
 HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &msk) {

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
             const int r = __ffs(pending) - 1;
             pending &= pending - 1;
             const uint32_t rf = __shfl_sync(FULL, flg, r);
-            row_job_lane<N>(chunk, r, 0u, 0u, rf & ~F_RELABEL, P, g0 + r + (long long)t * P.G, lane, [] { __syncwarp(); });
+            row_job_lane<N>(chunk, r, rf, P, g0 + r + (long long)t * P.G, lane, [] { __syncwarp(); });
             __syncwarp();
         }
 

@@ -7,9 +7,11 @@
 //                                      win), reward / done, episode accounting, auto-reset bookkeeping. Purely thread
 //                                      local: a ply only looks at the mover's OWN labels, so the opponent's ply does not
 //                                      depend on the agent's pending relabel and both requests are applied together.
-//   row jobs         warp-per-game     for every game that asked for one (ballot): the 32 lanes sweep that game's row
-//                                      of label words once - relabel (both plies' requests in one pass), or terminal
-//                                      observation + clear + opening stone when the game restarts.
+//   row jobs         warp-per-game     for every game that asked for one (ballot): the lanes sweep that game's row of label
+//                                      words - terminal observation + clear + opening stone when the game restarts (rare), or
+//                                      the relabel of merged groups (both plies' requests in one pass), in one of two forms:
+//                                      one row per pass (relabel_row_lane2, deep launches) or several rows per pass
+//                                      (relabel_rows_lane, launches of at most one wave and rollouts).
 //   encode_chunk     warp, elementwise label bytes -> obs + mask bytes, 16 bytes per lane per iteration, written straight
 //                                      to the [G,C] outputs. Encoding depends only on emptiness and the owner bit, never
 //                                      on the game index, so no per-word bookkeeping is needed.
@@ -336,44 +338,6 @@ struct RowSpan {
     static constexpr int SWEEPS = (WORDS + kWarp - 1) / kWarp;
 };
 
-// one relabel request applied to one word: every byte equal to o1 (or o2) becomes m; zf = 0x80 flags of the bytes to change
-HEXB_HD uint32_t relabel_flags(uint32_t x, uint32_t prm, uint32_t one) {
-    const uint32_t s1 = splat_byte<0>(prm), s2 = splat_byte<1>(prm);
-    uint32_t zf = zero_flags(x ^ s1, one);
-    if (s2 != s1) zf |= zero_flags(x ^ s2, one);  // a third adjacent group is rare; the branch is warp-uniform
-    return zf;
-}
-
-// regions[regions == label] = new_region_label (HexGame.py:141-142, HexSingleGame.py:152-153) for both plies of the step
-// in one sweep. The two requests touch disjoint byte values (the owner bit is part of the byte), so their order is free.
-// Usually only one of the two plies merges groups, and only two of them: the branches below are warp-uniform.
-template <int N>
-HEXB_HD void relabel_row_lane(uint32_t *lab32, int r, uint32_t prmA, uint32_t prmB, int lane, uint32_t one) {
-    constexpr int C = Geo<N>::C;
-    const int rs = r * C, re = rs + C;
-    const int w0 = rs >> 2, wl = (re - 1) >> 2;
-    // row_mask() of the row's first and last word, computed once per row (warp-uniform); every word in between is all ones
-    const uint32_t first = Chunk<N>::ALIGNED_ROWS ? 0xffffffffu : 0xffffffffu << (8 * (rs & 3));
-    const uint32_t last = Chunk<N>::ALIGNED_ROWS ? 0xffffffffu : 0xffffffffu >> (8 * (3 - ((re - 1) & 3)));
-#pragma unroll
-    for (int it = 0; it < RowSpan<N>::SWEEPS; ++it) {
-        const int w = w0 + lane + it * kWarp;
-        if (w > wl) break;
-        const uint32_t x = lab32[w];
-        const uint32_t rm = (w == w0 ? first : 0xffffffffu) & (w == wl ? last : 0xffffffffu);
-        uint32_t x2 = x;
-        if (prmA & P_NEED) {
-            const uint32_t mk = sign_fill(relabel_flags(x, prmA, one)) & rm;
-            x2 = (x2 & ~mk) | (splat_byte<2>(prmA) & mk);
-        }
-        if (prmB & P_NEED) {
-            const uint32_t mk = sign_fill(relabel_flags(x, prmB, one)) & rm;
-            x2 = (x2 & ~mk) | (splat_byte<2>(prmB) & mk);
-        }
-        if (x2 != x) lab32[w] = x2;
-    }
-}
-
 // ---- relabel sweep, one row per warp pass (the form for deep launches). Everything that depends only on the row index
 // (first / last word, edge masks) comes from a per-board-size table in constant memory, and the step's relabel requests are
 // prepared once per game by its own lane (thread-per-game, all lanes in parallel) instead of being decoded by every lane in
@@ -577,18 +541,16 @@ HEXB_HD void view_row_lane(const uint8_t *chunk, int r, const Params &P, long lo
     }
 }
 
-// one row job, one lane's share. Order: terminal observation (reads the finished board) -> clear (+ opening stone);
+// A finished game's row job, one lane's share: terminal observation (reads the finished board), then clear (+ opening stone);
 // the caller separates the two with a warp barrier (`sync`), because different lanes read and write the same words.
 template <int N, class SyncFn>
-HEXB_HD void row_job_lane(uint8_t *chunk, int r, uint32_t prmA, uint32_t prmB, uint32_t flg, const Params &P, long long g, int lane,
-                          SyncFn sync) {
+HEXB_HD void row_job_lane(uint8_t *chunk, int r, uint32_t flg, const Params &P, long long g, int lane, SyncFn sync) {
     uint32_t *lab32 = reinterpret_cast<uint32_t *>(chunk);
     if (flg & F_TERM) {
         term_row_lane<N>(chunk, r, flg, P, g, lane);
         sync();
     }
     if (flg & F_RESET) clear_row_lane<N>(lab32, r, flg, lane);
-    else if (flg & F_RELABEL) relabel_row_lane<N>(lab32, r, prmA, prmB, lane, P.one);
 }
 
 // ---------------------------------------------------------------------------------------------- encode (one lane's share)

@@ -68,7 +68,7 @@ static void run_tiles(Params P) {
                 if (flg[r] & F_TERM)
                     for (int lane = 0; lane < kWarp; ++lane) term_row_lane<N>(chunk, r, flg[r], P, g0 + r + so, lane);
                 for (int lane = 0; lane < kWarp; ++lane)
-                    row_job_lane<N>(chunk, r, 0u, 0u, flg[r] & ~(F_TERM | F_RELABEL), P, g0 + r + so, lane, [] {});
+                    row_job_lane<N>(chunk, r, flg[r] & ~F_TERM, P, g0 + r + so, lane, [] {});
             }
             const bool batched = g_force_sweep < 0 ? (P.mode == MODE_STEP) : (g_force_sweep != 0);
             if (!batched) {
