@@ -528,7 +528,10 @@ static long long wave_warps(int device) {
 template <int N>
 static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     constexpr int smem = SmemLayout<N>::BYTES;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {false};   // function attributes are per device
+    const int dev = e->cfg.device;
+    bool never = false;
+    bool &attr_done = (dev >= 0 && dev < 64) ? attr_done_dev[dev] : never;
     if (!attr_done) {
 #define HEXB_ATTR(K, B)                                                                                                        \
     CK(cudaFuncSetAttribute(hexb_step_kernel<N, K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
