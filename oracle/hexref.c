@@ -422,7 +422,7 @@ static void *step_range(void *arg) {
         int a;
         if (j->actions) a = j->actions[i];
         else a = was_done ? 0 : random_choice(&e->g, rng_random(&e->rng));
-        if (j->actions_out) j->actions_out[i] = a;
+        if (j->actions_out) j->actions_out[i] = was_done ? -1 : a; /* nothing is played in a finished game */
         const double *ou = j->opp_u ? &j->opp_u[2 * i] : NULL;
         float r;
         e->last_opp = -1;

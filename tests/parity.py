@@ -294,3 +294,61 @@ def golden_preset(make_raw, name):
         e = env.export()
         eq(e["regions"], z["regions_" + variant].astype(np.float64), "%s %s regions" % (name, variant))
         eq(e["region_counter"], z["counter_" + variant].astype(np.float64), "%s %s counter" % (name, variant))
+
+
+def api_fuzz(make, seed, T=50):
+    """Random walk over the step / reset API against the oracle: fused and external (sometimes illegal) agent moves, injected
+    opponent draws (opp_u), masked resets with and without injected opening draws (open_u), with and without auto-reset."""
+    rs = np.random.RandomState(1000 + seed)
+    N = int(rs.choice([3, 4, 5, 6, 7, 8, 9, 11, 13]))
+    G = int(rs.choice([1, 31, 32, 33, 97, 128, 200]))
+    variant_a = bool(rs.rand() < 0.35)
+    auto_reset = bool(rs.rand() < 0.6)
+    kw = dict(opponent_first=bool(rs.rand() < 0.5)) if variant_a else dict(agent_mode=int(rs.randint(0, 3)))
+    kind = hexref.KIND_ENV_A if variant_a else hexref.KIND_SELFPLAY_B
+    off = int(rs.randint(0, 1 << 40))
+    ref = hexref.RefBatch(kind, N, G, seed=seed, game_offset=off, **kw)
+    env = make(kind, N, G, seed=seed, game_offset=off, auto_reset=auto_reset, **kw)
+    what = "fuzz seed=%d N=%d G=%d %s auto_reset=%d %r" % (seed, N, G, "A" if variant_a else "B", auto_reset, kw)
+    ro, rm = ref.reset()
+    o, m = env.reset()
+    eq(o, ro, what + " reset obs")
+    eq(m, rm, what + " reset mask")
+    C = N * N
+    for t in range(T):
+        op = rs.choice(["fused", "actions", "actions_u", "reset_mask", "reset_mask_u"], p=[0.3, 0.3, 0.2, 0.1, 0.1])
+        w = "%s t=%d op=%s " % (what, t, op)
+        if op.startswith("reset"):
+            mask = (rs.rand(G) < 0.3).astype(np.uint8)
+            ou = rs.rand(G) if op.endswith("_u") else None
+            ro, rm = ref.reset(mask, ou)
+            o, m = env.reset(mask, ou)
+            eq(o, ro, w + "obs")
+            eq(m, rm, w + "mask")
+        else:
+            acts, u = None, None
+            if op != "fused":
+                cnt = rm.sum(1).astype(np.int64)
+                k = np.minimum((rs.rand(G) * cnt).astype(np.int64), np.maximum(cnt - 1, 0))
+                acts = np.argsort(-rm.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
+                bad = rs.rand(G) < 0.05
+                acts[bad] = rs.randint(-2, C + 2, size=int(bad.sum()))
+            if op == "actions_u":
+                u = rs.rand(G, 2)
+                u[rs.rand(G) < 0.1, 0] = 0.0
+                u[rs.rand(G) < 0.1, 0] = np.nextafter(1.0, 0.0)
+            r = ref.step(acts, u, auto_reset=auto_reset, want_term=True)
+            e = env.step(acts, u, want_term=True)
+            for key in ("reward", "done", "obs", "mask"):
+                eq(e[key], r[key], w + key)
+            if acts is None:
+                eq(e["actions"], r["actions"], w + "actions")
+            d = r["done"].astype(bool)
+            if auto_reset:
+                eq(e["term_obs"][d], r["term_obs"][d], w + "term_obs")
+            rm = r["mask"]
+        if t % 5 == 4:
+            re_, ee = ref.export(), env.export()
+            for key in STATE_KEYS:
+                eq(ee[key], re_[key], w + key)
+    eq(env.stats(), ref.stats(), what + " stats")

@@ -123,3 +123,8 @@ def test_both_relabel_sweep_forms(N, form):
         parity.snake_chain(make, N) if N in (7, 11) else None
     finally:
         emu.force_sweep(-1)
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_api_fuzz(seed):
+    parity.api_fuzz(make, seed)

@@ -361,3 +361,9 @@ def test_capture_steps_graph():
         o = b.step(acts)
         for k in ("obs", "mask", "reward", "done"):
             assert torch.equal(g1.outputs[k], o[k]), (k, t)
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_api_fuzz(make, seed):
+    """Random walks over the step / reset API (fused, external and illegal moves, injected draws, masked resets)."""
+    parity.api_fuzz(make, seed, T=60)
