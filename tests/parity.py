@@ -352,3 +352,34 @@ def api_fuzz(make, seed, T=50):
             for key in STATE_KEYS:
                 eq(ee[key], re_[key], w + key)
     eq(env.stats(), ref.stats(), what + " stats")
+
+
+def sampler_and_views(make, N, variant_a, seed=0):
+    """hexb_sample_actions and hexb_encode on their own, at positions reached by random play: the sampled action is the
+    int(u * n_empty)-th legal cell of the requested view in row-major order (BaseRandomPolicy.choose_action, SelfplayWrapper.py:17-22;
+    random_policy, minihex/__init__.py:8-12), for view 0 (the agent's) and view 1 (the side to move's); and encode(view 0) is
+    what the last step returned."""
+    G = 150
+    kind = hexref.KIND_ENV_A if variant_a else hexref.KIND_SELFPLAY_B
+    kw = {} if variant_a else dict(agent_mode=2)
+    env = make(kind, N, G, seed=seed, auto_reset=False, **kw)
+    rs = np.random.RandomState(seed)
+    env.reset()
+    for t in range(N * N // 2):
+        o = env.step()
+        obs0, mask0 = env.encode(0)
+        live = o["done"] == 0
+        eq(obs0[live], o["obs"][live], "encode(0) obs t=%d" % t)
+        eq(mask0[live], o["mask"][live], "encode(0) mask t=%d" % t)
+        for view in (0, 1):
+            obs, mask = env.encode(view)
+            empty = 2 if variant_a else 0
+            eq(mask.reshape(G, N, N) != 0, obs == empty, "view %d mask == empty cells t=%d" % (view, t))
+            u = rs.rand(G)
+            u[:5] = [0.0, np.nextafter(1.0, 0.0), 0.5, 1.0 / 3.0, 0.999999]
+            got = env.sample_actions(u, view)
+            cnt = mask.sum(1).astype(np.int64)
+            k = np.minimum((u * cnt).astype(np.int64), np.maximum(cnt - 1, 0))
+            want = np.argsort(-mask.astype(np.int8), axis=1, kind="stable")[np.arange(G), k]
+            ok = (cnt > 0) & live          # (a finished game has nobody to sample for)
+            eq(got[ok], want[ok].astype(np.int32), "sample_actions view %d t=%d" % (view, t))

@@ -128,3 +128,8 @@ def test_both_relabel_sweep_forms(N, form):
 @pytest.mark.parametrize("seed", range(80))
 def test_api_fuzz(seed):
     parity.api_fuzz(make, seed)
+
+
+@pytest.mark.parametrize("N,variant_a", [(3, False), (5, True), (6, False), (7, True), (11, False), (13, False)])
+def test_sampler_and_views(N, variant_a):
+    parity.sampler_and_views(make, N, variant_a, seed=N)

@@ -367,3 +367,8 @@ def test_capture_steps_graph():
 def test_api_fuzz(make, seed):
     """Random walks over the step / reset API (fused, external and illegal moves, injected draws, masked resets)."""
     parity.api_fuzz(make, seed, T=60)
+
+
+@pytest.mark.parametrize("N,variant_a", [(3, False), (5, True), (6, False), (7, True), (11, False), (13, False)])
+def test_sampler_and_views(make, N, variant_a):
+    parity.sampler_and_views(make, N, variant_a, seed=N)
