@@ -372,3 +372,24 @@ def test_api_fuzz(make, seed):
 @pytest.mark.parametrize("N,variant_a", [(3, False), (5, True), (6, False), (7, True), (11, False), (13, False)])
 def test_sampler_and_views(make, N, variant_a):
     parity.sampler_and_views(make, N, variant_a, seed=N)
+
+
+@pytest.mark.parametrize("N,G,T", [(11, 2048, 1500), (19, 256, 700), (5, 4096, 1200)])
+def test_long_run_vs_oracle(make, N, G, T):
+    """Dozens of episodes per game (auto-reset): reward / done / actions every step, the whole exported state every 100 steps
+    and the episode statistics at the end, bit-exact against the oracle."""
+    ref = hexref.RefBatch(hexref.KIND_SELFPLAY_B, N, G, seed=77, agent_mode=2)
+    env = make(hexref.KIND_SELFPLAY_B, N, G, seed=77, agent_mode=2)
+    ref.reset(); env.reset()
+    for t in range(T):
+        r, o = ref.step(), env.step()
+        for k in ("reward", "done", "actions"):
+            parity.eq(o[k], r[k], "long run N=%d t=%d %s" % (N, t, k))
+        if t % 100 == 99:
+            parity.eq(o["obs"], r["obs"], "long run obs t=%d" % t)
+            parity.eq(o["mask"], r["mask"], "long run mask t=%d" % t)
+            re_, e = ref.export(), env.export()
+            for k in parity.STATE_KEYS:
+                parity.eq(e[k], re_[k], "long run N=%d t=%d %s" % (N, t, k))
+    parity.eq(env.stats(), ref.stats(), "long run stats")
+    assert ref.stats()[0] > 3 * G
