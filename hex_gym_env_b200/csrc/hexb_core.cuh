@@ -145,6 +145,7 @@ HEXB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 HEXB_HD uint32_t splat(uint32_t b) { return b * 0x01010101u; }
+HEXB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Philox4x32-10 (Random123); pinned by the Random123 known-answer vectors in tests/test_philox.py.
 HEXB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1) {
@@ -261,21 +262,28 @@ HEXB_HD bool place_stone(uint8_t *L, Rec<N> &rec, int p, int cell, uint32_t &prm
     v[3] = rt ? L[cell + 1] : 0u;
     v[4] = (dn && lf) ? L[cell + N - 1] : 0u;
     v[5] = dn ? L[cell + N] : 0u;
+    // own labels as (label - 1) in 0..126, everything else (empty, the other colour, off the board) as a value >= 127:
+    // (b ^ tag) is the plain label for an own stone, has bit 7 set for a stone of the other colour and is 0 or 0x80 for an
+    // empty cell, so one XOR and one decrement sort all three cases (labels stay below 128)
+    constexpr uint32_t NONE = 127u;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) v[i] = (v[i] != 0u && (v[i] >> 7) == (uint32_t)p) ? (v[i] & 0x7fu) : 0xffu;
+    for (int i = 0; i < 6; ++i) v[i] = (v[i] ^ tag) - 1u;
     // implicit borders of the mover's padded plane
     const uint32_t far1 = p ? (rec.meta & M_FAR_C1) : (rec.meta & M_FAR_R1);
     const bool near_edge = p ? (x == 0) : (y == 0);
     const bool far_edge = p ? (x == N - 1) : (y == N - 1);
-    v[6] = near_edge ? 1u : 0xffu;
-    v[7] = far_edge ? (far1 ? 1u : 2u) : 0xffu;
-    uint32_t m = 0xffu, o1 = 0xffu, o2 = 0xffu;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m = v[i] < m ? v[i] : m;
+    v[6] = near_edge ? 0u : NONE;                     // label 1
+    v[7] = far_edge ? (far1 ? 0u : 1u) : NONE;        // label 1 once connected, else 2
+    uint32_t m = umin32(umin32(umin32(v[0], v[1]), umin32(v[2], v[3])), umin32(umin32(v[4], v[5]), umin32(v[6], v[7])));
+    uint32_t o1 = NONE, o2 = NONE;
 #pragma unroll
     for (int i = 0; i < 8; ++i) o1 = (v[i] > m && v[i] < o1) ? v[i] : o1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o2 = (v[i] > o1 && v[i] < o2) ? v[i] : o2;  // o1 == 0xff => nothing is > o1
+    for (int i = 0; i < 8; ++i) o2 = (v[i] > o1 && v[i] < o2) ? v[i] : o2;  // o1 == NONE => nothing valid is > o1
+    // back to labels; 0xff = none
+    m = m < NONE ? m + 1u : 0xffu;
+    o1 = o1 < NONE ? o1 + 1u : 0xffu;
+    o2 = o2 < NONE ? o2 + 1u : 0xffu;
     const uint32_t cshift = p ? M_CTR_C_SHIFT : M_CTR_R_SHIFT;
     uint32_t lab;
     prm = 0;

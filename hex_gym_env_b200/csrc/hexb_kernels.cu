@@ -250,19 +250,23 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
             const bool need = (flg & (F_RELABEL | F_RESET)) == F_RELABEL;
             RelabelReq q = {0u, 0u, 0u, 0u, 0u};
             if (need) prep_request(prmA, prmB, q);   // each game's own lane decodes its requests once
-            uint32_t pending = __ballot_sync(FULL, need);
-            const uint32_t extra = __ballot_sync(FULL, need && q.nx != 0u);
+            const uint32_t all_rows = __ballot_sync(FULL, need);
+            const uint32_t extra = __ballot_sync(FULL, need && q.nx != 0u);   // rows with more than one (old -> new) pair
+            uint32_t pending = all_rows & ~extra;                             // the common case first: one pair, no inner loop
             while (pending) {
                 const int r = __ffs(pending) - 1;
                 pending &= pending - 1;
                 const uint32_t so = __shfl_sync(FULL, q.so0, r), sn = __shfl_sync(FULL, q.sn0, r);
-                uint32_t xo = 0u, xn = 0u, nx = 0u;
-                if ((extra >> r) & 1u) {   // warp-uniform: more than one (old -> new) pair in this row
-                    xo = __shfl_sync(FULL, q.xo, r);
-                    xn = __shfl_sync(FULL, q.xn, r);
-                    nx = __shfl_sync(FULL, q.nx, r);
-                }
-                relabel_row_lane2<N>(lab32, row_desc<N>(r), lane, so, sn, xo, xn, (int)nx, P.one);
+                relabel_row_lane2<N, false>(lab32, row_desc<N>(r), lane, so, sn, 0u, 0u, 0, P.one);
+                __syncwarp();
+            }
+            pending = extra;
+            while (pending) {
+                const int r = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t so = __shfl_sync(FULL, q.so0, r), sn = __shfl_sync(FULL, q.sn0, r);
+                const uint32_t xo = __shfl_sync(FULL, q.xo, r), xn = __shfl_sync(FULL, q.xn, r), nx = __shfl_sync(FULL, q.nx, r);
+                relabel_row_lane2<N, true>(lab32, row_desc<N>(r), lane, so, sn, xo, xn, (int)nx, P.one);
                 __syncwarp();
             }
         } else {

@@ -388,7 +388,7 @@ HEXB_HD void prep_request(uint32_t prmA, uint32_t prmB, RelabelReq &q) {
     q.xn = news >> 8;
     q.nx = n - 1u;
 }
-template <int N>
+template <int N, bool EXTRA = true>
 HEXB_HD void relabel_row_lane2(uint32_t *lab32, const RowDesc &d, int lane, uint32_t so0, uint32_t sn0, uint32_t xo, uint32_t xn, int nx,
                                uint32_t one) {
 #pragma unroll
@@ -401,7 +401,7 @@ HEXB_HD void relabel_row_lane2(uint32_t *lab32, const RowDesc &d, int lane, uint
         uint32_t mk = sign_fill(zero_flags((x & rm) ^ so0, one));
         uint32_t x2 = (x & ~mk) | (sn0 & mk);
 #pragma unroll 1
-        for (int p = 0; p < nx; ++p) {   // warp-uniform trip count (0 for most rows)
+        for (int p = 0; EXTRA && p < nx; ++p) {   // warp-uniform trip count; rows with a single pair are swept with EXTRA = false
             const uint32_t so = splat_byte_dyn(xo, p), sn = splat_byte_dyn(xn, p);
             mk = sign_fill(zero_flags((x2 & rm) ^ so, one));
             x2 = (x2 & ~mk) | (sn & mk);

@@ -72,13 +72,17 @@ static void run_tiles(Params P) {
             }
             const bool batched = g_force_sweep < 0 ? (P.mode == MODE_STEP) : (g_force_sweep != 0);
             if (!batched) {
-                for (int r = 0; r < kWarp; ++r)
-                    if ((flg[r] & (F_RELABEL | F_RESET)) == F_RELABEL) {
-                        RelabelReq q;
-                        prep_request(prmA[r], prmB[r], q);
-                        for (int lane = 0; lane < kWarp; ++lane)
-                            relabel_row_lane2<N>(reinterpret_cast<uint32_t *>(chunk), row_desc<N>(r), lane, q.so0, q.sn0, q.xo, q.xn, (int)q.nx, 1u);
-                    }
+                for (int pass = 0; pass < 2; ++pass)   // like the device: rows with a single (old -> new) pair first, then the others
+                    for (int r = 0; r < kWarp; ++r)
+                        if ((flg[r] & (F_RELABEL | F_RESET)) == F_RELABEL) {
+                            RelabelReq q;
+                            prep_request(prmA[r], prmB[r], q);
+                            if ((q.nx != 0u) != (pass == 1)) continue;
+                            for (int lane = 0; lane < kWarp; ++lane) {
+                                if (pass == 0) relabel_row_lane2<N, false>(reinterpret_cast<uint32_t *>(chunk), row_desc<N>(r), lane, q.so0, q.sn0, 0u, 0u, 0, 1u);
+                                else relabel_row_lane2<N, true>(reinterpret_cast<uint32_t *>(chunk), row_desc<N>(r), lane, q.so0, q.sn0, q.xo, q.xn, (int)q.nx, 1u);
+                            }
+                        }
             } else {   // batched relabel sweeps, as the device kernel runs them: lane group sg takes the sg-th pending row of a parity class
                 using SW = Sweep<N>;
                 uint32_t olds[kWarp], news[kWarp], cnt[kWarp], pend_all = 0;
