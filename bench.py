@@ -282,13 +282,14 @@ def run_gpu(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "hexb_step_kernel<%d> MODE_STEP" % N, "kernel_ms": kern_ms,
+                "kernel": "hexb_step_kernel<%d, KIND_STEP, %s>" % (N, "several-rows sweep" if (G + 127) // 128 * 4 <= 32 * torch.cuda.get_device_properties(dev).multi_processor_count else "one-row sweep"), "kernel_ms": kern_ms,
                 "bytes_per_env_step_contract": B, "bytes_per_env_step_moved": moved_bytes(N),
                 "achieved_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9,
                 "frac_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9 / peak,
                 "note": "achieved/frac use SURVEY 8(d)'s algorithmic bytes (state 290 B per game each way); this implementation "
-                        "packs the state into 161 B, so the bytes really moved (achieved_moved/frac_moved, cross-checked by "
-                        "traffic = ncu dram bytes per launch) are lower and frac can exceed 1",
+                        "packs the state into 161 B, so the bytes the kernel really requests (achieved_moved/frac_moved) are lower "
+                        "and frac can exceed 1; 20 MiB of the state are kept L2-resident across steps, so HBM sees slightly less "
+                        "than that again (traffic = ncu dram bytes per launch, measured with L2 flushed before the launch)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
     del env
 
