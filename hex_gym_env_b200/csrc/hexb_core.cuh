@@ -112,6 +112,7 @@ struct Params {
     uint8_t *to_move;     // [G] MODE_HALF / MODE_RESET out: 0 agent to move, 1 opponent to move, 2 finished
     int32_t *info_opp;    // [G] nullable, MODE_STEP out: the opponent's move of this step (info["last_move_opponent"]), -1 = none
     int8_t *info_winner;  // [G] nullable, MODE_STEP out: env.winner after the step: -1 None, 0 BLACK, 1 WHITE, 3 illegal move
+    int out_hint;           // 1 = the obs / mask stores also carry an explicit L2 evict_first policy (off; HEXB_L2_OUT_HINT=1 turns it on)
     long long keep_chunks;  // chunks [0, keep_chunks) are kept in L2 between steps (evict_last), the others streamed (evict_first)
     uint32_t one;  // always 1, but opaque to the compiler: a * one + b is issued as IMAD on the FMA pipe (see fma_add)
     // borrowed I/O (device pointers, any may be null unless noted)
