@@ -37,11 +37,11 @@ def contract_bytes(N):
 
 
 def moved_bytes(N, sampled=True):
-    """Bytes this implementation really moves per env-step per game: packed state in + out (C label bytes + (2W+2) u32
+    """Bytes this implementation really moves per env-step per game: packed state in + out (C label bytes + (W+2) u32
     record words), obs + mask + reward + done out (+ actions in when the agent is external)."""
     C = N * N
     W = (C + 31) // 32
-    S = C + 4 * (2 * W + 2)
+    S = C + 4 * (W + 2)
     return 2 * S + 2 * C + 5 + (0 if sampled else 4)
 
 
@@ -287,7 +287,7 @@ def run_gpu(args):
                 "achieved_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9,
                 "frac_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9 / peak,
                 "note": "achieved/frac use SURVEY 8(d)'s algorithmic bytes (state 290 B per game each way); this implementation "
-                        "packs the state into 161 B, so the bytes the kernel really requests (achieved_moved/frac_moved) are lower "
+                        "packs the state into 145 B, so the bytes the kernel really requests (achieved_moved/frac_moved) are lower "
                         "and frac can exceed 1; 20 MiB of the state are kept L2-resident across steps, so HBM sees slightly less "
                         "than that again (traffic = ncu dram bytes per launch, measured with L2 flushed before the launch)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}

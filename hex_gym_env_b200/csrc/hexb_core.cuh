@@ -14,9 +14,10 @@
 //   * "stored" = true coordinates when the agent is BLACK, the transpose when the agent is WHITE
 //     (the hex neighbourhood is symmetric under transposition), so the agent's observation, mask and
 //     action index are the stored row-major order and never need a transpose on the hot path.
-//   * a small per-game record (u32 words): occupancy bitboards in row-major and column-major
-//     order (the random opponent picks the k-th empty cell of ITS perspective = stored column-major
-//     order, SelfplayWrapper.py:17-22, minihex/__init__.py:8-12), counters, flags, RNG draw index.
+//   * a small per-game record (u32 words): the occupancy bitboard in stored row-major order,
+//     counters, flags, RNG draw index. (The random opponent picks the k-th empty cell of ITS
+//     perspective = stored column-major order, SelfplayWrapper.py:17-22, minihex/__init__.py:8-12:
+//     select_kth_zero_colmajor finds it from the same bitboard.)
 //   * games are stored chunk-major, 32 games (one warp) per contiguous block: their label bytes
 //     [32][C], then their record words [word][lane] (see chunk_state_bytes below).
 //
@@ -75,7 +76,7 @@ template <int N>
 struct Geo {
     static constexpr int C = N * N;
     static constexpr int W = (C + 31) / 32;      // bitboard words
-    static constexpr int R = 2 * W + 2;          // record words: occ_rm[W], occ_cm[W], meta, draws
+    static constexpr int R = W + 2;              // record words: occ_rm[W], meta, draws
     static constexpr int CHUNK_LAB = 32 * C;               // label bytes of a chunk (multiple of 16)
     static constexpr int CHUNK_STATE = 32 * (C + 4 * R);   // whole chunk: labels + records (multiple of 16)
     static constexpr uint32_t LAST_MASK = (C % 32) ? ((1u << (C % 32)) - 1u) : 0xffffffffu;
@@ -83,15 +84,14 @@ struct Geo {
 
 template <int N>
 struct Rec {
-    uint32_t occ_rm[Geo<N>::W];
-    uint32_t occ_cm[Geo<N>::W];
+    uint32_t occ_rm[Geo<N>::W];   // occupancy bitboard, stored row-major order (bit y*N + x)
     uint32_t meta, draws;  // (plies of the running episode = stones on the board = popcount of the occupancy)
 };
 
 // Packed state, chunk-major: games are grouped in chunks of 32 (one warp); chunk k occupies CHUNK_STATE contiguous,
 // 16-byte aligned bytes = the 32 games' label bytes [32][C] followed by their record words [R][32] (word-major so that lane
 // i reads word w at [w*32 + i] without bank conflicts). One bulk copy moves a whole chunk.
-HEXB_HD long long chunk_state_bytes(int C) { return 32ll * (C + 4 * (2 * ((C + 31) / 32) + 2)); }
+HEXB_HD long long chunk_state_bytes(int C) { return 32ll * (C + 4 * ((C + 31) / 32 + 2)); }
 HEXB_HD long long labels_offset(long long g, int C) { return (g >> 5) * chunk_state_bytes(C) + (g & 31) * C; }
 HEXB_HD long long rec_offset(long long g, int C) { return (g >> 5) * chunk_state_bytes(C) + 32ll * C + 4 * (g & 31); }  // word w: + 128*w
 constexpr int kRecStride = 32;  // words between consecutive record words of one game
@@ -183,17 +183,16 @@ HEXB_HD int choice_of(double u, int n) {
     return k < 0 ? 0 : (k >= n ? n - 1 : k);
 }
 
-// index of the k-th (0-based) ZERO bit among the first C bits of a W-word bitboard
+// index of the k-th (0-based) SET bit of a W-word bit set (k < number of set bits)
 template <int N>
-HEXB_HD int select_kth_zero(const uint32_t (&occ)[Geo<N>::W], int k) {
+HEXB_HD int select_kth_set(const uint32_t (&bits)[Geo<N>::W], int k) {
     constexpr int W = Geo<N>::W;
     uint32_t z = 0;
     int base = 0;
     bool found = false;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-        uint32_t zw = ~occ[w];
-        if (w == W - 1) zw &= Geo<N>::LAST_MASK;
+        const uint32_t zw = bits[w];
         const int c = popc32(zw);
         if (!found) {
             if (k < c) { z = zw; base = 32 * w; found = true; }
@@ -208,6 +207,75 @@ HEXB_HD int select_kth_zero(const uint32_t (&occ)[Geo<N>::W], int k) {
     c = popc32(z & 0x3u);    if (k >= c) { k -= c; pos += 2;  z >>= 2; }
     c = (int)(z & 1u);       if (k >= c) { pos += 1; }
     return base + pos;
+}
+
+// the empty cells of a bitboard as a bit set (bits >= C cleared)
+template <int N>
+HEXB_HD void empty_bits(const uint32_t (&occ)[Geo<N>::W], uint32_t (&e)[Geo<N>::W]) {
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) e[w] = ~occ[w];
+    e[Geo<N>::W - 1] &= Geo<N>::LAST_MASK;
+}
+
+// index of the k-th (0-based) ZERO bit among the first C bits of a W-word bitboard: the k-th empty cell in row-major order
+template <int N>
+HEXB_HD int select_kth_zero(const uint32_t (&occ)[Geo<N>::W], int k) {
+    uint32_t e[Geo<N>::W];
+    empty_bits<N>(occ, e);
+    return select_kth_set<N>(e, k);
+}
+
+// ---- the k-th empty cell in COLUMN-major order, from the row-major bitboard.
+// The random opponent picks the k-th empty cell of ITS view (SelfplayWrapper.py:17-22, minihex/__init__.py:8-12), which is the
+// stored board transposed, i.e. stored column-major order. Instead of carrying a second, transposed bitboard in the state
+// (W words read and written per game and step), the column is found by bisection on "empty cells in columns < X" and the row
+// by a k-th-set-bit selection inside that column. The masks are periodic with period N bits, so they are made by ONE multiply
+// per word: an N-bit field times the constant with a one at every multiple of N (the copies cannot overlap, so no carries).
+template <int N>
+HEXB_HD constexpr uint32_t rep_word(int w) {   // word w of the C-bit constant with bits 0, N, 2N, ..., (N-1)N set
+    uint32_t v = 0;
+    for (int y = 0; y < N; ++y) {
+        const int b = y * N;
+        if ((b >> 5) == w) v |= 1u << (b & 31);
+    }
+    return v;
+}
+template <int N>
+HEXB_HD void spread_field(uint32_t field, uint32_t (&out)[Geo<N>::W]) {   // field (< 2^N) copied to bit offsets 0, N, 2N, ...
+    uint32_t carry = 0;
+#pragma unroll
+    for (int w = 0; w < Geo<N>::W; ++w) {
+        constexpr uint32_t REP[] = {rep_word<N>(0), rep_word<N>(1), rep_word<N>(2), rep_word<N>(3), rep_word<N>(4), rep_word<N>(5),
+                                    rep_word<N>(6), rep_word<N>(7), rep_word<N>(8), rep_word<N>(9), rep_word<N>(10), rep_word<N>(11)};
+        const unsigned long long p = (unsigned long long)field * REP[w];
+        out[w] = (uint32_t)p | carry;
+        carry = (uint32_t)(p >> 32);
+    }
+}
+constexpr int ceil_log2(int n) { return n <= 1 ? 0 : 1 + ceil_log2((n + 1) / 2); }
+// returns the stored (row-major) cell of the k-th empty cell in column-major order and its column in `col`
+template <int N>
+HEXB_HD int select_kth_zero_colmajor(const uint32_t (&occ)[Geo<N>::W], int k, int &col) {
+    constexpr int W = Geo<N>::W;
+    uint32_t e[W], m[W];
+    empty_bits<N>(occ, e);
+    // invariant: empties in columns < lo  <=  k  <  empties in columns < hi
+    int lo = 0, hi = N, below = 0;
+#pragma unroll
+    for (int it = 0; it < ceil_log2(N); ++it) {
+        const int mid = (lo + hi + 1) >> 1;   // lo < mid <= hi while hi - lo > 1; mid == hi when hi - lo == 1 (then c > k: no change)
+        spread_field<N>((1u << mid) - 1u, m);
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) c += popc32(e[w] & m[w]);
+        if (c <= k) { lo = mid; below = c; }
+        else hi = mid;
+    }
+    col = lo;
+    spread_field<N>(1u << lo, m);
+#pragma unroll
+    for (int w = 0; w < W; ++w) m[w] &= e[w];
+    return select_kth_set<N>(m, k - below);
 }
 
 template <int N>
@@ -303,7 +371,6 @@ HEXB_HD bool place_stone(uint8_t *L, Rec<N> &rec, int p, int cell, uint32_t &prm
     }
     L[cell] = (uint8_t)(lab | tag);
     set_bit<N>(rec.occ_rm, cell);
-    set_bit<N>(rec.occ_cm, x * N + y);
     return (rec.meta & (p ? M_FAR_C1 : M_FAR_R1)) != 0u;
 }
 
@@ -380,7 +447,7 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
     uint32_t meta = rec.meta & (M_TRANSPOSED | M_COLOUR_SET);
     meta |= M_LIVE | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
 #pragma unroll
-    for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
+    for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = 0u;
     bool opp_opens;
     if (P.raw) {
         opp_opens = false;
@@ -419,7 +486,6 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
         else if (x == N - 1) lab = 2u;
         else { lab = 3u; meta += 1u << M_CTR_C_SHIFT; }
         set_bit<N>(rec.occ_rm, y * N + x);
-        set_bit<N>(rec.occ_cm, k);
         flg |= F_OPEN | ((lab | 0x80u) << 8) | ((uint32_t)(y * N + x) << 16);
     }
     rec.meta = meta;  // R (the agent) to move unless a caller-driven opponent opens

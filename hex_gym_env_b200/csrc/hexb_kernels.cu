@@ -92,7 +92,7 @@ constexpr int kCtaThreads = kWarpsPerCta * kWarp;
 // resident CTAs per SM the register allocation should allow: 12 (48 warps) while the record is small, else whatever the
 // shared-memory footprint of the four chunks permits anyway
 constexpr int min_ctas(int n) {
-    const int smem = kWarpsPerCta * 32 * (n * n + 4 * (2 * ((n * n + 31) / 32) + 2)) + 64;
+    const int smem = kWarpsPerCta * 32 * (n * n + 4 * ((n * n + 31) / 32 + 2)) + 64;
     const int by_smem = 220 * 1024 / smem;
     const int want = 10 * 4 / kWarpsPerCta;   // 40 warps per SM (48 registers): measured equal to 48 warps, and no spills
     const int cap = 8 * 4 / kWarpsPerCta;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     double u_agent = 0.0, u_opp = 0.0;
     if (STEP_ONLY && g < P.G) {
         const uint32_t *grec = reinterpret_cast<const uint32_t *>(gl + Geo<N>::CHUNK_LAB) + lane;
-        pre_draws(P, grec[(2 * Geo<N>::W) * kRecStride], grec[(2 * Geo<N>::W + 1) * kRecStride],
+        pre_draws(P, grec[Geo<N>::W * kRecStride], grec[(Geo<N>::W + 1) * kRecStride],
                   (unsigned long long)(P.game_offset + g), u_agent, u_opp);
     }
     __syncwarp();  // the barrier's initialisation is visible to the other lanes

@@ -48,20 +48,16 @@ HEXB_HD void load_rec(const uint32_t *b, Rec<N> &r) {
     constexpr int W = Geo<N>::W;
 #pragma unroll
     for (int w = 0; w < W; ++w) r.occ_rm[w] = b[w * kRecStride];
-#pragma unroll
-    for (int w = 0; w < W; ++w) r.occ_cm[w] = b[(W + w) * kRecStride];
-    r.meta = b[(2 * W) * kRecStride];
-    r.draws = b[(2 * W + 1) * kRecStride];
+    r.meta = b[W * kRecStride];
+    r.draws = b[(W + 1) * kRecStride];
 }
 template <int N>
 HEXB_HD void store_rec(uint32_t *b, const Rec<N> &r) {
     constexpr int W = Geo<N>::W;
 #pragma unroll
     for (int w = 0; w < W; ++w) b[w * kRecStride] = r.occ_rm[w];
-#pragma unroll
-    for (int w = 0; w < W; ++w) b[(W + w) * kRecStride] = r.occ_cm[w];
-    b[(2 * W) * kRecStride] = r.meta;
-    b[(2 * W + 1) * kRecStride] = r.draws;
+    b[W * kRecStride] = r.meta;
+    b[(W + 1) * kRecStride] = r.draws;
 }
 
 // reward HexEnv.step would hand out again for an already finished variant-A game (HexGame.py:250,267-279)
@@ -146,11 +142,12 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &
                 rec.draws += (P.variant == VARIANT_B) ? 2u : 1u;  // variant B: rv = random.uniform(0,1), unused (:159), then the choice
                 u = u_opp;
             }
-            const int n = count_empty<N>(rec.occ_cm);
-            const int i = select_kth_zero<N>(rec.occ_cm, choice_of(u, n));  // k-th empty cell of the opponent's view = stored column-major
-            const int x = i / N, y = i - x * N;
-            const bool won = place_stone<N>(L, rec, 1, y * N + x, prmB);
-            opp_move = P.variant == VARIANT_A ? y * N + x : i;  // A: transposed back to the true cell (HexGame.py:341-346); B: its own view
+            const int n = count_empty<N>(rec.occ_rm);
+            int x;
+            const int cell = select_kth_zero_colmajor<N>(rec.occ_rm, choice_of(u, n), x);  // k-th empty cell of the opponent's view
+            const bool won = place_stone<N>(L, rec, 1, cell, prmB);
+            // A: the env transposes the move back to the true cell (HexGame.py:341-346); B: the index in the opponent's own view
+            if (P.info_opp) opp_move = P.variant == VARIANT_A ? cell : x * N + (cell - x) / N;
             loc.st[7]++;
             rec.meta ^= M_TOMOVE;
             if (won) {
@@ -224,7 +221,9 @@ HEXB_HD void game_half(uint8_t *L, const Params &P, long long g, Rec<N> &rec, Lo
         if (P.actions) a = P.actions[g];
         else {  // the built-in random opponent (BaseRandomPolicy / random_policy): k-th empty cell of ITS view
             const double u = draw01(P.seed, gid, rec.draws++);
-            a = select_kth_zero<N>(rec.occ_cm, choice_of(u, count_empty<N>(rec.occ_cm)));
+            int x;
+            const int cell = select_kth_zero_colmajor<N>(rec.occ_rm, choice_of(u, count_empty<N>(rec.occ_rm)), x);
+            a = x * N + (cell - x) / N;   // the same cell as an index of the opponent's own view (its transpose)
         }
         loc.action = a;
         if (side == 0) loc.st[6] = 1;                                   // an env step starts with the agent's ply

@@ -17,7 +17,7 @@ HEXB_HD const uint32_t *view_rec(const View &V, long long g) {
 HEXB_HD const uint8_t *view_labels(const View &V, long long g) { return V.state + labels_offset(g, V.N * V.N); }
 HEXB_HD uint32_t view_meta(const View &V, long long g) {
     const int W = (V.N * V.N + 31) / 32;
-    return view_rec(V, g)[(2 * W) * kRecStride];
+    return view_rec(V, g)[W * kRecStride];
 }
 
 // K5: obs + mask of the current state. view 0: the agent's (stored orientation, or the opponent's for an episode the
@@ -47,13 +47,18 @@ template <int N>
 HEXB_HD void sample_at(const View &V, int view, long long g, const double *u, int32_t *out) {
     constexpr int W = Geo<N>::W;
     const uint32_t *rw = view_rec(V, g);
-    const uint32_t meta = rw[(2 * W) * kRecStride];
+    const uint32_t meta = rw[W * kRecStride];
     const bool opp = (V.variant == VARIANT_B ? (view == 1 || V.raw) : (view == 1 && !V.raw)) && (meta & M_TOMOVE);
     uint32_t occ[W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) occ[w] = rw[((opp ? W : 0) + w) * kRecStride];
+    for (int w = 0; w < W; ++w) occ[w] = rw[w * kRecStride];
     const int n = count_empty<N>(occ);
-    out[g] = n > 0 ? select_kth_zero<N>(occ, choice_of(u[g], n)) : -1;
+    if (n <= 0) { out[g] = -1; return; }
+    const int k = choice_of(u[g], n);
+    if (!opp) { out[g] = select_kth_zero<N>(occ, k); return; }
+    int x;
+    const int cell = select_kth_zero_colmajor<N>(occ, k, x);   // the opponent's view is the transpose of the stored board
+    out[g] = x * N + (cell - x) / N;
 }
 
 // K6: reference-layout dump. Element i = (game, plane, padded cell); board / scalars ride on the first elements.
@@ -105,7 +110,7 @@ HEXB_HD void export_at(const View &V, long long i, double *board, double *region
             winner[g] = (int8_t)(w == 0u ? -1 : (int)((w - 1u) ^ (uint32_t)tr));
         }
         if (agent) agent[g] = (int8_t)tr;
-        if (draws) draws[g] = view_rec(V, g)[(2 * W + 1) * kRecStride];
+        if (draws) draws[g] = view_rec(V, g)[(W + 1) * kRecStride];
     }
 }
 
@@ -126,7 +131,7 @@ HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true,
     const int tr = (keep & M_TRANSPOSED) ? 1 : 0;
     if (!env_game) rec.draws = 0;
 #pragma unroll
-    for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = rec.occ_cm[w] = 0u;
+    for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = 0u;
     rec.meta = keep | M_LIVE | (3u << M_CTR_R_SHIFT) | (3u << M_CTR_C_SHIFT);
     for (int c = 0; c < C; ++c) L[c] = 0;
     for (int c = 0; c < C; ++c) {

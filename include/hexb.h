@@ -69,7 +69,7 @@ const char *hexb_strerror(int32_t code);
 int32_t hexb_last_cuda_error(void);
 
 /* Bytes of packed device state for `cfg` (0 on a bad config). Layout (chunk-major): per chunk of 32 games the label bytes
- * u8[32][N*N] followed by the record words u32[R][32] (occupancy bitboards, counters, flags, draw index); then striped
+ * u8[32][N*N] followed by the record words u32[R][32] (occupancy bitboard, counters, flags, draw index); then striped
  * int64[128][8] statistics. */
 size_t hexb_state_bytes(const hexb_config *cfg);
 

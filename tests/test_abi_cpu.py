@@ -43,7 +43,7 @@ def test_state_bytes_and_errors(L):
     c = cfg()
     n = L.hexb_state_bytes(ctypes.byref(c))
     chunks = (1000 + 127) // 128 * 4                       # games padded to 128, 32 per chunk
-    assert n >= chunks * 32 * (121 + 4 * 10) and n % 256 == 0
+    assert n >= chunks * 32 * (121 + 4 * 6) and n % 256 == 0   # labels + record words (W + 2 = 6 at 11x11)
     assert L.hexb_host_workspace_bytes(ctypes.byref(c)) >= 1000 * (4 + 121 + 121 + 4 + 1)
     for bad in (cfg(board_size=2), cfg(board_size=20), cfg(variant=2), cfg(num_games=0), cfg(agent_mode=3),
                 cfg(variant=0, agent_mode=1), cfg(game_offset=-1), cfg(raw=1, manual_opponent=1), cfg(pool_size=-1)):

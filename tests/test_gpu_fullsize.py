@@ -148,7 +148,7 @@ def test_sharding_invariance_full_size():
     # the packed state is chunk-major (32 games per block), so shard r's game blocks are a contiguous slice of the whole's
     ws = whole.state_dict()["state"]
     C, W = N * N, (N * N + 31) // 32
-    per_shard = S // 32 * 32 * (C + 4 * (2 * W + 2))                             # labels + records per chunk
+    per_shard = S // 32 * 32 * (C + 4 * (W + 2))                                 # labels + records per chunk
     for r, sh in enumerate(shards):
         assert torch.equal(sh.state_dict()["state"][:per_shard], ws[r * per_shard:(r + 1) * per_shard]), r
     assert properties.checksum(torch.cat([sh._out["obs"] for sh in shards])) == properties.checksum(whole._out["obs"])

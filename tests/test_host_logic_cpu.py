@@ -26,9 +26,9 @@ def test_random_start_boards_invariants():
 def test_contract_and_moved_bytes():
     # SURVEY.md section 8(d) table
     assert [bench.contract_bytes(N) for N in (5, 6, 7, 11, 19)] == [207, 289, 367, 831, 2399]
-    # this implementation: 2 * (C + 4 * (2W + 2)) + 2C + 5
-    assert bench.moved_bytes(11) == 2 * (121 + 40) + 242 + 5 == 569
-    assert bench.moved_bytes(11, sampled=False) == 573
+    # this implementation: 2 * (C + 4 * (W + 2)) + 2C + 5
+    assert bench.moved_bytes(11) == 2 * (121 + 24) + 242 + 5 == 537
+    assert bench.moved_bytes(11, sampled=False) == 541
 
 
 def test_scripted_choice_is_legal_and_deterministic():
