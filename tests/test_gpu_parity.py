@@ -369,7 +369,8 @@ def test_api_fuzz(make, seed):
     parity.api_fuzz(make, seed, T=60)
 
 
-@pytest.mark.parametrize("N,variant_a", [(3, False), (5, True), (6, False), (7, True), (11, False), (13, False)])
+@pytest.mark.parametrize("N,variant_a", [(3, False), (4, True), (5, True), (6, False), (7, True), (8, False), (9, True), (10, False), (11, False),
+                                         (12, True), (13, False), (14, False), (15, True), (16, False), (17, False), (18, True), (19, False)])
 def test_sampler_and_views(make, N, variant_a):
     parity.sampler_and_views(make, N, variant_a, seed=N)
 
