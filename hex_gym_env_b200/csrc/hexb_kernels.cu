@@ -591,7 +591,8 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
 #define HEXB_ATTR(K, B)                                                                                                        \
     CK(cudaFuncSetAttribute(hexb_step_kernel<N, K, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
     CK(cudaFuncSetAttribute(hexb_step_kernel<N, K, B>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        HEXB_ATTR(KIND_STEP, false) HEXB_ATTR(KIND_STEP, true) HEXB_ATTR(KIND_ROLLOUT, true) HEXB_ATTR(KIND_OTHER, false)
+        HEXB_ATTR(KIND_STEP, false) HEXB_ATTR(KIND_STEP, true) HEXB_ATTR(KIND_ROLLOUT, false) HEXB_ATTR(KIND_ROLLOUT, true)
+        HEXB_ATTR(KIND_OTHER, false)
 #undef HEXB_ATTR
         attr_done = true;
     }
@@ -603,7 +604,8 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
         if (small) hexb_step_kernel<N, KIND_STEP, true><<<grid, kCtaThreads, smem, s>>>(P);
         else hexb_step_kernel<N, KIND_STEP, false><<<grid, kCtaThreads, smem, s>>>(P);
     } else if (P.mode == MODE_STEP) {
-        hexb_step_kernel<N, KIND_ROLLOUT, true><<<grid, kCtaThreads, smem, s>>>(P);
+        if (small) hexb_step_kernel<N, KIND_ROLLOUT, true><<<grid, kCtaThreads, smem, s>>>(P);
+        else hexb_step_kernel<N, KIND_ROLLOUT, false><<<grid, kCtaThreads, smem, s>>>(P);
     } else {
         hexb_step_kernel<N, KIND_OTHER, false><<<grid, kCtaThreads, smem, s>>>(P);
     }
