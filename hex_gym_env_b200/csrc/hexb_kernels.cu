@@ -201,6 +201,14 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     const long long g = g0 + lane;          // this lane's game
     uint8_t *gl = P.state + wglobal * SL::CHUNK;
 
+    // ---- programmatic dependent launch: the step kernels are launched with the programmatic-stream-serialization attribute, so
+    //      a launch that follows another kernel on the stream may be set up while that kernel drains; it waits HERE, before its
+    //      first global access, until the previous grid has completed and its writes are visible (a no-op without the attribute).
+    //      This hides ~2 us of launch gap per step for steps issued one by one (1 Mi games 11x11: 93.6 -> 91.4 us; a CUDA graph
+    //      has no such gap). Letting the next grid in EARLY (griddepcontrol.launch_dependents at the top) was measured and
+    //      rejected: its waiting CTAs take slots from this grid (65,536 games of 7x7: 9.1 -> 12.7 us per step).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // ---- chunk in (asynchronous: labels and records in ONE bulk copy); meanwhile the two draws of the (first) step, which
     //      only need the game's meta and stream-position words (two plain loads of lines the bulk copy is fetching anyway)
     const bool use_hint = P.keep_chunks > 0;               // warp-uniform (kernel-uniform)
@@ -597,17 +605,29 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
         attr_done = true;
     }
     const unsigned grid = (unsigned)(P.Gpad / kCtaThreads);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kCtaThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = s;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !(getenv("HEXB_PDL") && atoi(getenv("HEXB_PDL")) == 0);   // HEXB_PDL=0: plain stream-ordered launches
+    lc.attrs = la;
+    lc.numAttrs = pdl ? 1 : 0;
     // at most about one wave of warps: the step time is one warp's latency -> the batched relabel sweep; deeper launches are
     // HBM-bound and run the one-row-per-pass sweep (measured on 1 Mi games 11x11: 99.5 us vs 105.0 us; on 4,096 games 6x6: 6.7 vs 6.0 us)
     const bool small = P.Gpad / kWarp <= wave_warps(e->cfg.device);
+    const Params &Q = P;
     if (P.mode == MODE_STEP && P.steps == 1) {
-        if (small) hexb_step_kernel<N, KIND_STEP, true><<<grid, kCtaThreads, smem, s>>>(P);
-        else hexb_step_kernel<N, KIND_STEP, false><<<grid, kCtaThreads, smem, s>>>(P);
+        if (small) CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_STEP, true>, Q));
+        else CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_STEP, false>, Q));
     } else if (P.mode == MODE_STEP) {
-        if (small) hexb_step_kernel<N, KIND_ROLLOUT, true><<<grid, kCtaThreads, smem, s>>>(P);
-        else hexb_step_kernel<N, KIND_ROLLOUT, false><<<grid, kCtaThreads, smem, s>>>(P);
+        if (small) CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_ROLLOUT, true>, Q));
+        else CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_ROLLOUT, false>, Q));
     } else {
-        hexb_step_kernel<N, KIND_OTHER, false><<<grid, kCtaThreads, smem, s>>>(P);
+        CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_OTHER, false>, Q));
     }
     CK(cudaGetLastError());
     return HEXB_OK;
