@@ -261,8 +261,9 @@ HEXB_HD int select_kth_zero_colmajor(const uint32_t (&occ)[Geo<N>::W], int k, in
     empty_bits<N>(occ, e);
     // invariant: empties in columns < lo  <=  k  <  empties in columns < hi
     int lo = 0, hi = N, below = 0;
+    constexpr int STEPS = ceil_log2(N);   // evaluated at compile time
 #pragma unroll
-    for (int it = 0; it < ceil_log2(N); ++it) {
+    for (int it = 0; it < STEPS; ++it) {
         const int mid = (lo + hi + 1) >> 1;   // lo < mid <= hi while hi - lo > 1; mid == hi when hi - lo == 1 (then c > k: no change)
         spread_field<N>((1u << mid) - 1u, m);
         int c = 0;
