@@ -72,6 +72,8 @@ constexpr uint32_t F_TERM_OPP = 1u << 4;
 constexpr uint32_t F_RELABEL = 1u << 5;
 constexpr uint32_t F_ROWJOB = F_RESET | F_TERM | F_RELABEL;  // anything the warp has to sweep the row for
 
+constexpr int ceil_log2(int n) { return n <= 1 ? 0 : 1 + ceil_log2((n + 1) / 2); }
+
 template <int N>
 struct Geo {
     static constexpr int C = N * N;
@@ -79,6 +81,7 @@ struct Geo {
     static constexpr int R = W + 2;              // record words: occ_rm[W], meta, draws
     static constexpr int CHUNK_LAB = 32 * C;               // label bytes of a chunk (multiple of 16)
     static constexpr int CHUNK_STATE = 32 * (C + 4 * R);   // whole chunk: labels + records (multiple of 16)
+    static constexpr int COL_STEPS = ceil_log2(N);         // bisection steps over the columns (select_kth_zero_colmajor)
     static constexpr uint32_t LAST_MASK = (C % 32) ? ((1u << (C % 32)) - 1u) : 0xffffffffu;
 };
 
@@ -252,7 +255,6 @@ HEXB_HD void spread_field(uint32_t field, uint32_t (&out)[Geo<N>::W]) {   // fie
         carry = (uint32_t)(p >> 32);
     }
 }
-constexpr int ceil_log2(int n) { return n <= 1 ? 0 : 1 + ceil_log2((n + 1) / 2); }
 // returns the stored (row-major) cell of the k-th empty cell in column-major order and its column in `col`
 template <int N>
 HEXB_HD int select_kth_zero_colmajor(const uint32_t (&occ)[Geo<N>::W], int k, int &col) {
@@ -261,9 +263,8 @@ HEXB_HD int select_kth_zero_colmajor(const uint32_t (&occ)[Geo<N>::W], int k, in
     empty_bits<N>(occ, e);
     // invariant: empties in columns < lo  <=  k  <  empties in columns < hi
     int lo = 0, hi = N, below = 0;
-    constexpr int STEPS = ceil_log2(N);   // evaluated at compile time
 #pragma unroll
-    for (int it = 0; it < STEPS; ++it) {
+    for (int it = 0; it < Geo<N>::COL_STEPS; ++it) {
         const int mid = (lo + hi + 1) >> 1;   // lo < mid <= hi while hi - lo > 1; mid == hi when hi - lo == 1 (then c > k: no change)
         spread_field<N>((1u << mid) - 1u, m);
         int c = 0;
