@@ -366,12 +366,15 @@ class HexBatch(object):
         torch.cuda.current_stream(self.device).synchronize()
         off = self._state_ptr - self._state.data_ptr()
         cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
-        return {"config": cfg, "state": self._state[off:off + self.state_bytes].clone()}
+        return {"config": cfg, "layout_version": int(self._lib.hexb_version()), "state": self._state[off:off + self.state_bytes].clone()}
 
     def load_state_dict(self, sd):
         cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
         if sd["config"] != cfg:
             raise ValueError("checkpoint belongs to a different configuration: %r vs %r" % (sd["config"], cfg))
+        if sd.get("layout_version") != int(self._lib.hexb_version()) or sd["state"].numel() != self.state_bytes:
+            raise ValueError("checkpoint was written by another version of the packed state layout (%r, library %r)"
+                             % (sd.get("layout_version"), int(self._lib.hexb_version())))
         off = self._state_ptr - self._state.data_ptr()
         self._state[off:off + self.state_bytes].copy_(sd["state"].to(self.device))
 

@@ -500,7 +500,7 @@ static Layout layout_of(const hexb_config *c) {
 
 extern "C" {
 
-int32_t hexb_version(void) { return (1 << 16) | 1; }
+int32_t hexb_version(void) { return (1 << 16) | 2; }   // 1.2: hexb_get_config, state without the transposed bitboard
 
 const char *hexb_strerror(int32_t code) {
     switch (code) {
