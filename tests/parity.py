@@ -383,3 +383,21 @@ def sampler_and_views(make, N, variant_a, seed=0):
             want = np.argsort(-mask.astype(np.int8), axis=1, kind="stable")[np.arange(G), k]
             ok = (cnt > 0) & live          # (a finished game has nobody to sample for)
             eq(got[ok], want[ok].astype(np.int32), "sample_actions view %d t=%d" % (view, t))
+
+
+def raw_random_games(make, N, G, seed=0, variant_b=False):
+    """BASELINE config 1: G raw HexGame instances played random-vs-random (uniformly random cells, so some moves are illegal
+    and some games continue after a win, which fast_move allows), return code and the whole state compared with the oracle
+    after EVERY ply (HexGame.py:85-142 / HexSingleGame.py:88-153)."""
+    kind = hexref.KIND_GAME_B if variant_b else hexref.KIND_GAME_A
+    env = make(kind, N, G)
+    ref = hexref.RefBatch(kind, N, G)
+    env.reset()
+    rs = np.random.RandomState(seed)
+    for t in range(N * N + 6):
+        a = rs.randint(0, N * N, size=G).astype(np.int32)
+        a[rs.rand(G) < 0.02] = rs.randint(-3, N * N + 3)
+        eq(env.ply(a), ref.ply(a), "raw games N=%d ret t=%d" % (N, t))
+        e, r = env.export(), ref.export()
+        for k in ("board", "regions", "region_counter", "cur", "done", "winner"):
+            eq(e[k], r[k], "raw games N=%d %s t=%d" % (N, k, t))

@@ -134,3 +134,8 @@ def test_api_fuzz(seed):
                                          (12, True), (13, False), (14, False), (15, True), (16, False), (17, False), (18, True), (19, False)])
 def test_sampler_and_views(N, variant_a):
     parity.sampler_and_views(make, N, variant_a, seed=N)
+
+
+@pytest.mark.parametrize("N", [3, 5, 8, 11])
+def test_raw_random_games(N):
+    parity.raw_random_games(make, N, 200, seed=N)

@@ -394,3 +394,13 @@ def test_long_run_vs_oracle(make, N, G, T):
                 parity.eq(e[k], re_[k], "long run N=%d t=%d %s" % (N, t, k))
     parity.eq(env.stats(), ref.stats(), "long run stats")
     assert ref.stats()[0] > 3 * G
+
+
+def test_config1_ten_thousand_raw_games(make):
+    """BASELINE config 1: 10,000 raw 5x5 HexGame instances, random-vs-random, state compared after every ply."""
+    parity.raw_random_games(make, 5, 10000, seed=1)
+
+
+@pytest.mark.parametrize("N", [3, 7, 11, 14])
+def test_raw_random_games(make, N):
+    parity.raw_random_games(make, N, 600, seed=N)
