@@ -85,12 +85,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 //   thread-per-game plies, the rare finished-game rows, the elementwise obs/mask encode with 16-byte coalesced stores, the
 //   warp-per-game relabel sweeps, and one bulk copy of the chunk back to global memory.
 #ifndef HEXB_WARPS_PER_CTA
-#define HEXB_WARPS_PER_CTA 1   // measured: 1 warp per CTA 102.2 us, 2: 104.0 us, 4: 104.4 us per 1 Mi-game step (finer-grained tail)
+#define HEXB_WARPS_PER_CTA 1   // measured (r1h): 1 warp per CTA 90.0 us, 2: 94.0 us, 4: 94.7 us per 1 Mi-game step (finer-grained tail)
 #endif
 constexpr int kWarpsPerCta = HEXB_WARPS_PER_CTA;   // Gpad is a multiple of kTile = 128 games, so 1, 2 and 4 all divide it
 constexpr int kCtaThreads = kWarpsPerCta * kWarp;
-// resident CTAs per SM the register allocation should allow: 12 (48 warps) while the record is small, else whatever the
-// shared-memory footprint of the four chunks permits anyway
+// resident CTAs per SM the register allocation should allow (the hardware holds at most 32 CTAs per SM, i.e. 32 warps with one
+// warp per CTA; the step kernel uses 56 registers, so registers are not the limit), for large boards whatever the shared-memory
+// footprint of the chunk permits
 constexpr int min_ctas(int n) {
     const int smem = kWarpsPerCta * 32 * (n * n + 4 * ((n * n + 31) / 32 + 2)) + 64;
     const int by_smem = 220 * 1024 / smem;
