@@ -40,3 +40,21 @@ def test_scripted_choice_is_legal_and_deterministic():
             continue
         a = scripted_choice(board, mask)
         assert mask[a] and a == scripted_choice(board.astype(np.float64), mask.astype(np.uint8))
+
+
+def test_product_never_touches_the_oracle_or_the_emulator():
+    """The package (the product path) must not import, load or mention the test infrastructure: oracle/ and tests/emu."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hex_gym_env_b200")
+    pat = re.compile(r"^\s*(from|import)\s+(oracle|tests|emu)\b|libhexref|libhexb_emu|HEXB_HOST_EMU\s*1", re.M)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), os.path.join(dirpath, f)
+    # and importing the package does not pull them in
+    import subprocess
+    import sys
+    code = "import sys, hex_gym_env_b200; bad = [m for m in sys.modules if m.split('.')[0] in ('oracle', 'emu')]; assert not bad, bad"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=os.path.dirname(root))
