@@ -67,3 +67,17 @@ def test_no_cpu_fallback():
     from hex_gym_env_b200.rollout import masked_sample
     with pytest.raises(RuntimeError, match="GPU only"):
         masked_sample(torch.zeros(2, 9), torch.ones(2, 9, dtype=torch.uint8))
+
+
+def test_missing_library_fails_loudly():
+    """Without libhexb.so the package must raise, not fall back: load it from a path that does not exist, in a fresh interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = ("import hex_gym_env_b200._native as n\n"
+            "try:\n    n.lib()\nexcept RuntimeError as e:\n    assert 'no CPU fallback' in str(e).lower() or 'There is no CPU fallback' in str(e), e\n    print('raised')\n"
+            "else:\n    raise SystemExit('loaded something')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, HEXB_LIB="/nonexistent/libhexb.so"),
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and "raised" in out.stdout, out.stderr
