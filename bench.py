@@ -10,7 +10,23 @@ and legal-action mask) over ALL games of the rank's shard: variant B (SelfPlayEn
 random per game, the agent itself a random policy drawing from the game's Philox stream ("random self-play").
 Weak scaling: every GPU owns `--games-per-gpu` games (default 1,048,576 = config 3's one million games; at N GPUs the job
 is N million games, sharded by global game index with no data-path collective; the only exchange is one NCCL all-reduce
-of the int64[8] episode statistics).
+of the int64[8] episode statistics, issued on a side stream AFTER the timed steps and timed on its own as collective_ms).
+
+Order of the device-resident leg: reset -> [3 steps, then K steps timed = `early_game`] -> untimed pre-roll of --preroll steps
+(one hexb_rollout launch: de-synchronises the games over a few ~54-step episodes so that the steady state is measured
+whatever --warmup is) -> W warm-up steps -> the K steps captured as ONE CUDA graph, replayed once untimed -> barrier ->
+e0 | one replay = exactly K step-kernel launches | e1 -> statistics + all-reduce on the side stream. `value` = all ranks' env
+steps / max over ranks of [e0, e1] (`ms_per_rank` lists every rank's figure).
+
+roofline: achieved = bytes this design must move per launch / the step kernel's average duration in that same bracket (it
+holds nothing else), B'(N) = 2*(C + 4*(W+2)) + 2*C + 5 bytes per env step (packed state in and out, obs, mask, reward, done;
+537 B at 11x11). `frac_contract` is the same time against SURVEY.md 8(d)'s B(N) = 831 B, which assumes a
+state twice as large as this design's and therefore exceeds 1.
+
+e2e: the same step through hexb_step_host with pinned HOST buffers (actions H2D, obs/mask/reward/done D2H inside the timed
+region). cpu_baseline / --impl reference: the UNMODIFIED reference's SelfPlayEnv loop from oracle/_ref (oracle/make_ref.py,
+oracle/ref_loop.py), one process per host core. extra_configs (1-GPU line only): BASELINE configs 2 and 5, the literal
+config-3 shard (131,072 games) and config 4's env side, each pre-rolled and timed the same way.
 """
 import argparse
 import json
@@ -94,9 +110,12 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU legs
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def cpu_port_rate(N, budget_s, threads):
     """The C restatement of the reference loop (oracle/hexref.c), `threads` pthreads over independent games."""
-    import numpy as np  # noqa: F401
     from oracle import hexref
     hexref.set_threads(threads)
     G = 2048 * threads
@@ -114,52 +133,81 @@ def cpu_port_rate(N, budget_s, threads):
     return G * n / dt, "%d games x %d steps (C port, %d threads)" % (G, n, threads)
 
 
-def py_rate(N, seconds, procs):
-    """oracle/pyloop.py in a child interpreter (keeps fork() away from this process's CUDA context)."""
+def ref_kind():
+    """"reference" when the byte-identical copy of the reference (oracle/_ref, oracle/make_ref.py) is present, else "port"."""
+    from oracle import ref_loop
+    return "reference" if ref_loop.available() else "port"
+
+
+def py_rate(N, seconds, procs, kind):
+    """The reference's random self-play loop in child interpreters (keeps fork() away from this process's CUDA context):
+    kind "reference" = the UNMODIFIED minihex classes from oracle/_ref (oracle/ref_loop.py), "port" = the Python/numpy
+    restatement (oracle/pyloop.py), used only when the copy is missing."""
     import subprocess
-    out = subprocess.run([sys.executable, "-m", "oracle.pyloop", str(N), str(seconds), str(procs)], cwd=ROOT, check=True,
+    mod = "oracle.ref_loop" if kind == "reference" else "oracle.pyloop"
+    out = subprocess.run([sys.executable, "-m", mod, str(N), str(seconds), str(procs)], cwd=ROOT, check=True,
                          stdout=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")).stdout
     j = json.loads(out.strip().splitlines()[-1])
     return j["value"], j["sample"]
 
 
 def cpu_baseline(N, budget_s=12.0):
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    v, sample = py_rate(N, budget_s, cores)
-    p1, _ = py_rate(N, min(budget_s, 4.0), 1)
-    c1, _ = cpu_port_rate(N, 2.0, 1)
-    cn, _ = cpu_port_rate(N, 3.0, cores)
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "python_loop_1_core": p1,
-            "c_port_1_thread": c1, "c_port_all_threads": cn}
+    cores, kind = host_cores(), ref_kind()
+    v, sample = py_rate(N, budget_s, cores, kind)
+    p1, _ = py_rate(N, min(budget_s, 3.0), 1, kind)
+    out = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "one_core": p1}
+    if kind == "reference":   # how the restatements compare with the real thing, same box, same run
+        out["python_port_all_cores"], _ = py_rate(N, 3.0, cores, "port")
+    out["c_port_1_thread"], _ = cpu_port_rate(N, 2.0, 1)
+    out["c_port_all_threads"], _ = cpu_port_rate(N, 3.0, cores)
+    return out
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line - the same for both arms (the reference arm samples this workload on host cores)."""
+    N, G, K = args.board, args.games_per_gpu, args.steps
+    use_graph = (not args.no_graph) and K >= 2
+    return {"workload": ("11x11 SelfPlayEnv (variant B) random self-play, random opponent, auto-reset (BASELINE config 3)" if N == 11
+                         else "%dx%d SelfPlayEnv random self-play" % (N, N)),
+            "board_size": N, "games_per_gpu": G, "global_games": world * G, "parallelism": "games sharded by index x%d" % world,
+            "l2_policy": "working set %.0f MB per step > 126 MB L2" % (G * moved_bytes(N) / 1e6),
+            "agent": "random policy (BaseRandomPolicy) drawing from the game's own stream", "seed": args.seed,
+            "preroll_steps": args.preroll + (K if use_graph else 0),
+            "launch": ("ONE CUDA graph of the K = %d step launches" % K) if use_graph else "one launch per step"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU loop (mask -> random action -> SelfPlayEnv.step, reset on done) restated in
-    Python/numpy (oracle/pyloop.py, same per-step numpy work as minihex), one process per host core."""
+    """Reference arm: the reference's own CPU implementation of the path - the UNMODIFIED minihex SelfPlayEnv loop
+    (mask = legal_actions(); a = BaseRandomPolicy().choose_action(obs); step(a); reset on done) from oracle/_ref, one process
+    per host core (the reference is single-threaded). Every "step" is one bounded sample of that loop on all cores; exactly
+    --steps samples are timed after --warmup untimed ones, and the sample length is chosen so that the run ends in ~1 minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    steps = min(args.steps, 10)          # bounded: every step is a per_step_s sample on all cores
-    per_step_s = 2.0
-    for _ in range(min(max(args.warmup, 0), 3)):
-        py_rate(BOARD, 0.3, cores)
+    N = args.board
+    cores, kind = host_cores(), ref_kind()
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    per_step_s = min(2.0, max(0.4, args.ref_budget / (steps + 0.5 * warm)))   # interpreter start-up (~0.3 s) comes on top of each
+    for _ in range(warm):
+        py_rate(N, 0.5 * per_step_s, cores, kind)
     t0 = time.perf_counter()
     samples = []
     for _ in range(steps):
-        v, sample = py_rate(BOARD, per_step_s, cores)
+        v, sample = py_rate(N, per_step_s, cores, kind)
         samples.append(v)
     dt = time.perf_counter() - t0
     v = sum(samples) / len(samples)
-    c_all, c_sample = cpu_port_rate(BOARD, 3.0, cores)
+    c_all, c_sample = cpu_port_rate(N, 2.0, cores)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "samples_run": steps, "ms_per_step": 1e3 * dt / max(steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "11x11 SelfPlayEnv random self-play (BASELINE config 3), reference CPU loop",
-                       "board_size": BOARD, "note": "each step = %.1f s sample of the loop on every host core" % per_step_s},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "python/numpy restatement of the minihex loop, %d processes x %.1f s x %d steps"
-                                       % (cores, per_step_s, steps),
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, max(args.gpus, 1)),
+            "arm_note": "reference CPU loop, one env per host core (%d); each step = one %.2f s sample of the loop on every core; "
+                        "the GPU-side keys of config describe the arm this one is compared with" % (cores, per_step_s),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%s, %d processes x %.2f s x %d steps"
+                                       % ("unmodified minihex SelfPlayEnv loop (oracle/_ref)" if kind == "reference"
+                                          else "python/numpy restatement of the minihex loop (oracle/_ref missing)", cores, per_step_s, steps),
                              "c_port_all_threads": c_all, "c_port_sample": c_sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -167,102 +215,181 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
+def pin_rank_cpus(local, local_world):
+    """Give this rank its own slice of the host CPUs. NVML's ideal set for the GPU is the starting point (on these single-socket
+    VMs it is the same 32 CPUs for every GPU, which is how 8 launch loops + 8 NVML samplers + the NCCL proxies ended up sharing
+    cores in round 1); the ranks whose GPUs share a set split it evenly by position."""
+    if not hasattr(os, "sched_getaffinity"):
+        return "unchanged (no sched_getaffinity)"
+    allowed = sorted(os.sched_getaffinity(0))
+    mine, peers = allowed, list(range(local_world))
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        words = (max(allowed) // 64) + 1
+
+        def ideal(i):
+            m = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words)
+            s = [c for c in allowed if (m[c // 64] >> (c % 64)) & 1]
+            return s or allowed
+        sets = [ideal(i) for i in range(local_world)]
+        mine = sets[local]
+        peers = [i for i in range(local_world) if sets[i] == mine]
+    except Exception:
+        pass
+    k, n = peers.index(local), len(peers)
+    per = max(len(mine) // n, 1)
+    sl = mine[k * per:(k + 1) * per] if k * per < len(mine) else mine
+    try:
+        os.sched_setaffinity(0, sl)
+    except Exception as exc:
+        return "not set (%s)" % (str(exc)[:60],)
+    return "cpus %d-%d (%d of %d allowed, slice %d/%d)" % (sl[0], sl[-1], len(sl), len(allowed), k, n)
+
+
+def capture_steps(env, dev, n, **kw):
+    """n calls of env.step(**kw) as ONE CUDA graph (a replay = n step-kernel launches, no host work in between)."""
+    import torch
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(n):
+                env.step(**kw)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    return g
+
+
+def time_steps(env, dev, K, use_graph, reps=1):
+    """CUDA-event time (ms) of `reps` x K env.step() launches on the current stream; with a graph, one replay = K launches."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g = capture_steps(env, dev, K) if use_graph else None
+    if g is not None:
+        g.replay()                       # untimed: first replay of a fresh graph uploads it
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        if g is not None:
+            g.replay()
+        else:
+            for _ in range(K):
+                env.step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1), (K if g is not None else 0)
+
+
+def extra_config(name, N, G, variant, agent_mode, K, preroll, dev, peak):
+    """One more BASELINE configuration on this GPU (N = 1 run only): untimed pre-roll, then K graph-replayed steps."""
+    import torch
+    from hex_gym_env_b200 import HexBatch
+    env = HexBatch(N, G, variant=variant, device=dev.index, seed=0, agent_mode=agent_mode, auto_reset=True)
+    env.reset()
+    env.rollout(preroll, outputs=False)
+    for _ in range(3):
+        env.step()
+    ms, _ = time_steps(env, dev, K, True)
+    us = 1e3 * ms / K
+    mv = G * moved_bytes(N) / (us * 1e-6) / 1e9
+    out = {"config": name, "board_size": N, "games": G, "steps": K, "preroll_steps": preroll, "us_per_step": us,
+           "env_steps_per_sec": G / (us * 1e-6), "moved_GBps": mv, "frac_of_hbm_peak": mv / peak,
+           "bytes_per_env_step_moved": moved_bytes(N)}
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from hex_gym_env_b200 import HexBatch, VARIANT_B, AGENT_RANDOM
+    from hex_gym_env_b200 import HexBatch, VARIANT_A, VARIANT_B, AGENT_RANDOM, AGENT_BLACK
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = "unchanged"
-    try:  # run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU: the end-to-end leg is PCIe / host-memory bound
-        import pynvml
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-        numa = "nvmlDeviceSetCpuAffinity(gpu %d): %d cpus" % (local, len(os.sched_getaffinity(0)))
-    except Exception as exc:
-        numa = "not set (%s)" % (str(exc)[:60],)
+    numa = pin_rank_cpus(local, local_world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N, G, K, Wm = args.board, args.games_per_gpu, args.steps, args.warmup
+    use_graph = (not args.no_graph) and K >= 2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    def gather_ms(ms):
         if world == 1:
-            return ms
+            return [ms]
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        out = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().tolist()
 
     # ------------------------------------------------ device-resident leg (value + roofline)
     env = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                    auto_reset=True)
-    env.reset()
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev)
     stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    env.reset()
+    # (a) the early game, for the record: all games start together on empty boards, few merges, no game ends
+    for _ in range(3):
+        env.step()
+    early_ms, _ = time_steps(env, dev, K, use_graph)
+    # (b) untimed, declared pre-roll: games de-synchronise over a few episodes (mean episode ~54 env steps at 11x11), so
+    #     that the timed steps see the steady-state mix of merges, finished games and restarts whatever --warmup is
+    env.rollout(args.preroll, outputs=False)
     for _ in range(Wm):
         env.step()
-    # The step loop is captured in a CUDA graph (GRAPH_STEPS launches per replay) so that the ~3 us launch gap of a Python
-    # loop does not sit between 110 us kernels; K steps = K kernel launches either way.
-    GRAPH_STEPS = 50
-    graph = None
-    if not args.no_graph and K >= 2 * GRAPH_STEPS:
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            env.step()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                for _ in range(GRAPH_STEPS):
-                    env.step()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph.replay()      # (warm-up: these 51 steps are outside the timed region)
-
-    def run_steps(n):
-        if graph is not None:
-            for _ in range(n // GRAPH_STEPS):
-                graph.replay()
-            n %= GRAPH_STEPS
-        for _ in range(n):
-            env.step()
-
-    env.stats(out=stats)
-    if world > 1:
-        dist.all_reduce(stats)
+    graph = capture_steps(env, dev, K) if use_graph else None
+    if graph is not None:
+        graph.replay()                   # untimed: uploads the graph (K more steps of pre-roll)
+    for _ in range(3):                   # the collective is warm before anything is timed
+        env.stats(out=stats)
+        if world > 1:
+            dist.all_reduce(stats)
     s0 = stats.clone()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     e0.record()
-    run_steps(K)
-    env.stats(out=stats)
-    if world > 1:
-        dist.all_reduce(stats)      # K7: the only collective of the path (64 bytes)
+    if graph is not None:
+        graph.replay()                   # exactly K step launches
+    else:
+        for _ in range(K):
+            env.step()
     e1.record()
+    # K7 + the path's only collective (64 bytes), on a side stream that waits for the K steps: it is never between two step
+    # kernels, and it is outside the [e0, e1] bracket (timed on its own as collective_ms)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        env.stats(out=stats)
+        c0.record()
+        if world > 1:
+            dist.all_reduce(stats)
+        c1.record()
+    main.wait_stream(side)
     barrier()
     clocks = sampler.stop()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = K + 1
+    my_ms = e0.elapsed_time(e1)
+    per_rank = gather_ms(my_ms)
+    ms = max(per_rank)
+    collective_ms = c0.elapsed_time(c1) if world > 1 else 0.0
+    launches = K
     value = world * G * K / (ms * 1e-3)
     ds = (stats - s0).cpu().tolist()
 
-    # kernel-only duration for the roofline: the K step launches alone, CUDA events on the launching stream
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    k0.record()
-    run_steps(K)
-    k1.record()
-    torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / K
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -270,8 +397,9 @@ def run_gpu(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    B = contract_bytes(N)
-    achieved = G * B / (kern_ms * 1e-3) / 1e9
+    kern_ms = my_ms / K                  # the bracket holds nothing but the K step-kernel launches
+    Bm, Bc = moved_bytes(N), contract_bytes(N)
+    achieved = G * Bm / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -281,17 +409,22 @@ def run_gpu(args):
             traffic = ent["dram_bytes_per_launch"]
     except Exception:
         pass
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "hexb_step_kernel<%d, KIND_STEP, %s>" % (N, "several-rows sweep" if (G + 127) // 128 * 4 <= 32 * torch.cuda.get_device_properties(dev).multi_processor_count else "one-row sweep"), "kernel_ms": kern_ms,
-                "bytes_per_env_step_contract": B, "bytes_per_env_step_moved": moved_bytes(N),
-                "achieved_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9,
-                "frac_moved": G * moved_bytes(N) / (kern_ms * 1e-3) / 1e9 / peak,
-                "note": "achieved/frac use SURVEY 8(d)'s algorithmic bytes (state 290 B per game each way); this implementation "
-                        "packs the state into 145 B, so the bytes the kernel really requests (achieved_moved/frac_moved) are lower "
-                        "and frac can exceed 1; 20 MiB of the state are kept L2-resident across steps, so HBM sees slightly less "
-                        "than that again (traffic = ncu dram bytes per launch, measured with L2 flushed before the launch)",
+                "kernel": "hexb_step_kernel<%d, KIND_STEP, %s>" % (N, "several-rows sweep" if (G + 127) // 128 * 4 <= 32 * sms else "one-row sweep"),
+                "kernel_ms": kern_ms, "bytes_per_env_step": Bm, "bytes_per_launch": G * Bm,
+                "bytes_formula": "B'(N) = 2*(C + 4*(W+2)) [packed state in + out] + 2*C [obs + mask] + 5 [reward + done] (+4 with external actions); C = N*N, W = ceil(C/32)",
+                "frac_contract": G * Bc / (kern_ms * 1e-3) / 1e9 / peak, "bytes_per_env_step_contract": Bc,
+                "note": "achieved/frac count the bytes this design must move per env step (DESIGN.md section 6); frac_contract uses SURVEY "
+                        "8(d)'s B(N), whose state term (290 B per game each way) is twice this design's 145 B and therefore exceeds 1. "
+                        "20 MiB of the state stay L2-resident across steps, so HBM sees slightly less than bytes_per_launch "
+                        "(traffic = ncu dram bytes per launch)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
-    del env
+    early = {"ms_per_step": early_ms / K, "value": world * G * K / (early_ms * 1e-3),
+             "note": "the same K steps timed right after reset (3 warm-up steps): every game in its opening, no merges, no restarts"}
+    env.close()
+    del env, graph
+    torch.cuda.empty_cache()
 
     # ------------------------------------------------ end-to-end leg: host actions in, host obs/mask/reward/done out
     E = min(K, args.e2e_steps)
@@ -309,6 +442,7 @@ def run_gpu(args):
         host_actions[t].copy_(a)
         rec.step(a, outputs=False)
     torch.cuda.synchronize()
+    rec.close()
     del rec
     env = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                    auto_reset=True)
@@ -327,26 +461,35 @@ def run_gpu(args):
         checksum += float(io["reward"][0])             # host read of the step's result
     e1.record()
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_rank = gather_ms(e0.elapsed_time(e1))
+    e2e_ms = max(e2e_rank)
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches_e2e = E
     invalid = int(env.stats().cpu()[5])
     e2e = {"value": world * G * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * G,
            "d2h_bytes_per_step": G * (2 * N * N + 5), "steps": E, "ms_per_step": e2e_ms / E, "wall_ms_per_step": wall_ms / E,
            "api": "hexb_step_host (C ABI, pinned host buffers)", "illegal_moves_in_replay": invalid, "cpu_affinity": numa}
+    env.close()
+    del env
+    torch.cuda.empty_cache()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "11x11 SelfPlayEnv (variant B) random self-play, random opponent, auto-reset (BASELINE config 3)"
-                       if N == 11 else "%dx%d SelfPlayEnv random self-play" % (N, N),
-                       "board_size": N, "games_per_gpu": G, "global_games": world * G, "parallelism": "games sharded by index x%d" % world,
-                       "l2_policy": "working set %.0f MB per step > 126 MB L2" % (G * moved_bytes(N) / 1e6),
-                       "agent": "fused on-device random policy (Philox stream per game)", "seed": args.seed,
-                       "launch": ("CUDA graph of %d step launches per replay" % GRAPH_STEPS) if graph is not None else "one launch per step"},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "gpu_launches_detail": {"timed_region": "%d x hexb_step_kernel + 1 x hexb_stats_kernel" % K, "roofline_region": K, "e2e_region": launches_e2e}, "clocks": clocks,
+            "config": workload_config(args, world),
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches,
+            "gpu_launches_detail": {"timed_region": "%d x hexb_step_kernel" % K, "after_timed_region": "1 x hexb_stats_kernel%s (side stream)" % (" + ncclAllReduce int64[8]" if world > 1 else ""), "e2e_region": launches_e2e},
+            "ms_per_rank": [m / K for m in per_rank], "collective_ms": collective_ms, "clocks": clocks, "early_game": early,
             "plies_per_sec": ds[7] / (ms * 1e-3), "episodes_in_timed_region": ds[0],
             "episode_stats": dict(zip(("episodes", "black_wins", "white_wins", "agent_wins", "episode_plies", "invalid_ends",
                                        "env_steps", "plies"), ds))}
+    if rank == 0 and world == 1 and not args.no_extra:
+        # the other BASELINE configurations that fit one GPU, and the literal config-3 shard (1 Mi games over 8 GPUs)
+        line["extra_configs"] = [
+            extra_config("config 2: 7x7 HexEnv (variant A) + random_policy opponent, 65,536 games", 7, 65536, VARIANT_A, AGENT_BLACK, 200, 100, dev, peak),
+            extra_config("config 3 shard: 11x11 SelfPlayEnv, 131,072 games (1 Mi games / 8 GPUs)", 11, 131072, VARIANT_B, AGENT_RANDOM, 200, 300, dev, peak),
+            extra_config("config 4 env side: 6x6 SelfPlayEnv, 4,096 games", 6, 4096, VARIANT_B, AGENT_RANDOM, 200, 100, dev, peak),
+            extra_config("config 5: 19x19 SelfPlayEnv, 4,194,304 games", 19, 4194304, VARIANT_B, AGENT_RANDOM, 30, 200, dev, peak),
+        ]
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(N, args.cpu_budget)
@@ -367,8 +510,8 @@ def _claim_stdout():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--board", type=int, default=BOARD)
     ap.add_argument("--games-per-gpu", type=int, default=GAMES_PER_GPU)
@@ -377,6 +520,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--preroll", type=int, default=2000, help="untimed env steps (one hexb_rollout launch) before warm-up: de-synchronises the games")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs block of the 1-GPU line")
+    ap.add_argument("--ref-budget", type=float, default=45.0, help="--impl reference: seconds of CPU sampling in total")
     args = ap.parse_args()
     args.out = _claim_stdout()
     if args.impl == "reference":

@@ -7,18 +7,34 @@ reference imports UNMODIFIED. Its module-level ``random`` (``SelfplayWrapper.py:
 ``minihex/__init__.py:5``, ``HexGame.py:5``) is then swapped for a per-game stream
 (``oracle.philox.GameStream``) so draws are reproducible and keyed per game.
 
-This file is used only by ``oracle/gen_golden.py`` (and by optional cross-checks that are
-skipped when /root/reference is absent, i.e. on the GPU box). Nothing here ships.
+This file is used by ``oracle/gen_golden.py``, by optional cross-checks that are skipped when the
+reference is absent, and by ``oracle/ref_loop.py`` (the CPU baseline ``bench.py`` times: the
+unmodified reference from the byte-identical copy ``oracle/make_ref.py`` puts under ``oracle/_ref``).
+Nothing here ships.
 """
 import os
 import sys
 import types
 
+REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.py: unmodified copy that travels
 REFERENCE_ROOT = os.environ.get("HEX_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "minihex")) and os.path.isdir(os.path.join(REF_COPY, "minihex")):
+    REFERENCE_ROOT = REF_COPY   # the GPU box has no /root/reference; the byte-identical copy stands in
+
+
+def use_copy():
+    """Import the reference from oracle/_ref even where /root/reference exists (bench.py: the same files in both places)."""
+    global REFERENCE_ROOT
+    if _mods is not None and REFERENCE_ROOT != REF_COPY:
+        raise RuntimeError("the reference is already imported from %s" % REFERENCE_ROOT)
+    REFERENCE_ROOT = REF_COPY
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "minihex"))
+
+
+_mods = None
 
 
 def _install_stubs():
@@ -46,9 +62,6 @@ def _install_stubs():
         pg = types.ModuleType("pygame")
         pg.Color = lambda *a, **k: None
         sys.modules["pygame"] = pg
-
-
-_mods = None
 
 
 def load():
