@@ -37,7 +37,7 @@ def _ptr(t):
 class HexBatch(object):
     def __init__(self, board_size, num_games, variant=VARIANT_B, device=None, seed=0, game_offset=0,
                  agent_mode=AGENT_BLACK, opponent_first=False, auto_reset=True, eval_state=False, raw=False,
-                 manual_opponent=False, pool_size=0):
+                 manual_opponent=False, pool_size=0, obs_dtype=torch.int8):
         self._h = None
         self._lib = _native.lib()  # raises if libhexb.so cannot be built / loaded
         if not torch.cuda.is_available():
@@ -47,10 +47,14 @@ class HexBatch(object):
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         self.N, self.G, self.C = int(board_size), int(num_games), int(board_size) * int(board_size)
         self.variant, self.raw, self.auto_reset = int(variant), bool(raw), bool(auto_reset)
+        if obs_dtype not in (torch.int8, torch.float32):
+            raise ValueError("obs_dtype must be torch.int8 or torch.float32")
+        self.obs_dtype = obs_dtype   # element type of every obs / term_obs tensor (hexb_config.obs_dtype)
         self.cfg = HexbConfig(board_size=self.N, variant=self.variant, num_games=self.G, game_offset=int(game_offset),
                               seed=int(seed) & 0xFFFFFFFFFFFFFFFF, agent_mode=int(agent_mode), opponent_first=int(bool(opponent_first)),
                               auto_reset=int(bool(auto_reset)), eval_state=int(bool(eval_state)), raw=int(bool(raw)),
-                              device=self.device.index, manual_opponent=int(bool(manual_opponent)), pool_size=int(pool_size))
+                              device=self.device.index, manual_opponent=int(bool(manual_opponent)), pool_size=int(pool_size),
+                              obs_dtype=1 if obs_dtype == torch.float32 else 0)
         self.manual_opponent = bool(manual_opponent)
         nbytes = self._lib.hexb_state_bytes(ctypes.byref(self.cfg))
         if nbytes == 0:
@@ -73,6 +77,7 @@ class HexBatch(object):
         self._out = {}
         self._ws = None
         self._pinned = None
+        self._packed = None
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -125,7 +130,7 @@ class HexBatch(object):
         G, N, C = self.G, self.N, self.C
         rm = self._in(reset_mask, (G,), torch.uint8, "reset_mask")
         ou = self._in(open_u, (G,), torch.float64, "open_u")
-        obs = self._chk(obs, (G, N, N), torch.int8, "obs") if obs is not None else self._buf("obs", (G, N, N), torch.int8)
+        obs = self._chk(obs, (G, N, N), self.obs_dtype, "obs") if obs is not None else self._buf("obs", (G, N, N), self.obs_dtype)
         mask = self._chk(mask, (G, C), torch.uint8, "mask") if mask is not None else self._buf("mask", (G, C), torch.uint8)
         with torch.cuda.device(self.device):
             check(self._lib.hexb_reset(self._h, _ptr(rm), _ptr(ou), _ptr(obs), _ptr(mask), self._stream()))
@@ -143,14 +148,14 @@ class HexBatch(object):
         a = self._in(actions, (G,), torch.int32, "actions")
         u = self._in(opp_u, (G, 2), torch.float64, "opp_u")
         if outputs:
-            obs = self._chk(obs, (G, N, N), torch.int8, "obs") if obs is not None else self._buf("obs", (G, N, N), torch.int8)
+            obs = self._chk(obs, (G, N, N), self.obs_dtype, "obs") if obs is not None else self._buf("obs", (G, N, N), self.obs_dtype)
             mask = self._chk(mask, (G, C), torch.uint8, "mask") if mask is not None else self._buf("mask", (G, C), torch.uint8)
             reward = self._chk(reward, (G,), torch.float32, "reward") if reward is not None else self._buf("reward", (G,), torch.float32)
             done = self._chk(done, (G,), torch.uint8, "done") if done is not None else self._buf("done", (G,), torch.uint8)
         if term_obs is not None:
-            term_obs = self._chk(term_obs, (G, N, N), torch.int8, "term_obs")
+            term_obs = self._chk(term_obs, (G, N, N), self.obs_dtype, "term_obs")
         elif want_term:
-            term_obs = self._buf("term_obs", (G, N, N), torch.int8)
+            term_obs = self._buf("term_obs", (G, N, N), self.obs_dtype)
         if actions_out is not None:
             actions_out = self._chk(actions_out, (G,), torch.int32, "actions_out")
         elif want_actions:
@@ -171,11 +176,11 @@ class HexBatch(object):
         obs i8[T,G,N,N], mask u8[T,G,C], reward f32[T,G], done u8[T,G] (+ term_obs, actions_out when given)."""
         T, G, N, C = int(num_steps), self.G, self.N, self.C
         if outputs:
-            obs = self._chk(obs, (T, G, N, N), torch.int8, "obs") if obs is not None else self._buf("r_obs%d" % T, (T, G, N, N), torch.int8)
+            obs = self._chk(obs, (T, G, N, N), self.obs_dtype, "obs") if obs is not None else self._buf("r_obs%d" % T, (T, G, N, N), self.obs_dtype)
             mask = self._chk(mask, (T, G, C), torch.uint8, "mask") if mask is not None else self._buf("r_mask%d" % T, (T, G, C), torch.uint8)
             reward = self._chk(reward, (T, G), torch.float32, "reward") if reward is not None else self._buf("r_rew%d" % T, (T, G), torch.float32)
             done = self._chk(done, (T, G), torch.uint8, "done") if done is not None else self._buf("r_done%d" % T, (T, G), torch.uint8)
-        term_obs = self._chk(term_obs, (T, G, N, N), torch.int8, "term_obs")
+        term_obs = self._chk(term_obs, (T, G, N, N), self.obs_dtype, "term_obs")
         actions_out = self._chk(actions_out, (T, G), torch.int32, "actions_out")
         with torch.cuda.device(self.device):
             check(self._lib.hexb_rollout(self._h, T, _ptr(obs), _ptr(mask), _ptr(reward), _ptr(done), _ptr(term_obs), _ptr(actions_out),
@@ -219,25 +224,63 @@ class HexBatch(object):
         if self._pinned is None:
             G, N, C = self.G, self.N, self.C
             self._pinned = dict(actions=torch.empty(G, dtype=torch.int32).pin_memory(),
-                                obs=torch.empty((G, N, N), dtype=torch.int8).pin_memory(),
+                                obs=torch.empty((G, N, N), dtype=self.obs_dtype).pin_memory(),
                                 mask=torch.empty((G, C), dtype=torch.uint8).pin_memory(),
                                 reward=torch.empty(G, dtype=torch.float32).pin_memory(),
                                 done=torch.empty(G, dtype=torch.uint8).pin_memory())
         return self._pinned
+
+    def set_launch_form(self, warps_per_chunk=0):
+        """0: the kernel form is chosen by launch depth; 1 / 2 / 4 / 8: that many warps per 32-game chunk (tuning, tests)."""
+        check(self._lib.hexb_set_launch_form(self._h, int(warps_per_chunk)))
+
+    def _host_ws(self):
+        if self._ws is None:
+            n = self._lib.hexb_host_workspace_bytes(ctypes.byref(self.cfg))
+            self._ws = torch.empty(int(n) + 256, dtype=torch.uint8, device=self.device)
+        return ctypes.c_void_p(self._ws.data_ptr() + ((-self._ws.data_ptr()) % 256))
+
+    def step_host_begin(self, actions_host=None, io=None, want_obs=True, want_mask=True):
+        """step_host split in two: enqueue H2D + step + D2H and return at once (a host-side policy can work meanwhile);
+        step_host_end() waits until `io` holds the results. One step may be pending."""
+        io = io or self.pinned_io()
+        if actions_host is not None and actions_host is not io["actions"]:
+            io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_step_host_begin(self._h, self._host_ws(), _ptr(io["actions"]) if actions_host is not None else None,
+                                                 _ptr(io["obs"]) if want_obs else None, _ptr(io["mask"]) if want_mask else None,
+                                                 _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
+        return io
+
+    def step_host_end(self):
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_step_host_end(self._h))
+
+    def step_host_packed(self, actions_host=None, io=None):
+        """step_host with the observations crossing PCIe as 2 bits per cell; host threads expand them into io["obs"] / io["mask"]
+        (bit-identical to step_host; int8 observations only)."""
+        io = io or self.pinned_io()
+        if self._packed is None:
+            n = int(self._lib.hexb_host_packed_bytes(ctypes.byref(self.cfg)))
+            self._packed = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
+        ph = self._packed.data_ptr() + ((-self._packed.data_ptr()) % 64)
+        if actions_host is not None and actions_host is not io["actions"]:
+            io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_step_host_packed(self._h, self._host_ws(), ctypes.c_void_p(ph),
+                                                  _ptr(io["actions"]) if actions_host is not None else None, _ptr(io["obs"]),
+                                                  _ptr(io["mask"]), _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
+        return io
 
     def step_host(self, actions_host=None, io=None, want_obs=True, want_mask=True):
         """The step as a host-side user of the reference API makes it: HOST actions in, HOST obs/mask/reward/done out
         (one call, copies inside, returns when the results are in host memory). `io` = pinned_io() or compatible CPU
         tensors. actions_host=None: fused agent sampling on the device (no H2D)."""
         io = io or self.pinned_io()
-        if self._ws is None:
-            n = self._lib.hexb_host_workspace_bytes(ctypes.byref(self.cfg))
-            self._ws = torch.empty(int(n) + 256, dtype=torch.uint8, device=self.device)
-        ws = self._ws.data_ptr() + ((-self._ws.data_ptr()) % 256)
         if actions_host is not None and actions_host is not io["actions"]:
             io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
         with torch.cuda.device(self.device):
-            check(self._lib.hexb_step_host(self._h, ctypes.c_void_p(ws), _ptr(io["actions"]) if actions_host is not None else None,
+            check(self._lib.hexb_step_host(self._h, self._host_ws(), _ptr(io["actions"]) if actions_host is not None else None,
                                            _ptr(io["obs"]) if want_obs else None, _ptr(io["mask"]) if want_mask else None,
                                            _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
         return io
@@ -251,9 +294,9 @@ class HexBatch(object):
         reward = self._chk(reward, (G,), torch.float32, "reward") if reward is not None else self._buf("h_reward%d" % side, (G,), torch.float32)
         done = self._chk(done, (G,), torch.uint8, "done") if done is not None else self._buf("h_done%d" % side, (G,), torch.uint8)
         if term_obs is not None:
-            term_obs = self._chk(term_obs, (G, N, N), torch.int8, "term_obs")
+            term_obs = self._chk(term_obs, (G, N, N), self.obs_dtype, "term_obs")
         elif want_term:
-            term_obs = self._buf("term_obs", (G, N, N), torch.int8)
+            term_obs = self._buf("term_obs", (G, N, N), self.obs_dtype)
         with torch.cuda.device(self.device):
             check(self._lib.hexb_half_step(self._h, int(side), _ptr(a), _ptr(reward), _ptr(done), _ptr(term_obs), self._stream()))
         out = dict(reward=reward, done=done)
@@ -263,7 +306,7 @@ class HexBatch(object):
 
     def opponent_opening(self, opponent_fn):
         """After reset(): let the caller's opponent open the games in which it moves first (agent is WHITE)."""
-        o1, m1 = self._buf("opp_obs", (self.G, self.N, self.N), torch.int8), self._buf("opp_mask", (self.G, self.C), torch.uint8)
+        o1, m1 = self._buf("opp_obs", (self.G, self.N, self.N), self.obs_dtype), self._buf("opp_mask", (self.G, self.C), torch.uint8)
         self.encode(1, obs=o1, mask=m1)
         self.half_step(1, opponent_fn(o1, m1, self.to_move, self.opp_index))
 
@@ -273,10 +316,10 @@ class HexBatch(object):
         to_move u8[G], opp_index i32[G]) -> actions i32[G]` sees the side-to-move view (what OpponentPolicy.choose_action gets,
         SelfplayWrapper.py:161) and must answer for the games with to_move == 1; its other entries are ignored."""
         G, N, C = self.G, self.N, self.C
-        term = self._buf("sw_term", (G, N, N), torch.int8) if want_term else None
+        term = self._buf("sw_term", (G, N, N), self.obs_dtype) if want_term else None
         h = self.half_step(0, actions, term_obs=term)
         reward, done = h["reward"].clone(), h["done"].clone()
-        o1, m1 = self._buf("opp_obs", (G, N, N), torch.int8), self._buf("opp_mask", (G, C), torch.uint8)
+        o1, m1 = self._buf("opp_obs", (G, N, N), self.obs_dtype), self._buf("opp_mask", (G, C), torch.uint8)
         for _ in range(2):
             self.encode(1, obs=o1, mask=m1)
             h = self.half_step(1, opponent_fn(o1, m1, self.to_move, self.opp_index), term_obs=term)
@@ -298,7 +341,7 @@ class HexBatch(object):
 
     def encode(self, view=0, obs=None, mask=None):
         G, N, C = self.G, self.N, self.C
-        obs = self._chk(obs, (G, N, N), torch.int8, "obs") if obs is not None else self._buf("obs", (G, N, N), torch.int8)
+        obs = self._chk(obs, (G, N, N), self.obs_dtype, "obs") if obs is not None else self._buf("obs", (G, N, N), self.obs_dtype)
         mask = self._chk(mask, (G, C), torch.uint8, "mask") if mask is not None else self._buf("mask", (G, C), torch.uint8)
         with torch.cuda.device(self.device):
             check(self._lib.hexb_encode(self._h, int(view), _ptr(obs), _ptr(mask), self._stream()))
@@ -366,7 +409,14 @@ class HexBatch(object):
         torch.cuda.current_stream(self.device).synchronize()
         off = self._state_ptr - self._state.data_ptr()
         cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
-        return {"config": cfg, "layout_version": int(self._lib.hexb_version()), "state": self._state[off:off + self.state_bytes].clone()}
+        sd = {"config": cfg, "layout_version": int(self._lib.hexb_version()), "state": self._state[off:off + self.state_bytes].clone()}
+        # per-game bookkeeping that lives outside the packed blob: the pool opponent drawn at reset for the running episode, whose
+        # turn it is, and (when enabled) the info-dict tensors
+        for name in ("opp_index", "to_move", "last_move_opponent", "winner"):
+            t = getattr(self, name, None)
+            if t is not None:
+                sd[name] = t.clone()
+        return sd
 
     def load_state_dict(self, sd):
         cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
@@ -377,6 +427,12 @@ class HexBatch(object):
                              % (sd.get("layout_version"), int(self._lib.hexb_version())))
         off = self._state_ptr - self._state.data_ptr()
         self._state[off:off + self.state_bytes].copy_(sd["state"].to(self.device))
+        for name in ("opp_index", "to_move", "last_move_opponent", "winner"):
+            t = getattr(self, name, None)
+            if t is not None:
+                if name not in sd:
+                    raise ValueError("checkpoint lacks %r, which this batch tracks" % name)
+                t.copy_(sd[name].to(self.device))
 
     def import_boards(self, board_true, to_move=None, import_mask=None):
         """Overwrite games with preset positions (true coordinates, 0 BLACK / 1 WHITE / 2 EMPTY); labels are rebuilt in raster

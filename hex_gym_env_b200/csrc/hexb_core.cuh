@@ -118,6 +118,8 @@ struct Params {
     int out_hint;           // 1 = the obs / mask stores also carry an explicit L2 evict_first policy (off; HEXB_L2_OUT_HINT=1 turns it on)
     long long keep_chunks;  // chunks [0, keep_chunks) are kept in L2 between steps (evict_last), the others streamed (evict_first)
     uint32_t one;  // always 1, but opaque to the compiler: a * one + b is issued as IMAD on the FMA pipe (see fma_add)
+    int obs_f32;   // 1: obs / term_obs point to float32 buffers (hexb_config.obs_dtype = HEXB_OBS_F32: the reference's observation
+                   // is a float array, HexSingleGame.py:175, and SB3's policies take float32), 0: int8
     // borrowed I/O (device pointers, any may be null unless noted)
     const int32_t *actions;    // [G]   null => sample the agent's move on device (one draw)
     const double *opp_u;       // [G,2] null => Philox stream
@@ -435,6 +437,12 @@ HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &m
     if (b == 0u) return 0u;
     const bool own = ((b >> 7) != 0u) == opp_view;  // R is "own" in the agent's view, C in the opponent's
     return own ? 0xffu : 0x01u;
+}
+
+// one observation cell into the caller's buffer in its dtype (the per-cell paths: terminal observations, opponent views, K5)
+HEXB_HD void store_obs(int8_t *obs, int obs_f32, long long i, uint32_t byte) {
+    if (obs_f32) reinterpret_cast<float *>(obs)[i] = (float)(int8_t)byte;
+    else obs[i] = (int8_t)byte;
 }
 
 // ----------------------------------------------------------------------------------------------

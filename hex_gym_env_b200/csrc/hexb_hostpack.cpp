@@ -1,0 +1,244 @@
+// hexb_hostpack.cpp - host half of hexb_step_host_packed (include/hexb.h): expands the 2-bit observation transport into the
+// API's int8 obs[G,N,N] and uint8 mask[G,N*N] host arrays on a small pool of host threads.
+//
+// Why it exists: with HOST buffers the step is bound by the device->host path (obs + mask = 2*N*N bytes per game and step,
+// 259 MB per 1 Mi-game 11x11 step at ~53 GB/s). Two bits per cell carry the same information (the mask is `cell empty`), so
+// 8x fewer bytes cross PCIe and host cores write the API's arrays instead of the DMA engine. Whether that is faster depends on
+// the host (profiles/r2*_e2e_packed.json has the A/B at 1 and 8 GPUs).
+//
+// Plain C++ (g++), no CUDA: 16 cells per packed word, cell i of the flat [G*N*N] order in bits 2*(i%16).. of word i/16,
+// code = obs byte & 3 (variant B: -1/0/+1 -> 3/0/1; variant A: BLACK 0, WHITE 1, EMPTY 2).
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace {
+
+struct Job {
+    const uint32_t *packed;
+    long long first, count, cells;
+    int variant;
+    int8_t *obs;
+    uint8_t *mask;
+};
+
+// ---- one worker's share: words [w0, w1) of the job
+void expand_scalar(const Job &j, long long w0, long long w1) {
+    // byte-wise LUT: 4 cells per packed byte
+    static uint32_t lut_obs[2][256], lut_msk[2][256];
+    static int ready = 0;
+    if (!__atomic_load_n(&ready, __ATOMIC_ACQUIRE)) {
+        for (int v = 0; v < 2; ++v)
+            for (int b = 0; b < 256; ++b) {
+                uint32_t o = 0, m = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t c = (b >> (2 * k)) & 3u;
+                    const uint32_t ob = v == 1 ? (c == 3u ? 0xffu : c) : c;          // variant B: code 3 is -1
+                    const uint32_t mk = v == 1 ? (c == 0u) : (c == 2u);              // legal == empty
+                    o |= ob << (8 * k);
+                    m |= mk << (8 * k);
+                }
+                lut_obs[v][b] = o;
+                lut_msk[v][b] = m;
+            }
+        __atomic_store_n(&ready, 1, __ATOMIC_RELEASE);   // racing initialisers write identical tables
+    }
+    const uint32_t *lo = lut_obs[j.variant ? 1 : 0], *lm = lut_msk[j.variant ? 1 : 0];
+    for (long long w = w0; w < w1; ++w) {
+        const uint32_t x = j.packed[w];
+        const long long c0 = 16 * w;
+        if (c0 + 16 <= j.cells) {
+            uint32_t *po = reinterpret_cast<uint32_t *>(j.obs + c0), *pm = reinterpret_cast<uint32_t *>(j.mask + c0);
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t b = (x >> (8 * k)) & 0xffu, o = lo[b], m = lm[b];
+                memcpy(po + k, &o, 4);
+                memcpy(pm + k, &m, 4);
+            }
+        } else {
+            for (int k = 0; k < 16 && c0 + k < j.cells; ++k) {
+                const uint32_t c = (x >> (2 * k)) & 3u;
+                j.obs[c0 + k] = (int8_t)(j.variant ? (c == 3u ? -1 : (int)c) : (int)c);
+                j.mask[c0 + k] = (uint8_t)(j.variant ? (c == 0u) : (c == 2u));
+            }
+        }
+    }
+}
+
+#if defined(__x86_64__)
+// 32 cells (two packed words) per iteration: bytes are spread with PSHUFB, the 2-bit field of each byte position is isolated
+// with 16-bit shifts, and two 16-entry PSHUFB tables map code -> obs byte and code -> mask byte. Results leave the core with
+// non-temporal stores when the destination is 32-byte aligned (nothing reads them back here).
+__attribute__((target("avx2"))) void expand_avx2(const Job &j, long long w0, long long w1) {
+    const __m256i spread = _mm256_setr_epi8(0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7);
+    const __m256i three = _mm256_set1_epi8(3);
+    const __m256i sel0 = _mm256_set1_epi32(0x000000ff), sel1 = _mm256_set1_epi32(0x0000ff00), sel2 = _mm256_set1_epi32(0x00ff0000);
+    const __m256i tab_obs = j.variant ? _mm256_setr_epi8(0, 1, 2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+                                      : _mm256_setr_epi8(0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i tab_msk = j.variant ? _mm256_setr_epi8(1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+                                      : _mm256_setr_epi8(0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+    long long w = w0;
+    if ((w & 1) && w < w1) { expand_scalar(j, w, w + 1); ++w; }   // keep the 32-cell groups 32-byte aligned relative to cell 0
+    const bool nt = ((((uintptr_t)j.obs) | ((uintptr_t)j.mask)) & 31) == 0;
+    for (; w + 2 <= w1 && 16 * (w + 2) <= j.cells; w += 2) {
+        uint64_t x;
+        memcpy(&x, j.packed + w, 8);
+        const __m128i lo = _mm_cvtsi64_si128((long long)x);
+        // both 128-bit lanes get the 8 packed bytes; lane 0 uses bytes 0-3, lane 1 bytes 4-7
+        const __m256i v = _mm256_shuffle_epi8(_mm256_broadcastsi128_si256(lo), spread);
+        const __m256i t0 = _mm256_and_si256(v, three);
+        const __m256i t1 = _mm256_and_si256(_mm256_srli_epi16(v, 2), three);
+        const __m256i t2 = _mm256_and_si256(_mm256_srli_epi16(v, 4), three);
+        const __m256i t3 = _mm256_and_si256(_mm256_srli_epi16(v, 6), three);
+        // byte position p of every 4-byte group takes t_p
+        const __m256i code = _mm256_or_si256(_mm256_or_si256(_mm256_and_si256(t0, sel0), _mm256_and_si256(t1, sel1)),
+                                             _mm256_or_si256(_mm256_and_si256(t2, sel2), _mm256_andnot_si256(_mm256_or_si256(_mm256_or_si256(sel0, sel1), sel2), t3)));
+        const __m256i o = _mm256_shuffle_epi8(tab_obs, code), m = _mm256_shuffle_epi8(tab_msk, code);
+        const long long c0 = 16 * w;
+        if (nt) {
+            _mm256_stream_si256(reinterpret_cast<__m256i *>(j.obs + c0), o);
+            _mm256_stream_si256(reinterpret_cast<__m256i *>(j.mask + c0), m);
+        } else {
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(j.obs + c0), o);
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(j.mask + c0), m);
+        }
+    }
+    if (nt) _mm_sfence();
+    if (w < w1) expand_scalar(j, w, w1);
+}
+#endif
+
+void expand_range(const Job &j, long long w0, long long w1) {
+#if defined(__x86_64__)
+    static const int have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) { expand_avx2(j, w0, w1); return; }
+#endif
+    expand_scalar(j, w0, w1);
+}
+
+// ---- a persistent pool: workers sleep on a condition variable between jobs
+struct Pool {
+    pthread_mutex_t mu;
+    pthread_cond_t cv_work, cv_done;
+    int nthreads, started;
+    unsigned long long generation;
+    int remaining;
+    Job job;
+    pthread_t th[64];
+};
+Pool g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, 0, 0, {}, {}};
+pthread_mutex_t g_submit = PTHREAD_MUTEX_INITIALIZER;   // one job at a time (several handles / host threads may call in)
+
+void share(const Job &j, int k, int n, long long &w0, long long &w1) {
+    // contiguous shares, boundaries on even words so that every share starts 32-byte aligned in the outputs
+    const long long per = ((j.count + n - 1) / n + 1) & ~1ll;
+    w0 = j.first + per * k;
+    w1 = w0 + per;
+    const long long end = j.first + j.count;
+    if (w0 > end) w0 = end;
+    if (w1 > end) w1 = end;
+}
+
+void *worker(void *arg) {
+    const int k = (int)(intptr_t)arg;
+    unsigned long long seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv_work, &g_pool.mu);
+        seen = g_pool.generation;
+        const Job j = g_pool.job;
+        const int n = g_pool.nthreads;
+        pthread_mutex_unlock(&g_pool.mu);
+        long long w0, w1;
+        share(j, k, n, w0, w1);
+        if (w1 > w0) expand_range(j, w0, w1);
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.remaining == 0) pthread_cond_signal(&g_pool.cv_done);
+    }
+    return nullptr;
+}
+
+int pool_threads() {
+    int n = 0;
+    const char *e = getenv("HEXB_HOST_THREADS");
+    if (e) n = atoi(e);
+    if (n <= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+    }
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    return n;
+}
+
+void after_fork_in_child() {   // threads do not survive fork(): the child starts its own pool on first use
+    g_pool.started = 0;
+    g_pool.nthreads = 0;
+    g_pool.generation = 0;
+    g_pool.remaining = 0;
+    pthread_mutex_init(&g_pool.mu, nullptr);
+    pthread_cond_init(&g_pool.cv_work, nullptr);
+    pthread_cond_init(&g_pool.cv_done, nullptr);
+    pthread_mutex_init(&g_submit, nullptr);
+}
+
+void pool_start() {   // called with g_submit held
+    if (g_pool.started) return;
+    static int atfork_set = 0;
+    if (!atfork_set) {
+        pthread_atfork(nullptr, nullptr, after_fork_in_child);
+        atfork_set = 1;
+    }
+    g_pool.nthreads = pool_threads();
+    // worker 0's share is run by the calling thread; the others are spawned once and live for the process
+    for (int k = 1; k < g_pool.nthreads; ++k) {
+        if (pthread_create(&g_pool.th[k], nullptr, worker, (void *)(intptr_t)k) != 0) {
+            g_pool.nthreads = k;
+            break;
+        }
+        pthread_detach(g_pool.th[k]);
+    }
+    g_pool.started = 1;
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("hidden"))) int hexb_hostpack_threads(void) {
+    pthread_mutex_lock(&g_submit);
+    pool_start();
+    const int n = g_pool.nthreads;
+    pthread_mutex_unlock(&g_submit);
+    return n;
+}
+
+// Expand packed words [first_word, first_word + n_words) into obs / mask (whole arrays' base pointers; n_cells = G*N*N).
+extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_expand(const uint32_t *packed, long long first_word, long long n_words,
+                                                                            long long n_cells, int variant, int8_t *obs, uint8_t *mask) {
+    pthread_mutex_lock(&g_submit);
+    pool_start();
+    Job j = {packed, first_word, n_words, n_cells, variant, obs, mask};
+    const int n = g_pool.nthreads;
+    if (n > 1) {
+        pthread_mutex_lock(&g_pool.mu);
+        g_pool.job = j;
+        g_pool.remaining = n - 1;
+        g_pool.generation++;
+        pthread_cond_broadcast(&g_pool.cv_work);
+        pthread_mutex_unlock(&g_pool.mu);
+    }
+    long long w0, w1;
+    share(j, 0, n, w0, w1);
+    if (w1 > w0) expand_range(j, w0, w1);
+    if (n > 1) {
+        pthread_mutex_lock(&g_pool.mu);
+        while (g_pool.remaining != 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+        pthread_mutex_unlock(&g_pool.mu);
+    }
+    pthread_mutex_unlock(&g_submit);
+}

@@ -462,6 +462,18 @@ HEXB_HD int pick_row(uint32_t &pp, int sg) {
     return mine;
 }
 
+// position of the k-th (0-based) set bit of m, -1 if m has fewer (the cooperative kernel hands the k-th pending row to lane group k)
+HEXB_HD int kth_set_bit32(uint32_t m, int k) {
+    if (k >= popc32(m)) return -1;
+    int pos = 0, c;
+    c = popc32(m & 0xffffu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
+    c = popc32(m & 0xffu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
+    c = popc32(m & 0xfu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
+    c = popc32(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
+    c = (int)(m & 1u);       if (k >= c) { pos += 1; }
+    return pos;
+}
+
 // One lane's share of one pass: sub-lane sl of the group that owns `row` applies the row's n pairs to its WPL words
 // (regions[regions == label] = new_region_label, HexGame.py:141-142, HexSingleGame.py:152-153, for both plies of the step).
 template <int N>
@@ -523,7 +535,7 @@ HEXB_HD void term_row_lane(const uint8_t *chunk, int r, uint32_t flg, const Para
     for (int c = lane; c < C; c += kWarp) {
         uint32_t mk;
         const uint32_t b = Lg[opp ? transpose_cell<N>(c) : c];
-        P.term_obs[g * C + c] = (int8_t)encode_byte(b, P.variant, opp, mk);
+        store_obs(P.term_obs, P.obs_f32, g * C + c, encode_byte(b, P.variant, opp, mk));
     }
 }
 
@@ -535,7 +547,7 @@ HEXB_HD void view_row_lane(const uint8_t *chunk, int r, const Params &P, long lo
     for (int c = lane; c < C; c += kWarp) {
         uint32_t mk;
         const uint32_t ob = encode_byte(Lg[transpose_cell<N>(c)], P.variant, true, mk);
-        if (P.obs) P.obs[g * C + c] = (int8_t)ob;
+        if (P.obs) store_obs(P.obs, P.obs_f32, g * C + c, ob);
         if (P.mask) P.mask[g * C + c] = (uint8_t)mk;
     }
 }

@@ -12,7 +12,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 
-#include "../../include/hexb.h"
+#include "../include/hexb.h"
 
 namespace {
 
@@ -53,6 +53,7 @@ struct Call {
     int64_t G, C;
     c10::cuda::CUDAGuard guard;
     void *stream;
+    c10::ScalarType obs_t() const { return c.obs_dtype == HEXB_OBS_F32 ? at::kFloat : at::kChar; }   // hexb_config.obs_dtype
     explicit Call(int64_t handle) : e(env_of(handle)), c(config_of(e)), G(c.num_games), C((int64_t)c.board_size * c.board_size), guard(c.device) {
         stream = at::cuda::getCurrentCUDAStream(c.device).stream();
     }
@@ -62,7 +63,7 @@ void op_reset(int64_t handle, OptT reset_mask, OptT open_u, OptT obs, OptT mask)
     Call k(handle);
     const int d = k.c.device;
     check_rc(hexb_reset(k.e, ptr<const uint8_t>(reset_mask, at::kByte, k.G, d, "reset_mask"), ptr<const double>(open_u, at::kDouble, k.G, d, "open_u"),
-                        ptr<int8_t>(obs, at::kChar, k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, k.G * k.C, d, "mask"), k.stream),
+                        ptr<void>(obs, k.obs_t(), k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, k.G * k.C, d, "mask"), k.stream),
              "reset");
 }
 
@@ -70,9 +71,9 @@ void op_step(int64_t handle, OptT actions, OptT opp_u, OptT obs, OptT mask, OptT
     Call k(handle);
     const int d = k.c.device;
     check_rc(hexb_step(k.e, ptr<const int32_t>(actions, at::kInt, k.G, d, "actions"), ptr<const double>(opp_u, at::kDouble, 2 * k.G, d, "opp_u"),
-                       ptr<int8_t>(obs, at::kChar, k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, k.G * k.C, d, "mask"),
+                       ptr<void>(obs, k.obs_t(), k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, k.G * k.C, d, "mask"),
                        ptr<float>(reward, at::kFloat, k.G, d, "reward"), ptr<uint8_t>(done, at::kByte, k.G, d, "done"),
-                       ptr<int8_t>(term_obs, at::kChar, k.G * k.C, d, "term_obs"), ptr<int32_t>(actions_out, at::kInt, k.G, d, "actions_out"),
+                       ptr<void>(term_obs, k.obs_t(), k.G * k.C, d, "term_obs"), ptr<int32_t>(actions_out, at::kInt, k.G, d, "actions_out"),
                        k.stream),
              "step");
 }
@@ -82,9 +83,9 @@ void op_rollout(int64_t handle, int64_t num_steps, OptT obs, OptT mask, OptT rew
     const int d = k.c.device;
     TORCH_CHECK(num_steps >= 1 && num_steps <= 65536, "hexb::rollout: num_steps out of range");
     const int64_t T = num_steps;
-    check_rc(hexb_rollout(k.e, (int32_t)T, ptr<int8_t>(obs, at::kChar, T * k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, T * k.G * k.C, d, "mask"),
+    check_rc(hexb_rollout(k.e, (int32_t)T, ptr<void>(obs, k.obs_t(), T * k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, T * k.G * k.C, d, "mask"),
                           ptr<float>(reward, at::kFloat, T * k.G, d, "reward"), ptr<uint8_t>(done, at::kByte, T * k.G, d, "done"),
-                          ptr<int8_t>(term_obs, at::kChar, T * k.G * k.C, d, "term_obs"),
+                          ptr<void>(term_obs, k.obs_t(), T * k.G * k.C, d, "term_obs"),
                           ptr<int32_t>(actions_out, at::kInt, T * k.G, d, "actions_out"), k.stream),
              "rollout");
 }
@@ -93,7 +94,7 @@ void op_half_step(int64_t handle, int64_t side, OptT actions, OptT reward, OptT 
     Call k(handle);
     const int d = k.c.device;
     check_rc(hexb_half_step(k.e, (int32_t)side, ptr<const int32_t>(actions, at::kInt, k.G, d, "actions"), ptr<float>(reward, at::kFloat, k.G, d, "reward"),
-                            ptr<uint8_t>(done, at::kByte, k.G, d, "done"), ptr<int8_t>(term_obs, at::kChar, k.G * k.C, d, "term_obs"), k.stream),
+                            ptr<uint8_t>(done, at::kByte, k.G, d, "done"), ptr<void>(term_obs, k.obs_t(), k.G * k.C, d, "term_obs"), k.stream),
              "half_step");
 }
 
@@ -106,7 +107,7 @@ void op_ply(int64_t handle, const Tensor &actions, OptT ret) {
 void op_encode(int64_t handle, int64_t view, OptT obs, OptT mask) {
     Call k(handle);
     const int d = k.c.device;
-    check_rc(hexb_encode(k.e, (int32_t)view, ptr<int8_t>(obs, at::kChar, k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, k.G * k.C, d, "mask"), k.stream),
+    check_rc(hexb_encode(k.e, (int32_t)view, ptr<void>(obs, k.obs_t(), k.G * k.C, d, "obs"), ptr<uint8_t>(mask, at::kByte, k.G * k.C, d, "mask"), k.stream),
              "encode");
 }
 
@@ -135,6 +136,22 @@ void op_masked_sample(const Tensor &logits, const Tensor &mask, const Tensor &u,
              "masked_sample");
 }
 
+void op_gae(const Tensor &rewards, const Tensor &values, const Tensor &dones, double gamma, double gae_lambda, Tensor advantages, OptT returns) {
+    TORCH_CHECK(rewards.is_cuda() && rewards.dim() == 2, "hexb::gae: rewards must be a CUDA tensor [T,G]");
+    const int d = rewards.get_device();
+    const int64_t T = rewards.size(0), G = rewards.size(1);
+    c10::cuda::CUDAGuard guard(d);
+    check_rc(hexb_gae(ptr<const float>(rewards, at::kFloat, T * G, d, "rewards"), ptr<const float>(values, at::kFloat, (T + 1) * G, d, "values"),
+                      ptr<const uint8_t>(dones, at::kByte, T * G, d, "dones"), (int32_t)T, G, gamma, gae_lambda,
+                      ptr<float>(advantages, at::kFloat, T * G, d, "advantages"), ptr<float>(returns, at::kFloat, T * G, d, "returns"), d,
+                      at::cuda::getCurrentCUDAStream(d).stream()),
+             "gae");
+}
+
+void op_set_launch_form(int64_t handle, int64_t warps_per_chunk) {
+    check_rc(hexb_set_launch_form(env_of(handle), (int32_t)warps_per_chunk), "set_launch_form");
+}
+
 int64_t op_version() { return hexb_version(); }
 
 }  // namespace
@@ -152,6 +169,8 @@ TORCH_LIBRARY(hexb, m) {
     m.def("sample_actions(int env, int view, Tensor u, Tensor(a!) actions_out) -> ()");
     m.def("stats(int env, Tensor(a!) out8) -> ()");
     m.def("masked_sample(Tensor logits, Tensor mask, Tensor u, Tensor(a!)? actions, Tensor(b!)? logp, Tensor(c!)? entropy) -> ()");
+    m.def("gae(Tensor rewards, Tensor values, Tensor dones, float gamma, float gae_lambda, Tensor(a!) advantages, Tensor(b!)? returns) -> ()");
+    m.def("set_launch_form(int env, int warps_per_chunk) -> ()", &op_set_launch_form);
 }
 
 // The handle is an int, so these operators have no tensor argument to dispatch on when every optional is None: register them
@@ -166,4 +185,5 @@ TORCH_LIBRARY_IMPL(hexb, CompositeExplicitAutograd, m) {
     m.impl("sample_actions", &op_sample_actions);
     m.impl("stats", &op_stats);
     m.impl("masked_sample", &op_masked_sample);
+    m.impl("gae", &op_gae);
 }

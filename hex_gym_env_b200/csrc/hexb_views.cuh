@@ -10,6 +10,7 @@ struct View {
     const uint8_t *state;
     long long G, Gpad;
     int N, variant, raw;
+    int obs_f32;   // dtype of the obs buffer handed to encode_at (hexb_config.obs_dtype)
 };
 HEXB_HD const uint32_t *view_rec(const View &V, long long g) {
     return reinterpret_cast<const uint32_t *>(V.state + rec_offset(g, V.N * V.N));
@@ -38,7 +39,7 @@ HEXB_HD void encode_at(const View &V, int view, long long i, int8_t *obs, uint8_
     const uint32_t b = view_labels(V, g)[opp ? x * V.N + y : c];
     uint32_t mk;
     const uint32_t ob = encode_byte(b, V.variant, opp, mk);
-    if (obs) obs[i] = (int8_t)ob;
+    if (obs) store_obs(obs, V.obs_f32, i, ob);
     if (mask) mask[i] = (uint8_t)mk;
 }
 

@@ -40,14 +40,39 @@ def masked_sample(logits, mask, u=None, generator=None, want_entropy=False):
     return (actions, logp, ent) if want_entropy else (actions, logp)
 
 
+def gae(rewards, values, dones, gamma=0.99, gae_lambda=0.95, advantages=None, returns=None):
+    """GAE(lambda) of a [T,G] rollout in ONE kernel (hexb_gae, thread per game, backward over T) - what SB3's
+    RolloutBuffer.compute_returns_and_advantage computes. rewards f32[T,G], values f32[T+1,G], dones u8[T,G] (the episode ended
+    in step t). Returns (advantages f32[T,G], returns f32[T,G]), written into the given tensors when passed."""
+    if not rewards.is_cuda:
+        raise RuntimeError("gae runs on the GPU only (no CPU fallback)")
+    T, G = rewards.shape
+    dev = rewards.device
+    for name, t, shape, dt in (("rewards", rewards, (T, G), torch.float32), ("values", values, (T + 1, G), torch.float32),
+                               ("dones", dones, (T, G), torch.uint8)):
+        if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or t.device != dev:
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s" % (name, dt, shape, dev))
+    advantages = torch.empty((T, G), dtype=torch.float32, device=dev) if advantages is None else advantages
+    returns = torch.empty((T, G), dtype=torch.float32, device=dev) if returns is None else returns
+    for name, t in (("advantages", advantages), ("returns", returns)):
+        if tuple(t.shape) != (T, G) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+            raise ValueError("%s must be a contiguous float32 tensor of shape %s on %s" % (name, (T, G), dev))
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        check(_native.lib().hexb_gae(p(rewards), p(values), p(dones), T, G, float(gamma), float(gae_lambda), p(advantages), p(returns),
+                                     dev.index, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return advantages, returns
+
+
 class RolloutBuffer(object):
-    """[T, G] rollout storage on the device in MaskableRolloutBuffer's layout. Observations are kept as the int8 bytes the
-    step kernel emits (obs_f32() converts a slice for the network)."""
+    """[T, G] rollout storage on the device in MaskableRolloutBuffer's layout. Observations have the batch's obs_dtype: create
+    the HexBatch with obs_dtype=torch.float32 and the step kernel writes the float32 observations the policy network reads
+    (SB3's buffer is float32 too), with int8 they are the bytes the kernel computes in and the policy call converts."""
 
     def __init__(self, n_steps, batch: HexBatch, gamma=0.99, gae_lambda=0.95):
         T, G, N, C, dev = n_steps, batch.G, batch.N, batch.C, batch.device
         self.T, self.G, self.gamma, self.gae_lambda = T, G, gamma, gae_lambda
-        self.obs = torch.zeros((T + 1, G, N, N), dtype=torch.int8, device=dev)       # slot T = the observation after the last step
+        self.obs = torch.zeros((T + 1, G, N, N), dtype=batch.obs_dtype, device=dev)  # slot T = the observation after the last step
         self.action_masks = torch.zeros((T + 1, G, C), dtype=torch.uint8, device=dev)
         self.actions = torch.zeros((T, G), dtype=torch.int32, device=dev)
         self.rewards = torch.zeros((T, G), dtype=torch.float32, device=dev)
@@ -59,7 +84,11 @@ class RolloutBuffer(object):
         self.returns = torch.zeros((T, G), dtype=torch.float32, device=dev)
 
     def compute_returns_and_advantage(self):
-        """GAE(lambda) exactly as SB3's RolloutBuffer: a finished episode (auto-reset) cuts the bootstrap."""
+        """GAE(lambda) exactly as SB3's RolloutBuffer: a finished episode (auto-reset) cuts the bootstrap. One hexb_gae launch."""
+        gae(self.rewards, self.values, self.dones, self.gamma, self.gae_lambda, self.advantages, self.returns)
+
+    def compute_returns_and_advantage_torch(self):
+        """The same recurrence as T eager PyTorch steps: the float32 reference hexb_gae is tested against (tests/test_gpu_rollout.py)."""
         last = torch.zeros(self.G, dtype=torch.float32, device=self.values.device)
         for t in reversed(range(self.T)):
             nonterminal = 1.0 - self.episode_starts[t + 1]

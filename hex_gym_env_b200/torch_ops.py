@@ -30,7 +30,7 @@ def build(force=False):
     import torch
     from torch.utils import cpp_extension as ce
     base = _native.build()
-    deps = [SRC, os.path.join(os.path.dirname(_HERE), "include", "hexb.h")]
+    deps = [SRC, _native.HEADER]
 
     def stale():
         return (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)

@@ -146,7 +146,7 @@ class HexVecEnv(_VecEnvBase):
         """One env step in sample_board mode, in the reference's order: agent ply -> (finished: new sampled board) ->
         opponent reply / opening -> (finished: new sampled board) -> opening."""
         b = self.batch
-        term = b._buf("sb_term", (b.G, b.N, b.N), torch.int8)
+        term = b._buf("sb_term", (b.G, b.N, b.N), b.obs_dtype)
         h = b.half_step(0, actions, term_obs=term)
         reward, done = h["reward"].clone(), h["done"].clone()
         self._restart_on_sampled_boards(h["done"])

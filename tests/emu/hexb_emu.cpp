@@ -148,6 +148,7 @@ static View view_of(const emu_env *e) {
     V.N = e->N;
     V.variant = e->base.variant;
     V.raw = e->base.raw;
+    V.obs_f32 = 0;
     return V;
 }
 

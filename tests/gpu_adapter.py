@@ -8,13 +8,20 @@ from oracle import hexref
 
 
 class GpuBatch(object):
-    def __init__(self, variant, N, G, **kw):
-        self.b = HexBatch(N, G, variant=variant, device=0, **kw)
+    def __init__(self, variant, N, G, launch_form=0, obs_f32=False, **kw):
+        self.b = HexBatch(N, G, variant=variant, device=0, obs_dtype=torch.float32 if obs_f32 else torch.int8, **kw)
+        if launch_form:
+            self.b.set_launch_form(launch_form)   # 1 / 2 / 4 / 8 warps per chunk instead of the depth-based choice
         self.N, self.G = N, G
 
     @staticmethod
     def _np(t):
-        return t.cpu().numpy()
+        a = t.cpu().numpy()
+        if a.dtype == np.float32 and a.ndim >= 3:   # float32 observations (obs_dtype f32) hold the same small integers
+            b = a.astype(np.int8)
+            assert np.array_equal(b.astype(np.float32), a), "float32 observation with a non-integer value"
+            return b
+        return a
 
     def reset(self, reset_mask=None, open_u=None):
         obs, mask = self.b.reset(reset_mask, open_u)
@@ -22,13 +29,13 @@ class GpuBatch(object):
 
     def step(self, actions=None, opp_u=None, want_term=False):
         if want_term:
-            self.b._buf("term_obs", (self.G, self.N, self.N), torch.int8).zero_()
+            self.b._buf("term_obs", (self.G, self.N, self.N), self.b.obs_dtype).zero_()
         o = self.b.step(actions, opp_u, want_term=want_term, want_actions=True)
         return {k: self._np(v) for k, v in o.items()}
 
     def half_step(self, side, actions, want_term=False):
         if want_term:
-            self.b._buf("term_obs", (self.G, self.N, self.N), torch.int8).zero_()
+            self.b._buf("term_obs", (self.G, self.N, self.N), self.b.obs_dtype).zero_()
         o = self.b.half_step(side, actions, want_term=want_term)
         out = {k: self._np(v) for k, v in o.items()}
         out["to_move"], out["opp_index"] = self.opp_state()
@@ -36,7 +43,7 @@ class GpuBatch(object):
 
     def rollout(self, T, want_term=False):
         G, N = self.G, self.N
-        term = torch.zeros((T, G, N, N), dtype=torch.int8, device="cuda") if want_term else None
+        term = torch.zeros((T, G, N, N), dtype=self.b.obs_dtype, device="cuda") if want_term else None
         acts = torch.empty((T, G), dtype=torch.int32, device="cuda")
         o = self.b.rollout(T, term_obs=term, actions_out=acts)
         return {k: self._np(v) for k, v in o.items()}
@@ -79,9 +86,20 @@ class GpuBatch(object):
 
 
 def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, auto_reset=True, eval_state=False,
-         manual_opponent=False, pool_size=0):
+         manual_opponent=False, pool_size=0, launch_form=0, obs_f32=False):
     if kind == hexref.KIND_GAME_A:
         return GpuBatch(0, N, G, raw=True)
     variant = 0 if kind == hexref.KIND_ENV_A else 1
     return GpuBatch(variant, N, G, seed=seed, game_offset=game_offset, agent_mode=agent_mode, opponent_first=opponent_first,
-                    auto_reset=auto_reset, eval_state=eval_state, manual_opponent=manual_opponent, pool_size=pool_size)
+                    auto_reset=auto_reset, eval_state=eval_state, manual_opponent=manual_opponent, pool_size=pool_size,
+                    launch_form=launch_form, obs_f32=obs_f32)
+
+
+def make_with(**fixed):
+    """`make` with some keyword arguments pinned (launch_form=..., obs_f32=...): the drivers in tests/parity.py pass the rest."""
+    def mk(kind, N, G, **kw):
+        kw.update(fixed)
+        if kind == hexref.KIND_GAME_A:
+            return make(kind, N, G)
+        return make(kind, N, G, **kw)
+    return mk

@@ -24,8 +24,15 @@ top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
 
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-    cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True, check=True).stdout.split("\n")
+    dis = None
+    for cubin in sorted(glob.glob(os.path.join(tmp, "*.cubin"))):   # one cubin per object file: find the one with the kernel
+        syms = subprocess.run(["cuobjdump", "-elf", cubin], stdout=subprocess.PIPE, text=True).stdout
+        if kernel in syms:
+            dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True, check=True).stdout.split("\n")
+            if any(l.startswith(kernel + ":") for l in dis):
+                break
+            dis = None
+    assert dis is not None, "kernel %s not found in %s" % (kernel, so)
 start = next(i for i, l in enumerate(dis) if l.startswith(kernel + ":"))
 loc, seq = None, []
 for l in dis[start + 1:]:
@@ -65,7 +72,7 @@ for (off, lc), r in zip(seq, data):
     tot_s += int(r[isamp])
 src = {}
 for f in os.listdir(srcdir):
-    if f.endswith((".cu", ".cuh")):
+    if f.endswith((".cu", ".cuh", ".h")):
         src[f] = open(os.path.join(srcdir, f)).read().split("\n")
 
 
@@ -75,7 +82,7 @@ def func_of(f, ln):
     L = src[f]
     for i in range(ln - 1, -1, -1):
         if re.match(r"^(HEXB_HD|__device__|__global__|static)", L[i]) and "(" in L[i]:
-            m = re.search(r"(\w+)\s*\(", L[i].replace("__launch_bounds__(kCtaThreads, min_ctas(N))", ""))
+            m = re.search(r"(\w+)\s*\(", re.sub(r"__launch_bounds__\([^)]*\)+", "", L[i]))
             return m.group(1) if m else L[i]
     return "?"
 
