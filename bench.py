@@ -428,7 +428,7 @@ def run_gpu(args):
 
     # ------------------------------------------------ end-to-end leg: host actions in, host obs/mask/reward/done out
     E = min(K, args.e2e_steps)
-    Ew = 3
+    Ew = 8     # untimed: also lets the adaptive transport split settle
     # (untimed) record a legal random trajectory on the device so that the timed loop replays HOST actions
     rec = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                    auto_reset=True)
@@ -444,34 +444,51 @@ def run_gpu(args):
     torch.cuda.synchronize()
     rec.close()
     del rec
-    env = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
-                   auto_reset=True)
-    env.reset()
-    io = env.pinned_io()
-    for t in range(Ew):
-        io["actions"].copy_(host_actions[t])
-        env.step_host(io["actions"], io)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    checksum = 0.0
-    for t in range(Ew, Ew + E):
-        io["actions"].copy_(host_actions[t])           # this step's inputs, host memory
-        env.step_host(io["actions"], io)               # H2D + kernel + D2H, returns with results in host memory
-        checksum += float(io["reward"][0])             # host read of the step's result
-    e1.record()
-    barrier()
-    e2e_rank = gather_ms(e0.elapsed_time(e1))
-    e2e_ms = max(e2e_rank)
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    launches_e2e = E
-    invalid = int(env.stats().cpu()[5])
-    e2e = {"value": world * G * E / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * G,
-           "d2h_bytes_per_step": G * (2 * N * N + 5), "steps": E, "ms_per_step": e2e_ms / E, "wall_ms_per_step": wall_ms / E,
-           "api": "hexb_step_host (C ABI, pinned host buffers)", "illegal_moves_in_replay": invalid, "cpu_affinity": numa}
-    env.close()
-    del env
-    torch.cuda.empty_cache()
+    def e2e_leg(mode):
+        """E timed steps of the host-buffer call hexb_step_host. mode "adaptive" = the call as shipped (obs + mask of some games
+        as plain DMA copies, of the others as 2 bits per cell expanded by host threads, split adapted to the two measured rates);
+        "dma" = plain copies only (hexb_set_host_transport(1)); "packed" = 2-bit transport only (0)."""
+        env = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
+                       auto_reset=True)
+        env.reset()
+        if mode != "adaptive":
+            env.set_host_transport(1.0 if mode == "dma" else 0.0)
+        io = env.pinned_io()
+        for t in range(Ew):
+            io["actions"].copy_(host_actions[t])
+            env.step_host(io["actions"], io)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        checksum = 0.0
+        for t in range(Ew, Ew + E):
+            io["actions"].copy_(host_actions[t])           # this step's inputs, host memory
+            env.step_host(io["actions"], io)               # H2D + kernel + D2H, returns with results in host memory
+            checksum += float(io["reward"][0]) + float(io["obs"][G - 1, N - 1, N - 1]) + float(io["mask"][G - 1, N * N - 1])   # host reads of the step's results
+        e1.record()
+        barrier()
+        ms = max(gather_ms(e0.elapsed_time(e1)))
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        invalid = int(env.stats().cpu()[5])
+        f = env.host_transport()
+        gd = int(f * G + 0.5) // 32 * 32 if f < 1.0 else G
+        d2h = gd * 2 * N * N + ((G - gd) * N * N + 15) // 16 * 4 + 5 * G
+        out = {"value": world * G * E / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * G, "d2h_bytes_per_step": d2h, "steps": E,
+               "ms_per_step": ms / E, "wall_ms_per_step": wall_ms / E,
+               "api": "hexb_step_host (C ABI, pinned host buffers); transport %s: %.0f %% of the games' obs + mask as plain DMA, the rest as "
+                      "2 bits per cell expanded by %d host threads" % (mode, 100.0 * gd / G, env._lib.hexb_host_threads()),
+               "dma_fraction": f, "illegal_moves_in_replay": invalid, "cpu_affinity": numa, "checksum": checksum}
+        env.close()
+        del env
+        torch.cuda.empty_cache()
+        return out
+
+    legs = {m: e2e_leg(m) for m in ("dma", "packed", "adaptive")}
+    assert len({legs[m]["checksum"] for m in legs}) == 1, "the host transports returned different results"
+    e2e = dict(legs["adaptive"])         # the headline end-to-end number: the public call as shipped
+    for m in ("dma", "packed"):
+        e2e[m + "_only"] = {k: legs[m][k] for k in ("value", "ms_per_step", "d2h_bytes_per_step")}
+    launches_e2e = 2 * E
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",

@@ -46,12 +46,16 @@ def main():
                     help="random: BaseRandomPolicy inside the fused step kernel; self: a frozen copy of the policy, refreshed every "
                          "--refresh iterations, played through the split step (hexb_half_step), like the reference's OpponentPolicy pool")
     ap.add_argument("--refresh", type=int, default=4)
+    ap.add_argument("--obs-dtype", choices=["f32", "i8"], default="f32",
+                    help="f32: the step kernel writes float32 observations straight into the rollout buffer (hexb_config.obs_dtype); "
+                         "i8: int8 observations, converted for the network at every use")
     ap.add_argument("--graph", action="store_true", help="replay the whole rollout (policy forward + sampling + env step + GAE) as one CUDA graph")
     args = ap.parse_args()
     torch.manual_seed(args.seed)
     dev = torch.device("cuda", 0)
     env = HexBatch(args.board, args.games, variant=VARIANT_B, device=0, seed=args.seed, agent_mode=AGENT_RANDOM, auto_reset=True,
-                   manual_opponent=(args.opponent == "self"), pool_size=0)
+                   manual_opponent=(args.opponent == "self"), pool_size=0,
+                   obs_dtype=torch.float32 if args.obs_dtype == "f32" else torch.int8)
     policy = MlpPolicy(env.C).to(dev)
     frozen = MlpPolicy(env.C).to(dev)
     frozen.load_state_dict(policy.state_dict())

@@ -140,6 +140,8 @@ SYMBOLS = {
     "hexb_host_packed_bytes": (_sz, [_cfgp]),
     "hexb_step_host_packed": (_i32, [_vp] * 9),
     "hexb_host_threads": (_i32, []),
+    "hexb_set_host_transport": (_i32, [_vp, ctypes.c_double]),
+    "hexb_get_host_transport": (_i32, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "hexb_set_launch_form": (_i32, [_vp, _i32]),
     "hexb_gae": (_i32, [_vp, _vp, _vp, _i32, ctypes.c_int64, ctypes.c_double, ctypes.c_double, _vp, _vp, _i32, _vp]),
     "hexb_ply": (_i32, [_vp] * 4),
@@ -147,6 +149,7 @@ SYMBOLS = {
     "hexb_sample_actions": (_i32, [_vp, _i32, _vp, _vp, _vp]),
     "hexb_export_state": (_i32, [_vp] * 10),
     "hexb_import_boards": (_i32, [_vp] * 5),
+    "hexb_import_labels": (_i32, [_vp] * 6),
     "hexb_stats": (_i32, [_vp] * 3),
     "hexb_rollout": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hexb_set_opponent_buffers": (_i32, [_vp, _vp, _vp]),

@@ -234,6 +234,16 @@ class HexBatch(object):
         """0: the kernel form is chosen by launch depth; 1 / 2 / 4 / 8: that many warps per 32-game chunk (tuning, tests)."""
         check(self._lib.hexb_set_launch_form(self._h, int(warps_per_chunk)))
 
+    def set_host_transport(self, dma_fraction=-1.0):
+        """How step_host moves obs + mask: share of the games copied as plain bytes by DMA, the rest as 2 bits per cell expanded
+        by host threads. Negative = adaptive (default), 1.0 = plain DMA only, 0.0 = everything packed."""
+        check(self._lib.hexb_set_host_transport(self._h, float(dma_fraction)))
+
+    def host_transport(self):
+        f = ctypes.c_double()
+        check(self._lib.hexb_get_host_transport(self._h, ctypes.byref(f)))
+        return f.value
+
     def _host_ws(self):
         if self._ws is None:
             n = self._lib.hexb_host_workspace_bytes(ctypes.byref(self.cfg))
@@ -442,6 +452,16 @@ class HexBatch(object):
         im = self._in(import_mask, (self.G,), torch.uint8, "import_mask")
         with torch.cuda.device(self.device):
             check(self._lib.hexb_import_boards(self._h, _ptr(b), _ptr(tm), _ptr(im), self._stream()))
+
+    def import_labels(self, board_true, regions, to_move=None, import_mask=None):
+        """Overwrite games with preset positions AND their region-label planes (u8[G,2,N+2,N+2], the reference's layout), adopted
+        as they are with region_counter = max(plane) + 1: HexGame.__init__(connected_stones=...)."""
+        b = self._in(board_true, (self.G, self.N, self.N), torch.int8, "board_true")
+        r = self._in(regions, (self.G, 2, self.N + 2, self.N + 2), torch.uint8, "regions")
+        tm = self._in(to_move, (self.G,), torch.int8, "to_move")
+        im = self._in(import_mask, (self.G,), torch.uint8, "import_mask")
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_import_labels(self._h, _ptr(b), _ptr(r), _ptr(tm), _ptr(im), self._stream()))
 
     def opponent_catch_up(self):
         """Let the built-in random opponent move in every game where it is to move (after import_boards on an env handle):

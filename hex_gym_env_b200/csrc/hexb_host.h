@@ -16,8 +16,16 @@ struct hexb_env {
     hexb_config cfg;
     hexb::Params base;   // state pointers + config, I/O pointers null
     int launch_form;     // hexb_set_launch_form: 0 = chosen by launch depth, 1 / 2 / 4 / 8 = warps per 32-game chunk
-    cudaEvent_t host_ev; // hexb_step_host_begin / _end: completion of the step's device->host copies (created on first use)
-    int host_pending;
+    // ---- host-buffer step (hexb_step_host*): events, staging and the adaptive DMA / packed split
+    cudaEvent_t host_ev, host_ev_dma0, host_ev_slice[4];   // all copies done; start of the DMA part; each packed slice arrived
+    int host_pending, host_adapt, host_frac_fixed;
+    double host_dma_frac;          // share of the games whose obs / mask rows travel as plain bytes by DMA
+    double host_dma_bytes;
+    long long host_plan_words, host_plan_first, host_slice_lo[4], host_slice_hi[4];
+    uint32_t *host_packed;         // pinned staging of the packed words (cudaHostAlloc, owned by the handle)
+    const uint32_t *host_packed_src;
+    int8_t *host_obs;
+    uint8_t *host_mask;
 };
 
 HEXB_LOCAL int hexb_cuda_fail(cudaError_t e);   // records the code for hexb_last_cuda_error, returns HEXB_ERR_CUDA

@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "hexb_host.h"
 
@@ -33,6 +34,12 @@ __global__ void hexb_export_kernel(View V, double *board, double *regions, doubl
                                    int8_t *winner, int8_t *agent, uint32_t *draws) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < V.G * 2 * (V.N + 2) * (V.N + 2)) export_at(V, i, board, regions, counter, cur, done, winner, agent, draws);
+}
+
+__global__ void hexb_import_labels_kernel(Params P, int N, const int8_t *board_true, const uint8_t *planes, const int8_t *to_move,
+                                          const uint8_t *import_mask) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < P.G) import_labels_game(P, N, g, board_true, planes, to_move, import_mask);
 }
 
 __global__ void hexb_stats_kernel(const long long *src, int64_t *dst) {
@@ -293,6 +300,15 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
         const char *oh = getenv("HEXB_L2_OUT_HINT");
         P.out_hint = (P.keep_chunks > 0 && oh && atoi(oh) == 1) ? 1 : 0;
     }
+    {   // host-buffer step: adaptive DMA / packed split unless HEXB_HOST_DMA_FRACTION pins it (1 = plain DMA only)
+        const char *hf = getenv("HEXB_HOST_DMA_FRACTION");
+        e->host_dma_frac = 0.5;
+        if (hf) {
+            const double f = atof(hf);
+            if (f >= 0.0 && f <= 1.0) { e->host_dma_frac = f; e->host_frac_fixed = 1; }
+        }
+        if (hexb_hostpack_threads() < 1) { e->host_dma_frac = 1.0; e->host_frac_fixed = 1; }
+    }
     {
         const char *lf = getenv("HEXB_LAUNCH_FORM");   // experiments: the same override as hexb_set_launch_form, for every handle
         const int f = lf ? atoi(lf) : 0;
@@ -304,10 +320,13 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
 
 int32_t hexb_destroy(hexb_env *env) {
     if (!env) return HEXB_ERR_ARG;
+    if (env->host_ev || env->host_packed) cudaSetDevice(env->cfg.device);
     if (env->host_ev) {
-        cudaSetDevice(env->cfg.device);
         cudaEventDestroy(env->host_ev);
+        cudaEventDestroy(env->host_ev_dma0);
+        for (int k = 0; k < 4; ++k) cudaEventDestroy(env->host_ev_slice[k]);
     }
+    if (env->host_packed) cudaFreeHost(env->host_packed);
     free(env);
     return HEXB_OK;
 }
@@ -432,33 +451,151 @@ static HostWs carve_ws(const hexb_env *env, void *workspace) {
     return h;
 }
 
-int32_t hexb_step_host_begin(hexb_env *env, void *workspace, const int32_t *actions_host, void *obs_host, uint8_t *mask_host,
-                             float *reward_host, uint8_t *done_host, void *stream) {
-    if (!env || !workspace || env->cfg.raw || env->cfg.manual_opponent || env->host_pending) return HEXB_ERR_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t G = (size_t)env->cfg.num_games, C = (size_t)env->cfg.board_size * env->cfg.board_size;
+// How the observation + mask bytes of a host-buffer step travel. They are 2*N*N of the 2*N*N + 5 bytes per game a step returns,
+// and on the boxes this was measured on the device->host DMA path (~53 GB/s for one GPU, ~95 GB/s for all eight GPUs of a VM
+// together) and the host cores' own store bandwidth (~50 GB/s on 16 cores, ~130 GB/s on 32) are separate bottlenecks. So the
+// games of a step are split: the first `dma_games` games' obs / mask rows are copied as they are, the others cross PCIe as
+// 2 bits per cell (K10) and host threads expand them into the same arrays (hexb_hostpack.cpp) while the DMA runs. The split
+// adapts from call to call to the two measured rates; the bytes that arrive are identical for every split.
+struct HostPlan {
+    long long dma_games;      // games [0, dma_games) by DMA, [dma_games, G) packed
+    long long first_word;     // first packed word (16 cells each) of the packed part
+    long long words;          // number of packed words
+};
+static HostPlan plan_host(const hexb_env *env, double frac) {
+    const long long G = env->cfg.num_games, C = (long long)env->cfg.board_size * env->cfg.board_size;
+    HostPlan p;
+    long long gd = (long long)(frac * (double)G + 0.5);
+    gd = gd / 32 * 32;              // 32*C cells: a multiple of 16, so the packed part starts on a word (and 32-byte) boundary
+    if (gd > G) gd = G;
+    if (frac >= 1.0) gd = G;
+    if (gd < 0) gd = 0;
+    p.dma_games = gd;
+    p.first_word = gd * C / 16;
+    p.words = (G * C + 15) / 16 - p.first_word;
+    if (gd == G) p.words = 0;
+    return p;
+}
+
+enum { kHostSlices = 4 };
+
+static int host_events(hexb_env *env) {
+    if (env->host_ev) return HEXB_OK;
+    CK(cudaEventCreateWithFlags(&env->host_ev, cudaEventDefault));
+    CK(cudaEventCreateWithFlags(&env->host_ev_dma0, cudaEventDefault));
+    for (int k = 0; k < kHostSlices; ++k) CK(cudaEventCreateWithFlags(&env->host_ev_slice[k], cudaEventDisableTiming));
+    return HEXB_OK;
+}
+
+// Enqueue one host-buffer step. frac = share of the games whose obs / mask rows travel by DMA (1 = all, 0 = all packed).
+static int host_step_enqueue(hexb_env *env, void *workspace, uint32_t *packed_host, double frac, const int32_t *actions_host,
+                             void *obs_host, uint8_t *mask_host, float *reward_host, uint8_t *done_host, cudaStream_t s) {
+    const long long G = env->cfg.num_games, C = (long long)env->cfg.board_size * env->cfg.board_size;
     const HostWs h = carve_ws(env, workspace);
+    const size_t ob = obs_elem(env);
     CK(cudaSetDevice(env->cfg.device));
-    if (!env->host_ev) CK(cudaEventCreateWithFlags(&env->host_ev, cudaEventDisableTiming));
-    if (actions_host) CK(cudaMemcpyAsync(h.act, actions_host, G * 4, cudaMemcpyHostToDevice, s));
-    const int rc = hexb_step(env, actions_host ? h.act : nullptr, nullptr, obs_host ? h.obs : nullptr, mask_host ? h.mask : nullptr,
-                             reward_host ? h.rew : nullptr, done_host ? h.done : nullptr, nullptr, nullptr, stream);
+    int rc = host_events(env);
     if (rc != HEXB_OK) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(obs_host, h.obs, G * C * obs_elem(env), cudaMemcpyDeviceToHost, s));
-    if (mask_host) CK(cudaMemcpyAsync(mask_host, h.mask, G * C, cudaMemcpyDeviceToHost, s));
-    if (reward_host) CK(cudaMemcpyAsync(reward_host, h.rew, G * 4, cudaMemcpyDeviceToHost, s));
-    if (done_host) CK(cudaMemcpyAsync(done_host, h.done, G, cudaMemcpyDeviceToHost, s));
+    const bool can_pack = packed_host && obs_host && mask_host && !env->base.obs_f32;
+    const HostPlan p = plan_host(env, can_pack ? frac : 1.0);
+    if (actions_host) CK(cudaMemcpyAsync(h.act, actions_host, (size_t)G * 4, cudaMemcpyHostToDevice, s));
+    const bool need_mask_dev = mask_host && p.dma_games > 0;
+    rc = hexb_step(env, actions_host ? h.act : nullptr, nullptr, obs_host ? h.obs : nullptr, need_mask_dev ? h.mask : nullptr,
+                   reward_host ? h.rew : nullptr, done_host ? h.done : nullptr, nullptr, nullptr, (void *)s);
+    if (rc != HEXB_OK) return rc;
+    env->host_plan_words = p.words;
+    env->host_plan_first = p.first_word;
+    if (p.words > 0) {
+        // the packed words first (they are small): host threads expand slice k while the later copies are still in flight
+        hexb_pack_obs_kernel<<<(unsigned)((p.words + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4 *>(h.obs) + p.first_word, p.words,
+                                                                            h.packed + p.first_word);
+        CK(cudaGetLastError());
+        for (int k = 0; k < kHostSlices; ++k) {
+            long long lo = p.first_word + ((p.words * k / kHostSlices) & ~15ll), hi = p.first_word + ((p.words * (k + 1) / kHostSlices) & ~15ll);
+            if (k == kHostSlices - 1) hi = p.first_word + p.words;
+            env->host_slice_lo[k] = lo;
+            env->host_slice_hi[k] = hi;
+            if (hi > lo) CK(cudaMemcpyAsync(packed_host + lo, h.packed + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(env->host_ev_slice[k], s));
+        }
+    }
+    CK(cudaEventRecord(env->host_ev_dma0, s));
+    const size_t dma_cells = (size_t)(p.dma_games * C);
+    if (obs_host && dma_cells) CK(cudaMemcpyAsync(obs_host, h.obs, dma_cells * ob, cudaMemcpyDeviceToHost, s));
+    if (mask_host && dma_cells) CK(cudaMemcpyAsync(mask_host, h.mask, dma_cells, cudaMemcpyDeviceToHost, s));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, h.rew, (size_t)G * 4, cudaMemcpyDeviceToHost, s));
+    if (done_host) CK(cudaMemcpyAsync(done_host, h.done, (size_t)G, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(env->host_ev, s));
+    env->host_dma_bytes = (double)dma_cells * (double)(ob + 1);
+    env->host_packed_src = packed_host;
+    env->host_obs = (int8_t *)obs_host;
+    env->host_mask = mask_host;
     env->host_pending = 1;
     return HEXB_OK;
 }
 
-int32_t hexb_step_host_end(hexb_env *env) {
-    if (!env || !env->host_pending) return HEXB_ERR_ARG;
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
+// Finish the pending step: expand the packed slices as they arrive, wait for the DMA part, and (adaptive mode) move the split
+// towards the ratio of the two measured rates.
+static int host_step_finish(hexb_env *env, bool adapt) {
     env->host_pending = 0;
     CK(cudaSetDevice(env->cfg.device));
+    const long long cells = (long long)env->cfg.num_games * env->cfg.board_size * env->cfg.board_size;
+    double cpu_ms = 0.0;
+    if (env->host_plan_words > 0) {
+        for (int k = 0; k < kHostSlices; ++k) {
+            CK(cudaEventSynchronize(env->host_ev_slice[k]));
+            const long long lo = env->host_slice_lo[k], hi = env->host_slice_hi[k];
+            if (hi > lo) {
+                const double t0 = now_ms();
+                hexb_hostpack_expand(env->host_packed_src, lo, hi - lo, cells, env->cfg.variant, env->host_obs, env->host_mask);
+                cpu_ms += now_ms() - t0;
+            }
+        }
+    }
     CK(cudaEventSynchronize(env->host_ev));
+    if (adapt && env->host_plan_words > 0 && env->host_dma_bytes > 0.0 && cpu_ms > 0.0) {
+        float dma_ms = 0.f;
+        if (cudaEventElapsedTime(&dma_ms, env->host_ev_dma0, env->host_ev) == cudaSuccess && dma_ms > 0.f) {
+            const double cpu_bytes = 2.0 * 16.0 * (double)env->host_plan_words;
+            const double d = env->host_dma_bytes / dma_ms, e = cpu_bytes / cpu_ms;   // bytes per ms of each path, under contention
+            double f = d / (d + e);
+            f = 0.5 * env->host_dma_frac + 0.5 * f;
+            env->host_dma_frac = f < 0.05 ? 0.05 : (f > 0.95 ? 0.95 : f);
+        }
+    }
     return HEXB_OK;
+}
+
+static int host_staging(hexb_env *env) {   // pinned staging for the packed words, owned by the handle
+    if (env->host_packed) return HEXB_OK;
+    CK(cudaSetDevice(env->cfg.device));
+    CK(cudaHostAlloc((void **)&env->host_packed, hexb_host_packed_bytes(&env->cfg) + 64, cudaHostAllocDefault));
+    return HEXB_OK;
+}
+
+int32_t hexb_step_host_begin(hexb_env *env, void *workspace, const int32_t *actions_host, void *obs_host, uint8_t *mask_host,
+                             float *reward_host, uint8_t *done_host, void *stream) {
+    if (!env || !workspace || env->cfg.raw || env->cfg.manual_opponent || env->host_pending) return HEXB_ERR_ARG;
+    // the hybrid transport needs both arrays, int8 observations, a host thread pool and enough games to split
+    const bool hybrid = obs_host && mask_host && !env->base.obs_f32 && env->host_dma_frac < 1.0 && env->cfg.num_games >= 4096;
+    if (hybrid) {
+        const int rc = host_staging(env);
+        if (rc != HEXB_OK) return rc;
+    }
+    env->host_adapt = hybrid && env->host_frac_fixed == 0;
+    return host_step_enqueue(env, workspace, hybrid ? env->host_packed : nullptr, env->host_dma_frac, actions_host, obs_host, mask_host,
+                             reward_host, done_host, (cudaStream_t)stream);
+}
+
+int32_t hexb_step_host_end(hexb_env *env) {
+    if (!env || !env->host_pending) return HEXB_ERR_ARG;
+    return host_step_finish(env, env->host_adapt != 0);
 }
 
 int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_host, void *obs_host, uint8_t *mask_host,
@@ -468,48 +605,33 @@ int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_ho
     return hexb_step_host_end(env);
 }
 
+int32_t hexb_set_host_transport(hexb_env *env, double dma_fraction) {
+    if (!env || env->host_pending) return HEXB_ERR_ARG;
+    if (dma_fraction < 0.0) {            // adaptive (the default)
+        env->host_frac_fixed = 0;
+        env->host_dma_frac = 0.5;
+    } else {
+        if (dma_fraction > 1.0) return HEXB_ERR_ARG;
+        env->host_frac_fixed = 1;
+        env->host_dma_frac = dma_fraction;
+    }
+    return HEXB_OK;
+}
+
+int32_t hexb_get_host_transport(const hexb_env *env, double *dma_fraction) {
+    if (!env || !dma_fraction) return HEXB_ERR_ARG;
+    *dma_fraction = env->host_dma_frac;
+    return HEXB_OK;
+}
+
 int32_t hexb_step_host_packed(hexb_env *env, void *workspace, void *packed_host, const int32_t *actions_host, int8_t *obs_host,
                               uint8_t *mask_host, float *reward_host, uint8_t *done_host, void *stream) {
     if (!env || !workspace || !packed_host || env->cfg.raw || env->cfg.manual_opponent || env->host_pending) return HEXB_ERR_ARG;
     if (env->base.obs_f32 || !obs_host || !mask_host) return HEXB_ERR_ARG;   // the transport carries int8 observations; the mask is implied
-    cudaStream_t s = (cudaStream_t)stream;
-    const long long G = env->cfg.num_games, C = (long long)env->cfg.board_size * env->cfg.board_size;
-    const long long cells = G * C, words = (cells + 15) / 16;
-    const HostWs h = carve_ws(env, workspace);
-    CK(cudaSetDevice(env->cfg.device));
-    if (!env->host_ev) CK(cudaEventCreateWithFlags(&env->host_ev, cudaEventDisableTiming));
-    if (actions_host) CK(cudaMemcpyAsync(h.act, actions_host, (size_t)G * 4, cudaMemcpyHostToDevice, s));
-    const int rc = hexb_step(env, actions_host ? h.act : nullptr, nullptr, h.obs, nullptr, reward_host ? h.rew : nullptr,
-                             done_host ? h.done : nullptr, nullptr, nullptr, stream);
+    const int rc = host_step_enqueue(env, workspace, (uint32_t *)packed_host, 0.0, actions_host, obs_host, mask_host, reward_host, done_host,
+                                     (cudaStream_t)stream);
     if (rc != HEXB_OK) return rc;
-    hexb_pack_obs_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4 *>(h.obs), words, h.packed);
-    CK(cudaGetLastError());
-    // the packed words come back in slices; host threads expand slice k while slice k+1 is still crossing PCIe
-    constexpr int SLICES = 4;
-    uint32_t *ph = (uint32_t *)packed_host;
-    cudaEvent_t ev[SLICES];
-    long long lo[SLICES + 1];
-    for (int k = 0; k <= SLICES; ++k) lo[k] = (words * k / SLICES) & ~15ll;
-    lo[SLICES] = words;
-    for (int k = 0; k < SLICES; ++k) {
-        CK(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-        if (lo[k + 1] > lo[k])
-            CK(cudaMemcpyAsync(ph + lo[k], h.packed + lo[k], (size_t)(lo[k + 1] - lo[k]) * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(ev[k], s));
-    }
-    if (reward_host) CK(cudaMemcpyAsync(reward_host, h.rew, (size_t)G * 4, cudaMemcpyDeviceToHost, s));
-    if (done_host) CK(cudaMemcpyAsync(done_host, h.done, (size_t)G, cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(env->host_ev, s));
-    int rc2 = HEXB_OK;
-    for (int k = 0; k < SLICES; ++k) {
-        const cudaError_t ce = cudaEventSynchronize(ev[k]);
-        if (ce != cudaSuccess && rc2 == HEXB_OK) rc2 = hexb_cuda_fail(ce);
-        if (rc2 == HEXB_OK && lo[k + 1] > lo[k]) hexb_hostpack_expand(ph, lo[k], lo[k + 1] - lo[k], cells, env->cfg.variant, obs_host, mask_host);
-        cudaEventDestroy(ev[k]);
-    }
-    if (rc2 != HEXB_OK) return rc2;
-    CK(cudaEventSynchronize(env->host_ev));
-    return HEXB_OK;
+    return host_step_finish(env, false);
 }
 
 size_t hexb_host_packed_bytes(const hexb_config *cfg) {
@@ -563,6 +685,17 @@ int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t
     if (!env || !board_true) return HEXB_ERR_ARG;
     CK(cudaSetDevice(env->cfg.device));
     return k_import[env->cfg.board_size - HEXB_MIN_BOARD](env->base, board_true, to_move, import_mask, (cudaStream_t)stream);
+}
+
+int32_t hexb_import_labels(hexb_env *env, const int8_t *board_true, const uint8_t *regions, const int8_t *to_move,
+                           const uint8_t *import_mask, void *stream) {
+    if (!env || !board_true || !regions) return HEXB_ERR_ARG;
+    CK(cudaSetDevice(env->cfg.device));
+    const Params P = env->base;
+    hexb_import_labels_kernel<<<(unsigned)((P.G + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, env->cfg.board_size, board_true, regions,
+                                                                                                to_move, import_mask);
+    CK(cudaGetLastError());
+    return HEXB_OK;
 }
 
 int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream) {

@@ -147,4 +147,48 @@ HEXB_HD void import_game(const Params &P, long long g, const int8_t *board_true,
     store_rec<N>(recw, rec);
 }
 
+// K6c: HexGame.__init__ with connected_stones given (HexGame.py:46-51, HexSingleGame.py:50-55): the label planes are adopted as
+// they are and region_counter = max(plane) + 1 per colour - what HexEnv.reset does from its second call on with the planes it
+// cached at the first one (HexGame.py:214-220, HexSingleGame.py:226-231), and with user-supplied `regions=`. After a merge the
+// highest label can be lower than the number of labels ever handed out, so these counters differ from a raster-order rebuild's.
+// planes u8[G,2,N+2,N+2] in the reference's layout (true colours and coordinates, borders included: the far border holds 1 once
+// that colour has connected). Board size at run time: this is a set-up path.
+HEXB_HD void import_labels_game(const Params &P, int N, long long g, const int8_t *board_true, const uint8_t *planes, const int8_t *to_move,
+                                const uint8_t *import_mask) {
+    const int C = N * N, W = (C + 31) / 32, Pd = N + 2, P2 = Pd * Pd;
+    if (import_mask && !import_mask[g]) return;
+    uint8_t *L = P.state + labels_offset(g, C);
+    uint32_t *recw = reinterpret_cast<uint32_t *>(P.state + rec_offset(g, C));
+    const uint32_t old_meta = recw[W * kRecStride];
+    const bool env_game = !P.raw && (old_meta & M_COLOUR_SET);
+    const uint32_t keep = env_game ? (old_meta & (M_TRANSPOSED | M_COLOUR_SET)) : M_COLOUR_SET;
+    const int tr = (keep & M_TRANSPOSED) ? 1 : 0;
+    const uint8_t *pl = planes + g * 2 * P2;
+    for (int w = 0; w < W; ++w) recw[w * kRecStride] = 0u;
+    for (int c = 0; c < C; ++c) {
+        const int y = c / N, x = c - y * N;
+        const int sc = tr ? x * N + y : c;              // stored cell
+        const int v = board_true[g * C + c];
+        uint32_t b = 0;
+        if (v == 0 || v == 1) {
+            b = (pl[v * P2 + (y + 1) * Pd + (x + 1)] & 0x7fu) | ((uint32_t)(v ^ tr) << 7);
+            recw[(sc >> 5) * kRecStride] |= 1u << (sc & 31);
+        }
+        L[sc] = (uint8_t)b;
+    }
+    uint32_t meta = keep | M_LIVE;
+    for (int col = 0; col < 2; ++col) {
+        uint32_t m = 0;
+        for (int i = 0; i < P2; ++i) m = pl[col * P2 + i] > m ? pl[col * P2 + i] : m;
+        const uint32_t ctr = m + 1u > 255u ? 255u : m + 1u;       // region_counter = max(plane) + 1
+        const int sp = col ^ tr;                                   // stored player holding true colour `col`
+        meta |= ctr << (sp ? M_CTR_C_SHIFT : M_CTR_R_SHIFT);
+        const uint32_t far = col == 0 ? pl[(N + 1) * Pd + 1] : pl[P2 + 1 * Pd + (N + 1)];
+        if (far == 1u) meta |= sp ? M_FAR_C1 : M_FAR_R1;
+    }
+    if (((to_move && to_move[g]) ? 1 : 0) ^ tr) meta |= M_TOMOVE;
+    recw[W * kRecStride] = meta;
+    if (!env_game) recw[(W + 1) * kRecStride] = 0u;
+}
+
 }  // namespace hexb

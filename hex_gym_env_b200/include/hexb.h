@@ -140,14 +140,25 @@ size_t hexb_host_workspace_bytes(const hexb_config *cfg);
 int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_host, void *obs_host, uint8_t *mask_host,
                        float *reward_host, uint8_t *done_host, void *stream);
 
+/* Transport of the observation + mask bytes inside hexb_step_host (they are 2*N*N of the 2*N*N + 5 bytes per game): by default
+ * the games of a step are split between plain DMA copies and a 2-bit-per-cell transport that host threads expand into the same
+ * arrays while the DMA runs (see hexb_step_host_packed); the split follows the two measured rates from call to call. The bytes
+ * that arrive do not depend on it. dma_fraction in [0,1] pins the share of games copied as plain bytes (1 = no host threads,
+ * plain DMA only, the behaviour of library version 1.2), a negative value selects the adaptive default again. Environment:
+ * HEXB_HOST_DMA_FRACTION, HEXB_HOST_THREADS. Applies when obs_host and mask_host are both given, obs_dtype is HEXB_OBS_I8
+ * and the shard has at least 4,096 games. */
+int32_t hexb_set_host_transport(hexb_env *env, double dma_fraction);
+int32_t hexb_get_host_transport(const hexb_env *env, double *dma_fraction);
+
 /* The same call split in two, so that a host-side policy can work while the step and its copies are in flight:
  * hexb_step_host_begin enqueues H2D + step + D2H on `stream` and returns at once; hexb_step_host_end waits until the results
- * are in the host buffers. One step may be pending per handle (a second _begin before _end is HEXB_ERR_ARG). */
+ * are in the host buffers (the host threads of the packed part of the transport work inside _end). One step may be pending per
+ * handle (a second _begin before _end is HEXB_ERR_ARG). */
 int32_t hexb_step_host_begin(hexb_env *env, void *workspace, const int32_t *actions_host, void *obs_host, uint8_t *mask_host,
                              float *reward_host, uint8_t *done_host, void *stream);
 int32_t hexb_step_host_end(hexb_env *env);
 
-/* hexb_step_host with a bit-packed transport: the step's observations cross PCIe as 2 bits per cell (the legal-action mask is
+/* hexb_step_host with ONLY the bit-packed transport (hexb_step_host itself mixes both): the step's observations cross PCIe as 2 bits per cell (the legal-action mask is
  * implied: legal == empty, HexSingleGame.py:205-206 / HexGame.py:203-204) and a pool of host threads (HEXB_HOST_THREADS, default:
  * the calling thread's CPU affinity count) expands them into the same int8 obs_host[G,N,N] and uint8 mask_host[G,N*N] arrays
  * hexb_step_host fills - bit-identical results, 8x fewer bytes on the device->host path, host cores doing the writes instead of
@@ -190,6 +201,14 @@ int32_t hexb_export_state(hexb_env *env, double *board, double *regions, double 
  * (SelfPlayEnv.reset -> continue_game, SelfplayWrapper.py:79-80); env handles used this way are manual_opponent=1 ones, whose
  * resets leave the opening move to that call. */
 int32_t hexb_import_boards(hexb_env *env, const int8_t *board_true, const int8_t *to_move, const uint8_t *import_mask, void *stream);
+
+/* HexGame.__init__ with connected_stones given (HexGame.py:46-51, HexSingleGame.py:50-55): the region-label planes are adopted as
+ * they are and region_counter = max(plane) + 1 - what HexEnv.reset does from its second call on with the planes cached at the
+ * first (HexGame.py:214-220, HexSingleGame.py:226-231), and with a user-supplied `regions=`. board_true as in hexb_import_boards;
+ * regions u8[G,2,N+2,N+2] in the reference's layout (plane 0 BLACK, plane 1 WHITE, true coordinates, borders included; every
+ * stone must carry its label, labels < 128). */
+int32_t hexb_import_labels(hexb_env *env, const int8_t *board_true, const uint8_t *regions, const int8_t *to_move,
+                           const uint8_t *import_mask, void *stream);
 
 /* Episode statistics accumulated by hexb_step since creation, int64[8] on the device:
  * [0] episodes finished, [1] BLACK wins, [2] WHITE wins, [3] agent wins, [4] plies of finished episodes,

@@ -9,6 +9,11 @@ host is what the reference also keeps outside HexGame: the env-level reward / do
 and the calls into Python's global `random`, made in exactly the reference's order so that a seeded reference run and a
 seeded run of these classes see the same draws.
 
+`selfplay_wrapper` below restates the bodies of minihex/SelfplayWrapper.py:37-199 (GUI branches and prints removed) on purpose:
+its method names, attribute names (opponent_models, opponent_scores, best_model, eval_state, ...) and the order of its calls
+into `random` ARE the contract the reference's callbacks and scripts rely on ("pool bookkeeping stays
+host-side Python"), so that class is a line-by-line host-side mirror, not new design; the game core underneath it is the GPU's.
+
 For throughput use the batched classes (HexBatch, vec_env.HexVecEnv): these single-game facades pay one kernel launch and
 one device->host read per call and exist for compatibility and for parity tests that read like the reference's own usage.
 
@@ -107,10 +112,14 @@ class DeviceGame(object):
         else:
             true_codes = np.where(board == -1, 0, np.where(board == 1, 1, 2)).astype(np.int8)
         stones = int((true_codes != 2).sum())
-        if stones or int(to_move) != 0:
-            # preset position: stones enter in raster order through flood_fill (HexGame.py:53-61 / HexSingleGame.py:57-65).
-            # `connected_stones` (the cached planes HexEnv.reset hands back, HexGame.py:214-220) is the result of that same
-            # rebuild for the same board, so it is not read.
+        if connected_stones is not None and stones:
+            # the planes are adopted as they are and region_counter = max(plane) + 1 (HexGame.py:46-51 / HexSingleGame.py:50-55):
+            # HexEnv.reset from its second call on (cached planes) and user-supplied `regions=`. After a merge the highest
+            # label can be lower than a raster-order rebuild's counter, so this is not the same state as the branch below.
+            planes = np.ascontiguousarray(np.asarray(connected_stones), dtype=np.uint8)
+            self._dev.import_labels(true_codes[None], planes[None], np.array([int(to_move)], np.int8))
+        elif stones or int(to_move) != 0:
+            # preset position: stones enter in raster order through flood_fill (HexGame.py:53-61 / HexSingleGame.py:57-65)
             self._dev.import_boards(true_codes[None], np.array([int(to_move)], np.int8))
         self.empty_fields = int(np.count_nonzero(board == self._empty))
         self._done_host = False
@@ -309,12 +318,15 @@ class HexEnvA(_EnvBase):
         return player((self.player + 1) % 2)
 
     def get_action_mask(self):
-        return self.simulator.board.flatten() == player.EMPTY
+        view = getattr(self, "_opponent_view", None)
+        board = self.simulator.board if view is None else view   # (opponent_predict asks for the mask of the inverted board, HexGame.py:358)
+        return board.flatten() == player.EMPTY
 
     def reset(self, seed=None, options=None):
+        cached = self.initial_regions      # None at the first reset (planes rebuilt), adopted afterwards (HexGame.py:207-220)
         self.simulator = HexGameA(self.current_player_num, np.array(self.initial_board), self.player,
-                                  connected_stones=self.initial_regions, debug=self.debug)
-        if self.initial_regions is None:
+                                  connected_stones=cached, debug=self.debug)
+        if cached is None:
             self.initial_regions = self.simulator.regions.copy()
         self.previous_opponent_move = None
         if self.player != self.current_player_num:
@@ -325,7 +337,11 @@ class HexEnvA(_EnvBase):
     def opponent_move(self, info):
         # the opponent sees the transposed, colour-swapped board and its action is transposed back (HexGame.py:332-346)
         seen = _swap_view(self.simulator.board, player.BLACK, player.WHITE)
-        a = self.opponent_policy(seen)
+        self._opponent_view = seen         # while the opponent chooses, the reference's simulator.board IS this inverted board
+        try:
+            a = self.opponent_policy(seen)
+        finally:
+            self._opponent_view = None
         y, x = self.simulator.action_to_coordinate(a)
         a = self.simulator.coordinate_to_action((x, y))
         self.winner = self.simulator.make_move(a)
@@ -423,8 +439,12 @@ class HexEnvB(_EnvBase):
             start = random_board(np.zeros((self.board_size, self.board_size)))
         else:
             start = np.array(self.initial_board)
-        self.simulator = HexGameB(self.current_player_num, start, connected_stones=self.initial_regions, debug=self.debug)
-        self.initial_regions = self.simulator.regions.copy()
+        # sample_board: a fresh position every time, its planes rebuilt (HexSingleGame.py:217-222); otherwise the planes cached at
+        # the first reset - or handed in as regions= - are adopted from then on (:211-216, :223-229)
+        cached = None if self.sample_board else self.initial_regions
+        self.simulator = HexGameB(self.current_player_num, start, connected_stones=cached, debug=self.debug)
+        if cached is None:
+            self.initial_regions = self.simulator.regions.copy()
         return self.simulator.board
 
     def step(self, action):

@@ -17,9 +17,10 @@ from ._native import check
 from .batch import HexBatch
 
 
-def masked_sample(logits, mask, u=None, generator=None, want_entropy=False):
+def masked_sample(logits, mask, u=None, generator=None, want_entropy=False, actions=None, logp=None):
     """Sample one legal action per row. logits f32[G,C], mask u8/bool[G,C] (1 = legal), u f64[G] uniforms (drawn with
-    torch if None). Returns (actions i32[G], log_prob f32[G][, entropy f32[G]])."""
+    torch if None). Returns (actions i32[G], log_prob f32[G][, entropy f32[G]]); `actions` / `logp` may be given (e.g. slices
+    of a rollout buffer) and are then written in place."""
     if not logits.is_cuda:
         raise RuntimeError("masked_sample runs on the GPU only (no CPU fallback)")
     G, C = logits.shape
@@ -30,8 +31,11 @@ def masked_sample(logits, mask, u=None, generator=None, want_entropy=False):
     if u is None:
         u = torch.rand(G, dtype=torch.float64, device=logits.device, generator=generator)
     u = u.contiguous().double()
-    actions = torch.empty(G, dtype=torch.int32, device=logits.device)
-    logp = torch.empty(G, dtype=torch.float32, device=logits.device)
+    for name, t, dt in (("actions", actions, torch.int32), ("logp", logp, torch.float32)):
+        if t is not None and (tuple(t.shape) != (G,) or t.dtype != dt or not t.is_contiguous() or t.device != logits.device):
+            raise ValueError("%s must be a contiguous %s tensor of shape (%d,) on %s" % (name, dt, G, logits.device))
+    actions = torch.empty(G, dtype=torch.int32, device=logits.device) if actions is None else actions
+    logp = torch.empty(G, dtype=torch.float32, device=logits.device) if logp is None else logp
     ent = torch.empty(G, dtype=torch.float32, device=logits.device) if want_entropy else None
     p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
     with torch.cuda.device(logits.device):
@@ -165,14 +169,16 @@ class RolloutCollector(object):
             buf.episode_starts[0].copy_(buf.episode_starts[-1])
         with torch.no_grad():
             for t in range(buf.T):
-                logits, values = policy(buf.obs[t].float())
-                actions, logp = masked_sample(logits, buf.action_masks[t], generator=self.gen)
-                buf.actions[t], buf.log_probs[t], buf.values[t] = actions, logp, values
+                obs = buf.obs[t]
+                logits, values = policy(obs if obs.dtype == torch.float32 else obs.float())
+                actions, _ = masked_sample(logits, buf.action_masks[t], generator=self.gen, actions=buf.actions[t], logp=buf.log_probs[t])
+                buf.values[t].copy_(values)
                 if b.manual_opponent:
                     o = b.step_with_opponent(actions, opponent_fn, obs=buf.obs[t + 1], mask=buf.action_masks[t + 1])
                     buf.rewards[t], buf.dones[t] = o["reward"], o["done"]
                 else:
                     b.step(actions, obs=buf.obs[t + 1], mask=buf.action_masks[t + 1], reward=buf.rewards[t], done=buf.dones[t])
-                buf.episode_starts[t + 1] = buf.dones[t].float()
-            _, buf.values[buf.T] = policy(buf.obs[buf.T].float())
+            obs = buf.obs[buf.T]
+            buf.values[buf.T].copy_(policy(obs if obs.dtype == torch.float32 else obs.float())[1])
+            buf.episode_starts[1:].copy_(buf.dones)     # SB3's layout: a step starts an episode iff the previous one ended it
         buf.compute_returns_and_advantage()

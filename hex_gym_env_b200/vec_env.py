@@ -105,6 +105,10 @@ class HexVecEnv(_VecEnvBase):
         if _VecEnvBase is not object:
             _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self.render_mode = None
+        # SB3 >= 2.0 VecEnv bookkeeping (base_vec_env.py: __init__): per-env reset infos, seeds and options of the next reset
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        self._seeds = [None for _ in range(self.num_envs)]
+        self._options = [{} for _ in range(self.num_envs)]
         self._actions = None
         self._mask = None
         self._pinned = None
@@ -134,6 +138,9 @@ class HexVecEnv(_VecEnvBase):
         self.batch.import_boards(boards, import_mask=which)
 
     def reset(self):
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        self._reset_seeds()
+        self._reset_options()
         obs, mask = self.batch.reset()
         if self.sample_board:
             self._restart_on_sampled_boards()
@@ -211,7 +218,34 @@ class HexVecEnv(_VecEnvBase):
         return [False] * n
 
     def seed(self, seed=None):
-        return [None] * self.num_envs  # like the reference, which accepts and ignores reset(seed=...)
+        """SB3: list of the seeds handed to the envs. Recorded, not used: the reference accepts and ignores reset(seed=...)
+        (HexGame.py:206, HexSingleGame.py:208, SelfplayWrapper.py:69); games are keyed by the constructor's seed."""
+        self._seeds = [None if seed is None else seed + i for i in range(self.num_envs)]
+        return list(self._seeds)
+
+    def set_options(self, options=None):
+        if options is None:
+            options = {}
+        self._options = [dict(options) for _ in range(self.num_envs)] if isinstance(options, dict) else [dict(o) for o in options]
+
+    def _reset_seeds(self):
+        self._seeds = [None for _ in range(self.num_envs)]
+
+    def _reset_options(self):
+        self._options = [{} for _ in range(self.num_envs)]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def getattr_depth_check(self, name, already_found):
+        return None
+
+    def get_images(self):
+        return [None for _ in range(self.num_envs)]
+
+    def render(self, mode=None):
+        return None
 
     def episode_stats(self):
         from .batch import STAT_NAMES

@@ -228,9 +228,199 @@ def gen_kats():
     np.savez_compressed(os.path.join(OUT, "kat.npz"), **k)
 
 
+def saturation_moves(N):
+    """Label-range stress: both colours found as many separate regions as the board allows before anything merges.
+    Cells with (x - y) % 3 == k form an independent set of the hex adjacency (a 3-colouring class). BLACK takes class 0 on its
+    interior rows 1..N-2, WHITE class 1 on its interior columns 1..N-2: every such stone is isolated, so region_counter reaches
+    3 + ~N(N-2)/3 for both colours (111 on 19x19; labels must stay below 128 in the packed state). Then the remaining cells are
+    filled in raster order, every stone merging up to three regions, until the board is full (play continues past the win).
+    Moves alternate BLACK / WHITE and never hit an occupied cell."""
+    blacks = [y * N + x for y in range(1, N - 1) for x in range(N) if (x - y) % 3 == 0]
+    whites = [y * N + x for y in range(N) for x in range(1, N - 1) if (x - y) % 3 == 1]
+    taken = set(blacks) | set(whites)
+    rest = [c for c in range(N * N) if c not in taken]
+    moves, bi, wi, ri = [], 0, 0, 0
+    for ply in range(N * N):
+        if ply % 2 == 0 and bi < len(blacks):
+            moves.append(blacks[bi]); bi += 1
+        elif ply % 2 == 1 and wi < len(whites):
+            moves.append(whites[wi]); wi += 1
+        elif ri < len(rest):
+            moves.append(rest[ri]); ri += 1
+        elif bi < len(blacks):
+            moves.append(blacks[bi]); bi += 1
+        else:
+            moves.append(whites[wi]); wi += 1
+    assert sorted(moves) == list(range(N * N))
+    return moves
+
+
+def gen_saturation(N):
+    """Variant-A HexGame driven through saturation_moves: return codes and snapshots of the planes / counters from the reference."""
+    minihex, A, B, S = rh.load()
+    moves = saturation_moves(N)
+    g = A.HexGame(A.player.BLACK, A.player.EMPTY * np.ones((N, N)), A.player.BLACK)
+    ret, snaps_t, regions, counter, board = [], [], [], [], []
+    for t, a in enumerate(moves):
+        ret.append(code(g.make_move(a)))
+        if t % 16 == 15 or t >= len(moves) - 3 or t == 2 * (N * (N - 2) // 3):
+            snaps_t.append(t)
+            regions.append(np.array(g.regions, dtype=np.uint8))
+            counter.append(np.array(g.region_counter, dtype=np.int16))
+            board.append(np.array(g.board, dtype=np.int8))
+    counter = np.array(counter)
+    assert counter.max() >= (105 if N >= 19 else 3 + (N - 2) * N // 3 - 2), counter.max()
+    np.savez_compressed(os.path.join(OUT, "saturation_N%d.npz" % N), N=N, moves=np.array(moves, np.int32), ret=np.array(ret, np.int8),
+                        snap_t=np.array(snaps_t, np.int32), regions=np.array(regions), counter=counter, board=np.array(board))
+
+
+def gen_facade(N, seed):
+    """The small HexGame methods (a2 / a3 / a7): is_valid_move, action_to_coordinate, coordinate_to_action, get_possible_actions
+    at positions along a random game, both variants; which out-of-range actions raise IndexError."""
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed)
+    C = N * N
+    out = {}
+    for variant in ("A", "B"):
+        if variant == "A":
+            g = A.HexGame(A.player.BLACK, A.player.EMPTY * np.ones((N, N)), A.player.BLACK)
+        else:
+            g = B.HexGame(0, np.zeros((N, N)))
+        moves = np.zeros(C - 2, np.int64)
+        valid, possible, npossible, at = [], [], [], []
+        for t in range(C - 2):
+            # a legal cell of the CURRENT view (after an illegal move HexEnv ends the episode; a raw game that plays on has its
+            # board and planes in different coordinate systems in the reference, which is outside every caller's contract)
+            legal = [k for k in range(C) if g.is_valid_move(k)]
+            a = moves[t] = legal[rs.randint(len(legal))]
+            if t % 3 == 0:
+                at.append(t)
+                valid.append([bool(g.is_valid_move(k)) for k in range(C)])
+                pa = np.asarray(g.get_possible_actions())
+                npossible.append(len(pa))
+                possible.append(np.concatenate([pa, -np.ones(C - len(pa), pa.dtype)]))
+            if variant == "B":
+                # raw variant-B games are driven the way HexEnv drives them: the board is flipped after every ply, the
+                # action is a cell of the mover's view (oracle/gen_golden.py: gen_raw_games)
+                pass
+            g.make_move(int(a))
+            if variant == "B":
+                bb = g.board.copy().T
+                bb[bb == -1] = 2; bb[bb == 1] = -1; bb[bb == 2] = 1
+                g.board = bb
+        out["moves_" + variant] = moves.astype(np.int32)
+        out["at_" + variant] = np.array(at, np.int32)
+        out["valid_" + variant] = np.array(valid, np.uint8)
+        out["possible_" + variant] = np.array(possible, np.int32)
+        out["npossible_" + variant] = np.array(npossible, np.int32)
+        raises = []
+        for k in (C, C + 1, C + N, 2 * C):
+            try:
+                g.is_valid_move(k)
+                raises.append(0)
+            except IndexError:
+                raises.append(1)
+        out["oob_actions"] = np.array([C, C + 1, C + N, 2 * C], np.int32)
+        out["oob_raises_" + variant] = np.array(raises, np.uint8)
+        out["coords_" + variant] = np.array([g.action_to_coordinate(k) for k in range(C)], np.int32)
+        out["actions_of_coords_" + variant] = np.array([g.coordinate_to_action(tuple(g.action_to_coordinate(k))) for k in range(C)], np.int32)
+    np.savez_compressed(os.path.join(OUT, "facade_N%d.npz" % N), N=N, **out)
+
+
+def gen_opponent_predict(N, G, T, seed, eps, opponent_first):
+    """Variant-A HexEnv with opponent_policy="opponent_predict" (HexGame.py:165-167, 354-359): with probability eps the opponent
+    is random_policy, else the model's deterministic prediction on the inverted board with the mask of that view."""
+    from oracle.scripted import ScriptedModelA
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed ^ 0xACE)
+    C = N * N
+    out = dict(actions=np.zeros((T, G), np.int32), obs=np.zeros((T, G, N, N), np.int8), reward=np.zeros((T, G), np.float32),
+               done=np.zeros((T, G), np.uint8), last_move_opponent=-np.ones((T, G), np.int32), winner=-9 * np.ones((T, G), np.int8),
+               draws=np.zeros((T, G), np.uint32), model_calls=np.zeros((T, G), np.int32), model_action=-np.ones((T, G), np.int32),
+               model_mask=np.zeros((T, G, C), np.uint8), model_board=np.zeros((T, G, N, N), np.int8),
+               obs0=np.zeros((G, N, N), np.int8), draws0=np.zeros(G, np.uint32), regions=np.zeros((T, G, 2, N + 2, N + 2), np.uint8),
+               counter=np.zeros((T, G, 2), np.int16))
+    for gi in range(G):
+        stream = GameStream(seed, gi)
+        rh.set_rng(stream)
+        log = []
+        env = A.HexEnv(opponent_policy="opponent_predict", opponent_model=ScriptedModelA(log), board_size=N, eps=eps,
+                       current_player_num=A.player.WHITE if opponent_first else A.player.BLACK)
+        obs, _ = env.reset()
+        del log[:]
+        out["obs0"][gi], out["draws0"][gi] = obs, stream.idx
+        for t in range(T):
+            legal = np.flatnonzero(env.get_action_mask())
+            a = int(rs.randint(C)) if rs.rand() < 0.04 else int(legal[rs.randint(len(legal))])
+            obs, r, done, _, info = env.step(a)
+            out["actions"][t, gi], out["reward"][t, gi], out["done"][t, gi] = a, r, done
+            out["last_move_opponent"][t, gi] = -1 if info["last_move_opponent"] is None else int(info["last_move_opponent"])
+            out["winner"][t, gi] = code(info["winner"])
+            out["model_calls"][t, gi] = len(log)
+            if log:
+                out["model_action"][t, gi], out["model_mask"][t, gi], out["model_board"][t, gi] = log[-1]
+            del log[:]
+            out["regions"][t, gi], out["counter"][t, gi] = env.simulator.regions, env.simulator.region_counter
+            if done:
+                obs, _ = env.reset()
+                del log[:]
+            out["obs"][t, gi], out["draws"][t, gi] = obs, stream.idx
+    np.savez_compressed(os.path.join(OUT, "oppredict_N%d_of%d.npz" % (N, int(opponent_first))), N=N, seed=seed, eps=eps,
+                        opponent_first=int(opponent_first), **out)
+
+
+def gen_preset_resets(N, n, seed):
+    """HexEnv.reset called repeatedly on a preset board (both variants): the first reset rebuilds the planes in raster order, the
+    later ones adopt the cached planes with region_counter = max(plane) + 1 (HexGame.py:207-220 / HexSingleGame.py:211-231), which
+    differs from the first reset's counters when the rebuild merged regions. Also user-supplied regions= at construction."""
+    minihex, A, B, S = rh.load()
+    rs = np.random.RandomState(seed)
+    true_codes = rs.choice([0, 1, 2], size=(n, N, N), p=[0.3, 0.3, 0.4]).astype(np.int8)
+    out = dict(board_true=true_codes)
+    for variant in ("A", "B"):
+        reg = np.zeros((n, 3, 2, N + 2, N + 2), np.uint8)
+        ctr = np.zeros((n, 3, 2), np.int16)
+        moved = np.zeros((n, 2, N + 2, N + 2), np.uint8)
+        moved_ctr = np.zeros((n, 2), np.int16)
+        move = -np.ones(n, np.int32)
+        for i in range(n):
+            if variant == "A":
+                env = A.HexEnv(opponent_policy=None, board=true_codes[i].astype(np.float64), board_size=N)
+                make = lambda regions: A.HexEnv(opponent_policy=None, board=true_codes[i].astype(np.float64), regions=regions, board_size=N)
+                empty = 2
+            else:
+                bb = np.where(true_codes[i] == 0, -1.0, np.where(true_codes[i] == 1, 1.0, 0.0))
+                env = B.HexEnv(board=bb, board_size=N)
+                make = lambda regions: B.HexEnv(board=bb, regions=regions, board_size=N)
+                empty = 0
+            for k in range(2):       # reset 0 rebuilds, reset 1 adopts the cached planes
+                env.reset()
+                reg[i, k], ctr[i, k] = env.simulator.regions, env.simulator.region_counter
+            env2 = make(np.array(reg[i, 0], dtype=np.float64))   # user-supplied regions= : adopted from the first reset on
+            env2.reset()
+            reg[i, 2], ctr[i, 2] = env2.simulator.regions, env2.simulator.region_counter
+            free = np.flatnonzero(env.simulator.board.flatten() == empty)
+            if len(free):            # one move on the adopted state: new regions take their label from the adopted counter
+                move[i] = int(free[rs.randint(len(free))])
+                env.simulator.make_move(int(move[i]))
+                moved[i], moved_ctr[i] = env.simulator.regions, env.simulator.region_counter
+        out["regions_" + variant], out["counter_" + variant] = reg, ctr
+        out["move_" + variant], out["moved_regions_" + variant], out["moved_counter_" + variant] = move, moved, moved_ctr
+    np.savez_compressed(os.path.join(OUT, "presetreset_N%d.npz" % N), N=N, **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_kats()
+    for N in (18, 19):
+        gen_saturation(N)
+    for N in (4, 7):
+        gen_facade(N, 500 + N)
+    for N, G, T in [(4, 12, 30), (7, 8, 60)]:
+        for of in (False, True):
+            gen_opponent_predict(N, G, T, seed=4000 + N, eps=0.5, opponent_first=of)
+    for N, n in [(4, 40), (7, 20)]:
+        gen_preset_resets(N, n, 600 + N)
     for N, n in [(3, 12), (4, 8), (5, 8), (7, 4), (11, 3), (13, 1)]:
         gen_raw_games("A", N, n, 100 + N)
         gen_raw_games("B", N, n, 200 + N)

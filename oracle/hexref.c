@@ -160,6 +160,32 @@ static void game_init(game_t *g, int N, int variant, int cur, const int *board /
     g->winner = NONE;
 }
 
+/* HexGame.__init__ with connected_stones given  A: HexGame.py:46-51,63-68   B: HexSingleGame.py:50-55,67-71: the planes are
+ * adopted as they are, region_counter = max(plane) + 1 per colour, no flood_fill runs. This is what HexEnv.reset does from its
+ * second call on with the planes it cached at the first (HexGame.py:214-220 / HexSingleGame.py:226-231). */
+static void game_init_adopt(game_t *g, int N, int variant, int cur, const int *board, const uint8_t *planes /* [2][(N+2)^2] */) {
+    const int P = N + 2, C = N * N;
+    g->N = N; g->variant = variant;
+    const int E = empty_code(g);
+    g->empty_fields = 0;
+    for (int c = 0; c < C; ++c) {
+        g->board[c] = board[c];
+        g->empty_fields += (g->board[c] == E);
+    }
+    memset(g->regions, 0, sizeof(g->regions));
+    for (int p = 0; p < 2; ++p) {
+        int m = 0;
+        for (int i = 0; i < P * P; ++i) {
+            g->regions[p][i] = planes[p * P * P + i];
+            if (g->regions[p][i] > m) m = g->regions[p][i];
+        }
+        g->counter[p] = m + 1;
+    }
+    g->cur = cur;
+    g->done = 0;
+    g->winner = NONE;
+}
+
 /* HexGame.fast_move  A: HexGame.py:85-111   B: HexSingleGame.py:88-122.
  * Returns NONE, BLACK, WHITE or INVALID. An out-of-range action (IndexError / negative wrap in the
  * reference, i.e. undefined) is treated as INVALID. */
@@ -598,6 +624,17 @@ void hexref_batch_env_set_board(void *h, const int8_t *boards, const uint8_t *ma
         e->env_cur = BLACK;
         e->plies = stones;
         e->env_winner = NONE;
+    }
+}
+
+/* Raw game from a preset board and its label planes (HexGame.__init__ with connected_stones given). */
+void hexref_batch_set_board_labels(void *h, const int8_t *boards, const uint8_t *planes /*[G,2,N+2,N+2]*/, int cur) {
+    batch_t *b = (batch_t *)h;
+    const int C = b->N * b->N, P2 = (b->N + 2) * (b->N + 2);
+    for (int64_t i = 0; i < b->G; ++i) {
+        int tmp[MAXC];
+        for (int c = 0; c < C; ++c) tmp[c] = boards[i * C + c];
+        game_init_adopt(&b->envs[i].g, b->N, b->envs[i].g.variant, cur, tmp, planes + i * 2 * P2);
     }
 }
 

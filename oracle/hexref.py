@@ -49,6 +49,7 @@ def lib():
         L.hexref_batch_opp_state.argtypes = [vp, vp, vp]
         L.hexref_batch_info.argtypes = [vp, vp, vp]
         L.hexref_batch_env_set_board.argtypes = [vp, vp, vp]
+        L.hexref_batch_set_board_labels.argtypes = [vp, vp, vp, i32]
         _LIB = L
     return _LIB
 
@@ -156,6 +157,12 @@ class RefBatch(object):
     def set_board(self, boards, cur=0):
         b = np.ascontiguousarray(boards, np.int8)
         lib().hexref_batch_set_board(self._h, _p(b), cur)
+
+    def set_board_labels(self, boards, planes, cur=0):
+        """Raw games from preset boards AND their label planes (HexGame.__init__ with connected_stones given)."""
+        b = np.ascontiguousarray(boards, np.int8)
+        p = np.ascontiguousarray(planes, np.uint8)
+        lib().hexref_batch_set_board_labels(self._h, _p(b), _p(p), cur)
 
     def export(self):
         N, G = self.N, self.G

@@ -43,6 +43,7 @@ def lib():
         L.emu_set_info.argtypes = [vp, vp, vp]
         L.emu_rollout.argtypes = [vp, i32] + [vp] * 6
         L.emu_force_sweep.argtypes = [i32]
+        L.emu_import_labels.argtypes = [vp] * 5
         _LIB = L
     return _LIB
 
@@ -153,6 +154,13 @@ class EmuBatch(object):
         tm = None if to_move is None else np.ascontiguousarray(to_move, np.int8)
         im = None if import_mask is None else np.ascontiguousarray(import_mask, np.uint8)
         lib().emu_import_boards(self._h, _p(b), _p(tm), _p(im))
+
+    def import_labels(self, board_true, regions, to_move=None, import_mask=None):
+        b = np.ascontiguousarray(board_true, np.int8)
+        r = np.ascontiguousarray(regions, np.uint8)
+        tm = None if to_move is None else np.ascontiguousarray(to_move, np.int8)
+        im = None if import_mask is None else np.ascontiguousarray(import_mask, np.uint8)
+        lib().emu_import_labels(self._h, _p(b), _p(r), _p(tm), _p(im))
 
     def opponent_catch_up(self):
         lib().emu_half_step(self._h, 1, None, None, None, None)

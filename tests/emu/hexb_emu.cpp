@@ -249,6 +249,10 @@ void emu_import_boards(void *h, const int8_t *board_true, const int8_t *to_move,
 #undef X
         }
 }
+void emu_import_labels(void *h, const int8_t *board_true, const uint8_t *planes, const int8_t *to_move, const uint8_t *import_mask) {
+    emu_env *e = (emu_env *)h;
+    for (long long g = 0; g < e->base.G; ++g) import_labels_game(e->base, e->N, g, board_true, planes, to_move, import_mask);
+}
 void emu_stats(void *h, int64_t *out8) {
     emu_env *e = (emu_env *)h;
     for (int i = 0; i < 8; ++i) out8[i] = e->base.stats[i];

@@ -73,6 +73,9 @@ class GpuBatch(object):
     def import_boards(self, board_true, to_move=None, import_mask=None):
         self.b.import_boards(board_true, to_move, import_mask)
 
+    def import_labels(self, board_true, regions, to_move=None, import_mask=None):
+        self.b.import_labels(board_true, regions, to_move, import_mask)
+
     def opponent_catch_up(self):
         self.b.opponent_catch_up()
 

@@ -401,3 +401,62 @@ def raw_random_games(make, N, G, seed=0, variant_b=False):
         e, r = env.export(), ref.export()
         for k in ("board", "regions", "region_counter", "cur", "done", "winner"):
             eq(e[k], r[k], "raw games N=%d %s t=%d" % (N, k, t))
+
+
+def golden_saturation(make, name):
+    """Label-range stress (oracle/gen_golden.py: saturation_moves): both colours found ~N(N-2)/3 separate regions (region_counter
+    110 / 111 on 19x19 - the packed state keeps labels in 7 bits) and then merge them all. Implementation vs the snapshots of the
+    unmodified reference AND vs the oracle after every ply."""
+    z = np.load(os.path.join(GOLDEN, name))
+    N, moves = int(z["N"]), z["moves"]
+    G = 33                                              # one chunk and a bit; every game plays the same list
+    env = make(hexref.KIND_GAME_A, N, G)
+    ref = hexref.RefBatch(hexref.KIND_GAME_A, N, G)
+    env.reset()
+    snaps = {int(t): i for i, t in enumerate(z["snap_t"])}
+    top = 0
+    for t, a in enumerate(moves):
+        acts = np.full(G, a, np.int32)
+        r = env.ply(acts)
+        eq(r, ref.ply(acts), "%s ret t=%d" % (name, t))
+        assert (r == z["ret"][t]).all(), (name, t)
+        if t in snaps or t % 9 == 0:
+            e, o = env.export(), ref.export()
+            for k in ("board", "regions", "region_counter", "cur", "done", "winner"):
+                eq(e[k], o[k], "%s %s t=%d" % (name, k, t))
+            top = max(top, int(e["region_counter"].max()))
+        if t in snaps:
+            i = snaps[t]
+            assert (e["regions"] == z["regions"][i].astype(np.float64)).all(), (name, "regions", t)
+            assert (e["region_counter"] == z["counter"][i].astype(np.float64)).all(), (name, "counter", t)
+            assert (e["board"] == z["board"][i].astype(np.float64)).all(), (name, "board", t)
+    assert top >= (105 if N >= 19 else 95), top         # the label range really was exercised
+    return top
+
+
+def golden_preset_resets(make_raw, name):
+    """HexGame.__init__ with connected_stones (cached planes of HexEnv.reset, user regions=): planes adopted as they are,
+    region_counter = max(plane) + 1, and the next new region takes its label from that counter. hexb_import_labels vs the
+    unmodified reference's second reset."""
+    z = np.load(os.path.join(GOLDEN, name))
+    N, tc = int(z["N"]), z["board_true"]
+    n = tc.shape[0]
+    for variant, kind in (("A", hexref.KIND_GAME_A), ("B", hexref.KIND_GAME_B)):
+        reg, ctr = z["regions_" + variant], z["counter_" + variant]
+        env = make_raw(kind, N, n)
+        env.reset()
+        env.import_boards(tc)                                   # reset 0: raster-order rebuild
+        e = env.export()
+        eq(e["regions"], reg[:, 0].astype(np.float64), "%s %s rebuild regions" % (name, variant))
+        eq(e["region_counter"], ctr[:, 0].astype(np.float64), "%s %s rebuild counter" % (name, variant))
+        env.import_labels(tc, reg[:, 0])                        # reset 1: the cached planes come back
+        e = env.export()
+        eq(e["regions"], reg[:, 1].astype(np.float64), "%s %s adopted regions" % (name, variant))
+        eq(e["region_counter"], ctr[:, 1].astype(np.float64), "%s %s adopted counter" % (name, variant))
+        assert (ctr[:, 0] != ctr[:, 1]).any()                   # the fixture does contain merged presets
+        mv = z["move_" + variant]
+        ok = mv >= 0
+        env.ply(np.where(ok, mv, 0).astype(np.int32))
+        e = env.export()
+        eq(e["regions"][ok], z["moved_regions_" + variant][ok].astype(np.float64), "%s %s regions after a move" % (name, variant))
+        eq(e["region_counter"][ok], z["moved_counter_" + variant][ok].astype(np.float64), "%s %s counter after a move" % (name, variant))

@@ -139,3 +139,14 @@ def test_sampler_and_views(N, variant_a):
 @pytest.mark.parametrize("N", [3, 5, 8, 11])
 def test_raw_random_games(N):
     parity.raw_random_games(make, N, 200, seed=N)
+
+
+@pytest.mark.parametrize("name", golden_files("saturation_"))
+def test_golden_label_saturation(name):
+    """~110 distinct region labels per colour on 18x18 / 19x19 (the packed state holds 7-bit labels), then everything merges."""
+    parity.golden_saturation(make, name)
+
+
+@pytest.mark.parametrize("name", golden_files("presetreset_"))
+def test_golden_preset_resets(name):
+    parity.golden_preset_resets(lambda kind, N, G: EmuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True), name)

@@ -142,3 +142,106 @@ def test_preset_board_rebuild(mh):
             e = ref.export()
             assert np.array_equal(g.regions, e["regions"][0]) and np.array_equal(g.region_counter, e["region_counter"][0])
             assert np.array_equal(g.board, board)
+
+
+# ------------------------------------------------------------------------------------------------ the small methods (a2 / a3 / a7, f4)
+@pytest.mark.parametrize("name", golden_files("facade_"))
+def test_small_game_methods(mh, name):
+    """is_valid_move (incl. IndexError beyond the board), action_to_coordinate, coordinate_to_action, get_possible_actions
+    (HexGame.py:74-76,113-122 / HexSingleGame.py:77-79,124-133) at positions along a random game, vs the unmodified reference."""
+    minihex, compat, A, B, S = mh
+    z = np.load(os.path.join(GOLDEN, name))
+    N = int(z["N"])
+    C = N * N
+    for variant in ("A", "B"):
+        g = A.HexGame(A.player.BLACK, A.player.EMPTY * np.ones((N, N)), A.player.BLACK) if variant == "A" else B.HexGame(0, np.zeros((N, N)))
+        at = {int(t): i for i, t in enumerate(z["at_" + variant])}
+        for t, a in enumerate(z["moves_" + variant]):
+            if t in at:
+                i = at[t]
+                assert [bool(g.is_valid_move(k)) for k in range(C)] == [bool(v) for v in z["valid_" + variant][i]], (name, variant, t)
+                pa = np.asarray(g.get_possible_actions())
+                n = int(z["npossible_" + variant][i])
+                assert len(pa) == n and np.array_equal(pa, z["possible_" + variant][i][:n]), (name, variant, t)
+            g.make_move(int(a))
+            if variant == "B":
+                g._ref_flipped = not g._ref_flipped      # what HexEnv.invert_board does to the reference's board after every ply
+        for k, raises in zip(z["oob_actions"], z["oob_raises_" + variant]):
+            if raises:
+                with pytest.raises(IndexError):
+                    g.is_valid_move(int(k))
+            else:
+                g.is_valid_move(int(k))
+        assert np.array_equal(np.array([g.action_to_coordinate(k) for k in range(C)]), z["coords_" + variant])
+        assert [int(g.coordinate_to_action(tuple(g.action_to_coordinate(k)))) for k in range(C)] == list(z["actions_of_coords_" + variant])
+
+
+@pytest.mark.parametrize("name", golden_files("oppredict_"))
+def test_opponent_predict(mh, name):
+    """Variant-A HexEnv(opponent_policy="opponent_predict", opponent_model=..., eps=0.5) (HexGame.py:165-167, 354-359): draw order
+    (uniform, then random_policy's draw when below eps), the board and the mask the model is shown, info dict, rewards."""
+    from oracle.scripted import ScriptedModelA
+    minihex, compat, A, B, S = mh
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, eps, of = int(z["N"]), int(z["seed"]), float(z["eps"]), int(z["opponent_first"])
+    T, G = z["actions"].shape
+    import random
+    try:
+        for gi in range(G):
+            stream = GameStream(seed, gi)
+            compat.random = stream
+            log = []
+            env = A.HexEnv(opponent_policy="opponent_predict", opponent_model=ScriptedModelA(log), board_size=N, eps=eps,
+                           current_player_num=A.player.WHITE if of else A.player.BLACK)
+            obs, _ = env.reset()
+            del log[:]
+            assert np.array_equal(obs, z["obs0"][gi]) and stream.idx == z["draws0"][gi], (name, gi)
+            for t in range(T):
+                obs, r, done, trunc, info = env.step(int(z["actions"][t, gi]))
+                w = (name, gi, t)
+                assert r == z["reward"][t, gi] and bool(done) == bool(z["done"][t, gi]) and trunc is False, w
+                lmo = -1 if info["last_move_opponent"] is None else int(info["last_move_opponent"])
+                assert lmo == z["last_move_opponent"][t, gi] and code(info["winner"]) == z["winner"][t, gi], w
+                assert len(log) == z["model_calls"][t, gi], w
+                if log:
+                    a, mask, board = log[-1]
+                    assert a == z["model_action"][t, gi] and np.array_equal(mask, z["model_mask"][t, gi]), w
+                    assert np.array_equal(board, z["model_board"][t, gi]), w
+                del log[:]
+                assert np.array_equal(env.simulator.regions, z["regions"][t, gi]), w
+                assert np.array_equal(env.simulator.region_counter, z["counter"][t, gi]), w
+                if done:
+                    obs, _ = env.reset()
+                    del log[:]
+                assert np.array_equal(obs, z["obs"][t, gi]) and stream.idx == z["draws"][t, gi], w
+    finally:
+        compat.random = random
+
+
+@pytest.mark.parametrize("name", golden_files("presetreset_"))
+def test_env_resets_on_preset_boards(mh, name):
+    """HexEnv.reset twice on a preset board, and with user-supplied regions=: the first reset rebuilds the planes, later ones
+    adopt the cached planes with region_counter = max(plane) + 1 (HexGame.py:207-220 / HexSingleGame.py:211-229)."""
+    minihex, compat, A, B, S = mh
+    z = np.load(os.path.join(GOLDEN, name))
+    N, tc = int(z["N"]), z["board_true"]
+    for i in range(min(len(tc), 12)):
+        for variant in ("A", "B"):
+            reg, ctr = z["regions_" + variant][i], z["counter_" + variant][i]
+            if variant == "A":
+                mk = lambda regions=None: A.HexEnv(opponent_policy=None, board=tc[i].astype(np.float64), regions=regions, board_size=N)
+            else:
+                bb = np.where(tc[i] == 0, -1.0, np.where(tc[i] == 1, 1.0, 0.0))
+                mk = lambda regions=None: B.HexEnv(board=bb, regions=regions, board_size=N)
+            env = mk()
+            for k in range(2):
+                env.reset()
+                assert np.array_equal(env.simulator.regions, reg[k]) and np.array_equal(env.simulator.region_counter, ctr[k]), (name, i, variant, k)
+            env2 = mk(np.array(reg[0], dtype=np.float64))
+            env2.reset()
+            assert np.array_equal(env2.simulator.regions, reg[2]) and np.array_equal(env2.simulator.region_counter, ctr[2]), (name, i, variant)
+            mv = int(z["move_" + variant][i])
+            if mv >= 0:
+                env.simulator.make_move(mv)
+                assert np.array_equal(env.simulator.regions, z["moved_regions_" + variant][i]), (name, i, variant)
+                assert np.array_equal(env.simulator.region_counter, z["moved_counter_" + variant][i]), (name, i, variant)

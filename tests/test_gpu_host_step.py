@@ -47,6 +47,24 @@ def test_step_host_packed_matches_device(torch_mod, N, G, variant):
     assert host._lib.hexb_host_threads() >= 1
 
 
+@pytest.mark.parametrize("frac", [-1.0, 0.0, 0.3, 0.5, 0.97, 1.0])
+def test_step_host_transports_match_device(torch_mod, frac):
+    """hexb_step_host with every DMA / packed split (adaptive, pinned fractions, plain DMA) returns the device step's bytes."""
+    torch = torch_mod
+    for N, G in ((11, 8192 + 77), (7, 4096), (5, 5000)):
+        dev, host = _pair(torch, N, G, 1, 4, agent_mode=2)
+        host.set_host_transport(frac)
+        io = host.pinned_io()
+        for t in range(25):
+            o = dev.step()
+            io["obs"].fill_(99); io["mask"].fill_(99)
+            host.step_host(None, io)
+            for k in ("obs", "mask", "reward", "done"):
+                assert np.array_equal(io[k].numpy(), o[k].cpu().numpy()), (N, k, t, frac)
+        f = host.host_transport()
+        assert 0.0 <= f <= 1.0 and (frac < 0 or f == frac)
+
+
 def test_step_host_begin_end_matches_step_host(torch_mod):
     torch = torch_mod
     a, b = _pair(torch, 7, 3000, 1, 5, agent_mode=2)

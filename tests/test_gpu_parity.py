@@ -404,3 +404,17 @@ def test_config1_ten_thousand_raw_games(make):
 @pytest.mark.parametrize("N", [3, 7, 11, 14])
 def test_raw_random_games(make, N):
     parity.raw_random_games(make, N, 600, seed=N)
+
+
+@pytest.mark.parametrize("name", golden_files("saturation_"))
+def test_golden_label_saturation(make, name):
+    """~110 distinct region labels per colour on 18x18 / 19x19 (the packed state holds 7-bit labels), then everything merges:
+    hexb_ply vs the unmodified reference's snapshots and vs the oracle after every ply."""
+    parity.golden_saturation(make, name)
+
+
+@pytest.mark.parametrize("name", golden_files("presetreset_"))
+def test_golden_preset_resets(name):
+    """hexb_import_labels: HexGame.__init__ with connected_stones (the cached planes of HexEnv.reset's later calls)."""
+    from gpu_adapter import GpuBatch
+    parity.golden_preset_resets(lambda kind, N, G: GpuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True), name)

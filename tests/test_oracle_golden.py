@@ -125,3 +125,45 @@ def test_kats():
     assert np.array_equal(o1["obs"][0], k["kat4_obs"][0]) and np.array_equal(o2["obs"][0], k["kat4_obs"][1])
     assert [o1["reward"][0], o2["reward"][0]] == list(k["kat4_r"]) == [0, -100]
     assert [bool(o1["done"][0]), bool(o2["done"][0])] == [False, True]
+
+
+@pytest.mark.parametrize("name", golden_files("saturation_"))
+def test_label_saturation(name):
+    """The oracle against the reference's snapshots of the label-range stress game (oracle/gen_golden.py: saturation_moves)."""
+    z = load(name)
+    N = int(z["N"])
+    b = hexref.RefBatch(hexref.KIND_GAME_A, N, 1)
+    snaps = {int(t): i for i, t in enumerate(z["snap_t"])}
+    for t, a in enumerate(z["moves"]):
+        assert b.ply(np.array([a], np.int32))[0] == z["ret"][t], (name, t)
+        if t in snaps:
+            e, i = b.export(), snaps[t]
+            assert np.array_equal(e["regions"][0], z["regions"][i].astype(np.float64)), (name, t)
+            assert np.array_equal(e["region_counter"][0], z["counter"][i].astype(np.float64)), (name, t)
+            assert np.array_equal(e["board"][0], z["board"][i].astype(np.float64)), (name, t)
+    assert z["counter"].max() >= (105 if N >= 19 else 95)
+
+
+@pytest.mark.parametrize("name", golden_files("presetreset_"))
+def test_preset_resets(name):
+    """HexGame.__init__ with and without connected_stones: raster-order rebuild vs adopted planes (different counters)."""
+    z = load(name)
+    N, tc = int(z["N"]), z["board_true"]
+    for variant, kind in (("A", hexref.KIND_GAME_A), ("B", hexref.KIND_GAME_B)):
+        boards = tc if variant == "A" else np.where(tc == 0, -1, np.where(tc == 1, 1, 0)).astype(np.int8)
+        b = hexref.RefBatch(kind, N, len(tc))
+        b.set_board(boards)
+        e = b.export()
+        assert np.array_equal(e["regions"], z["regions_" + variant][:, 0].astype(np.float64))
+        assert np.array_equal(e["region_counter"], z["counter_" + variant][:, 0].astype(np.float64))
+        for k in (1, 2):      # second reset (cached planes) and user-supplied regions=
+            b.set_board_labels(boards, z["regions_" + variant][:, 0])
+            e = b.export()
+            assert np.array_equal(e["regions"], z["regions_" + variant][:, k].astype(np.float64))
+            assert np.array_equal(e["region_counter"], z["counter_" + variant][:, k].astype(np.float64))
+        mv = z["move_" + variant]
+        ok = mv >= 0
+        b.ply(np.where(ok, mv, 0).astype(np.int32))
+        e = b.export()
+        assert np.array_equal(e["regions"][ok], z["moved_regions_" + variant][ok].astype(np.float64))
+        assert np.array_equal(e["region_counter"][ok], z["moved_counter_" + variant][ok].astype(np.float64))
