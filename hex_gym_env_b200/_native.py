@@ -61,7 +61,9 @@ def build(force=False, verbose=False, jobs=None):
     def stale():
         if not os.path.exists(LIB_PATH):
             return True
-        have = [s for s in SOURCES if os.path.exists(s)]    # an installed package may ship the library without every source
+        if not os.path.isfile(ROOT_HEADER):
+            return False      # an installed package (no repository around it): file times say nothing there, the shipped library is used
+        have = [s for s in SOURCES if os.path.exists(s)]
         return any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in have)
 
     try:

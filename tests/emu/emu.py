@@ -44,6 +44,9 @@ def lib():
         L.emu_rollout.argtypes = [vp, i32] + [vp] * 6
         L.emu_force_sweep.argtypes = [i32]
         L.emu_import_labels.argtypes = [vp] * 5
+        L.emu_philox4x32_10.argtypes = [vp] * 3
+        L.emu_draw01.restype = ctypes.c_double
+        L.emu_draw01.argtypes = [u64, u64, ctypes.c_uint32]
         _LIB = L
     return _LIB
 

@@ -253,6 +253,11 @@ void emu_import_labels(void *h, const int8_t *board_true, const uint8_t *planes,
     emu_env *e = (emu_env *)h;
     for (long long g = 0; g < e->base.G; ++g) import_labels_game(e->base, e->N, g, board_true, planes, to_move, import_mask);
 }
+// the device's Philox4x32-10 and draw construction on their own (tests/test_philox.py: Random123 known-answer vectors)
+void emu_philox4x32_10(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out2) {
+    philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1], out2[0], out2[1]);
+}
+double emu_draw01(unsigned long long seed, unsigned long long game, uint32_t idx) { return draw01(seed, game, idx); }
 void emu_stats(void *h, int64_t *out8) {
     emu_env *e = (emu_env *)h;
     for (int i = 0; i < 8; ++i) out8[i] = e->base.stats[i];
