@@ -428,7 +428,7 @@ def run_gpu(args):
 
     # ------------------------------------------------ end-to-end leg: host actions in, host obs/mask/reward/done out
     E = min(K, args.e2e_steps)
-    Ew = 8     # untimed: also lets the adaptive transport split settle
+    Ew = 12    # untimed: also lets the adaptive transport split settle
     # (untimed) record a legal random trajectory on the device so that the timed loop replays HOST actions
     rec = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                    auto_reset=True)
@@ -446,7 +446,7 @@ def run_gpu(args):
     del rec
     def e2e_leg(mode):
         """E timed steps of the host-buffer call hexb_step_host. mode "adaptive" = the call as shipped (obs + mask of some games
-        as plain DMA copies, of the others as 2 bits per cell expanded by host threads, split adapted to the two measured rates);
+        as plain DMA copies, of the others as 2 bits per cell expanded by host threads, the split found by a hill climb on the call's duration);
         "dma" = plain copies only (hexb_set_host_transport(1)); "packed" = 2-bit transport only (0)."""
         env = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                        auto_reset=True)

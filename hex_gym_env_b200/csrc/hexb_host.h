@@ -21,6 +21,7 @@ struct hexb_env {
     int host_pending, host_adapt, host_frac_fixed;
     double host_dma_frac;          // share of the games whose obs / mask rows travel as plain bytes by DMA
     double host_dma_bytes;
+    double host_t0_ms, host_hc_last_ms, host_hc_dir, host_hc_stride;   // hill climb on the call's duration (host_step_finish)
     long long host_plan_words, host_plan_first, host_slice_lo[4], host_slice_hi[4];
     uint32_t *host_packed;         // pinned staging of the packed words (cudaHostAlloc, owned by the handle)
     const uint32_t *host_packed_src;

@@ -303,6 +303,8 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     {   // host-buffer step: adaptive DMA / packed split unless HEXB_HOST_DMA_FRACTION pins it (1 = plain DMA only)
         const char *hf = getenv("HEXB_HOST_DMA_FRACTION");
         e->host_dma_frac = 0.5;
+        e->host_hc_dir = -1.0;
+        e->host_hc_stride = 0.2;
         if (hf) {
             const double f = atof(hf);
             if (f >= 0.0 && f <= 1.0) { e->host_dma_frac = f; e->host_frac_fixed = 1; }
@@ -456,7 +458,7 @@ static HostWs carve_ws(const hexb_env *env, void *workspace) {
 // together) and the host cores' own store bandwidth (~50 GB/s on 16 cores, ~130 GB/s on 32) are separate bottlenecks. So the
 // games of a step are split: the first `dma_games` games' obs / mask rows are copied as they are, the others cross PCIe as
 // 2 bits per cell (K10) and host threads expand them into the same arrays (hexb_hostpack.cpp) while the DMA runs. The split
-// adapts from call to call to the two measured rates; the bytes that arrive are identical for every split.
+// adapts from call to call (host_step_finish); the bytes that arrive are identical for every split.
 struct HostPlan {
     long long dma_games;      // games [0, dma_games) by DMA, [dma_games, G) packed
     long long first_word;     // first packed word (16 cells each) of the packed part
@@ -540,34 +542,37 @@ static double now_ms() {
     return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
-// Finish the pending step: expand the packed slices as they arrive, wait for the DMA part, and (adaptive mode) move the split
-// towards the ratio of the two measured rates.
+// Finish the pending step: expand the packed slices as they arrive, wait for the DMA part, and (adaptive mode) move the split.
+// The two paths are not independent - on a box where several GPUs copy at once they share the host's memory system, and plain
+// DMA bytes turned out more expensive there than host-written ones (8 GPUs: all-packed 15.1 ms, 34 % DMA 18.4 ms, all-DMA 22 ms;
+// one GPU: 6.3 / 4.3 (56 % DMA) / 5.1 ms) - so balancing two measured rates finds the wrong split. The controller is a plain
+// hill climb on the call's own duration instead: keep moving the split in the direction that made the last call faster,
+// reverse and shorten the stride when it got slower.
 static int host_step_finish(hexb_env *env, bool adapt) {
     env->host_pending = 0;
     CK(cudaSetDevice(env->cfg.device));
     const long long cells = (long long)env->cfg.num_games * env->cfg.board_size * env->cfg.board_size;
-    double cpu_ms = 0.0;
     if (env->host_plan_words > 0) {
         for (int k = 0; k < kHostSlices; ++k) {
             CK(cudaEventSynchronize(env->host_ev_slice[k]));
             const long long lo = env->host_slice_lo[k], hi = env->host_slice_hi[k];
-            if (hi > lo) {
-                const double t0 = now_ms();
-                hexb_hostpack_expand(env->host_packed_src, lo, hi - lo, cells, env->cfg.variant, env->host_obs, env->host_mask);
-                cpu_ms += now_ms() - t0;
-            }
+            if (hi > lo) hexb_hostpack_expand(env->host_packed_src, lo, hi - lo, cells, env->cfg.variant, env->host_obs, env->host_mask);
         }
     }
     CK(cudaEventSynchronize(env->host_ev));
-    if (adapt && env->host_plan_words > 0 && env->host_dma_bytes > 0.0 && cpu_ms > 0.0) {
-        float dma_ms = 0.f;
-        if (cudaEventElapsedTime(&dma_ms, env->host_ev_dma0, env->host_ev) == cudaSuccess && dma_ms > 0.f) {
-            const double cpu_bytes = 2.0 * 16.0 * (double)env->host_plan_words;
-            const double d = env->host_dma_bytes / dma_ms, e = cpu_bytes / cpu_ms;   // bytes per ms of each path, under contention
-            double f = d / (d + e);
-            f = 0.5 * env->host_dma_frac + 0.5 * f;
-            env->host_dma_frac = f < 0.05 ? 0.05 : (f > 0.95 ? 0.95 : f);
+    if (adapt) {
+        const double ms = now_ms() - env->host_t0_ms;
+        if (env->host_hc_last_ms > 0.0) {
+            if (ms > env->host_hc_last_ms * 0.995) {      // not faster: turn round, shorter stride
+                env->host_hc_dir = -env->host_hc_dir;
+                env->host_hc_stride = env->host_hc_stride * 0.6 < 0.03 ? 0.03 : env->host_hc_stride * 0.6;
+            }
         }
+        env->host_hc_last_ms = ms;
+        double f = env->host_dma_frac + env->host_hc_dir * env->host_hc_stride;
+        if (f <= 0.0) { f = 0.0; env->host_hc_dir = 1.0; }      // at an end of the range the next probe goes inwards
+        if (f >= 0.97) { f = 0.97; env->host_hc_dir = -1.0; }
+        env->host_dma_frac = f;
     }
     return HEXB_OK;
 }
@@ -589,20 +594,22 @@ int32_t hexb_step_host_begin(hexb_env *env, void *workspace, const int32_t *acti
         if (rc != HEXB_OK) return rc;
     }
     env->host_adapt = hybrid && env->host_frac_fixed == 0;
+    env->host_t0_ms = now_ms();
     return host_step_enqueue(env, workspace, hybrid ? env->host_packed : nullptr, env->host_dma_frac, actions_host, obs_host, mask_host,
                              reward_host, done_host, (cudaStream_t)stream);
 }
 
 int32_t hexb_step_host_end(hexb_env *env) {
     if (!env || !env->host_pending) return HEXB_ERR_ARG;
-    return host_step_finish(env, env->host_adapt != 0);
+    return host_step_finish(env, false);   // the caller's own work sits between _begin and _end: the duration says nothing about the split
 }
 
 int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_host, void *obs_host, uint8_t *mask_host,
                        float *reward_host, uint8_t *done_host, void *stream) {
     const int rc = hexb_step_host_begin(env, workspace, actions_host, obs_host, mask_host, reward_host, done_host, stream);
     if (rc != HEXB_OK) return rc;
-    return hexb_step_host_end(env);
+    if (!env->host_pending) return HEXB_ERR_ARG;
+    return host_step_finish(env, env->host_adapt != 0);
 }
 
 int32_t hexb_set_host_transport(hexb_env *env, double dma_fraction) {
@@ -610,6 +617,9 @@ int32_t hexb_set_host_transport(hexb_env *env, double dma_fraction) {
     if (dma_fraction < 0.0) {            // adaptive (the default)
         env->host_frac_fixed = 0;
         env->host_dma_frac = 0.5;
+        env->host_hc_dir = -1.0;
+        env->host_hc_stride = 0.2;
+        env->host_hc_last_ms = 0.0;
     } else {
         if (dma_fraction > 1.0) return HEXB_ERR_ARG;
         env->host_frac_fixed = 1;
