@@ -120,31 +120,36 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &
         loc.action = a;
         loc.st[6] = 1;
         const bool valid = (unsigned)a < (unsigned)C && !test_bit<N>(rec.occ_rm, a);
+        // The opponent's reply depends on the agent's ply only through the occupancy (one more bit) - not on its labels - so its
+        // k-th-empty selection is computed HERE, beside the agent's place_stone, from the occupancy as it will be: two independent
+        // dependent chains in one basic block instead of one after the other (the step is bound by one warp's instruction latency
+        // for sub-wave launches and co-limited by issue slots for deep ones). The result is used only if the reply really happens
+        // (a legal agent move that does not end the game); otherwise it is dropped, nothing else was touched.
+        int n_reply = 0, x_reply = 0, cell_reply = 0;
         if (!valid) {  // fast_move returns 3, state untouched; the env ends the episode (HexGame.py:252-253, HexSingleGame.py:240-241)
             rec.meta |= M_DONE | M_INVALID | M_AGENT_ENDED;
             loc.reward = P.variant == VARIANT_A ? -100.f : 0.f;
         } else {
+            uint32_t occ2[Geo<N>::W];
+#pragma unroll
+            for (int w = 0; w < Geo<N>::W; ++w) occ2[w] = rec.occ_rm[w] | ((w == (a >> 5)) ? (1u << (a & 31)) : 0u);
+            const double u = P.opp_u ? P.opp_u[2 * g] : u_opp;
+            n_reply = count_empty<N>(occ2);
+            cell_reply = select_kth_zero_colmajor<N>(occ2, choice_of(u, n_reply), x_reply);  // k-th empty cell of the opponent's view
             const bool won = place_stone<N>(L, rec, 0, a, prmA);
             loc.st[7]++;
             rec.meta ^= M_TOMOVE;
             if (won) {
                 rec.meta |= M_DONE | (1u << M_WIN_SHIFT) | M_AGENT_ENDED;
                 loc.reward = 1.f;
-            } else if (P.variant == VARIANT_B && count_empty<N>(rec.occ_rm) == 0) {
+            } else if (P.variant == VARIANT_B && n_reply == 0) {
                 rec.meta |= M_DONE | M_AGENT_ENDED;  // HexSingleGame.py:117-119 (cannot happen from an empty start)
             }
         }
         // ---- opponent ply: continue_game (SelfplayWrapper.py:146-172) / opponent_move (HexGame.py:332-349), random policy
         if (!(rec.meta & M_DONE)) {
-            double u;
-            if (P.opp_u) u = P.opp_u[2 * g];
-            else {
-                rec.draws += (P.variant == VARIANT_B) ? 2u : 1u;  // variant B: rv = random.uniform(0,1), unused (:159), then the choice
-                u = u_opp;
-            }
-            const int n = count_empty<N>(rec.occ_rm);
-            int x;
-            const int cell = select_kth_zero_colmajor<N>(rec.occ_rm, choice_of(u, n), x);  // k-th empty cell of the opponent's view
+            if (!P.opp_u) rec.draws += (P.variant == VARIANT_B) ? 2u : 1u;  // variant B: rv = random.uniform(0,1), unused (:159), then the choice
+            const int n = n_reply, x = x_reply, cell = cell_reply;
             const bool won = place_stone<N>(L, rec, 1, cell, prmB);
             // A: the env transposes the move back to the true cell (HexGame.py:341-346); B: the index in the opponent's own view
             if (P.info_opp) opp_move = P.variant == VARIANT_A ? cell : x * N + (cell - x) / N;
