@@ -411,7 +411,7 @@ def run_gpu(args):
         pass
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "hexb_step_kernel<%d, KIND_STEP, %s>" % (N, "several-rows sweep" if (G + 127) // 128 * 4 <= 32 * sms else "one-row sweep"),
+                "kernel": "hexb_step_kernel<%d, KIND_STEP, %s>" % (N, "several-rows sweep" if (G + 127) // 128 * 4 <= sms * (28 if N <= 8 else 12) else "one-row sweep"),
                 "kernel_ms": kern_ms, "bytes_per_env_step": Bm, "bytes_per_launch": G * Bm,
                 "bytes_formula": "B'(N) = 2*(C + 4*(W+2)) [packed state in + out] + 2*C [obs + mask] + 5 [reward + done] (+4 with external actions); C = N*N, W = ceil(C/32)",
                 "frac_contract": G * Bc / (kern_ms * 1e-3) / 1e9 / peak, "bytes_per_env_step_contract": Bc,

@@ -470,9 +470,9 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
         if (!inj_u && !P.eval_state) {  // setup_opponents (:97-103): 80 % the best model, else a uniformly drawn pool entry
             const double rv = draw01(P.seed, gid, rec.draws++);
             int pick = -1;
-            if (!(rv < 0.8)) {
-                const double ui = draw01(P.seed, gid, rec.draws++);
-                pick = P.pool_size > 0 ? choice_of(ui, P.pool_size) : -1;
+            if (!(rv < 0.8)) {   // random.random() for the pool index: the draw is always consumed, its value only matters to a caller-driven opponent
+                const uint32_t at = rec.draws++;
+                if (P.opp_index && P.pool_size > 0) pick = choice_of(draw01(P.seed, gid, at), P.pool_size);
             }
             if (P.opp_index) P.opp_index[gid - (unsigned long long)P.game_offset] = pick;
         }

@@ -643,9 +643,14 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     lc.gridDim = dim3((unsigned)(P.Gpad / kCtaThreads));
     lc.blockDim = dim3(kCtaThreads);
     lc.dynamicSmemBytes = SmemLayout<N>::BYTES;
-    // at most about one wave of warps: the step time is one warp's latency -> the batched relabel sweep; deeper launches are
-    // HBM-bound and run the one-row-per-pass sweep (measured on 1 Mi games 11x11: 99.5 us vs 105.0 us; on 4,096 games 6x6: 6.7 vs 6.0 us)
-    const bool small = chunks <= wave_warps(e->cfg.device);
+    // Which relabel sweep: several rows per pass shortens a warp's dependent chain and pays while the SMs are sparsely filled;
+    // one row per pass executes fewer instructions and wins once a launch is issue- or bandwidth-bound. Measured on the same box
+    // (profiles/r2i_sweep_ab.jsonl, us per step batched / one-row): 11x11 32,768 games 7.79 / 8.12, 65,536 10.25 / 10.11, 131,072
+    // 15.69 / 15.11, 1 Mi 106.4 / 94.9; 7x7 65,536 8.04 / 8.34, 131,072 12.13 / 12.14; 19x19 65,536 17.47 / 17.14. Short rows
+    // (small boards) leave most lanes of a one-row pass idle, so the cross-over comes later there.
+    static const int force_sweep = getenv("HEXB_SWEEP_BATCHED") ? atoi(getenv("HEXB_SWEEP_BATCHED")) : -1;   // experiments: 0 / 1
+    const long long sms = wave_warps(e->cfg.device) / 32;
+    const bool small = force_sweep >= 0 ? force_sweep != 0 : chunks <= sms * (N <= 8 ? 28 : 12);
     if (P.mode == MODE_STEP && P.steps == 1) {
         if (small) CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_STEP, true>, Q));
         else CK(cudaLaunchKernelEx(&lc, hexb_step_kernel<N, KIND_STEP, false>, Q));

@@ -7,7 +7,9 @@ from hex_gym_env_b200 import HexBatch, VARIANT_A, VARIANT_B, AGENT_RANDOM, AGENT
 from bench import capture_steps
 tag = sys.argv[1] if len(sys.argv) > 1 else "build"
 dev = torch.device("cuda", 0)
-CONFIGS = [("6x6 4096", 6, 4096, VARIANT_B, AGENT_RANDOM, 200), ("7x7 65536 A", 7, 65536, VARIANT_A, AGENT_BLACK, 200),
+CONFIGS = [("11x11 32768", 11, 32768, VARIANT_B, AGENT_RANDOM, 200), ("11x11 65536", 11, 65536, VARIANT_B, AGENT_RANDOM, 200),
+           ("7x7 131072 A", 7, 131072, VARIANT_A, AGENT_BLACK, 200), ("19x19 65536", 19, 65536, VARIANT_B, AGENT_RANDOM, 100),
+           ("6x6 4096", 6, 4096, VARIANT_B, AGENT_RANDOM, 200), ("7x7 65536 A", 7, 65536, VARIANT_A, AGENT_BLACK, 200),
            ("11x11 131072", 11, 131072, VARIANT_B, AGENT_RANDOM, 200), ("11x11 1Mi", 11, 1 << 20, VARIANT_B, AGENT_RANDOM, 100),
            ("19x19 1Mi", 19, 1 << 20, VARIANT_B, AGENT_RANDOM, 40)]
 for name, N, G, variant, am, K in CONFIGS:
