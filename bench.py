@@ -315,6 +315,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.set_num_threads(1)     # host-side torch work here is a few scalar reads; idle OpenMP workers would spin on the cores the
+                                 # library's own host threads (packed transport) run on
     numa = pin_rank_cpus(local, local_world)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -428,7 +430,7 @@ def run_gpu(args):
 
     # ------------------------------------------------ end-to-end leg: host actions in, host obs/mask/reward/done out
     E = min(K, args.e2e_steps)
-    Ew = 12    # untimed: also lets the adaptive transport split settle
+    Ew = 24    # untimed: the adaptive transport searches its split during the first 22 calls
     # (untimed) record a legal random trajectory on the device so that the timed loop replays HOST actions
     rec = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                    auto_reset=True)
@@ -446,7 +448,7 @@ def run_gpu(args):
     del rec
     def e2e_leg(mode):
         """E timed steps of the host-buffer call hexb_step_host. mode "adaptive" = the call as shipped (obs + mask of some games
-        as plain DMA copies, of the others as 2 bits per cell expanded by host threads, the split found by a hill climb on the call's duration);
+        as plain DMA copies, of the others as 2 bits per cell expanded by host threads, the split found by timing a few candidates in the first 22 calls);
         "dma" = plain copies only (hexb_set_host_transport(1)); "packed" = 2-bit transport only (0)."""
         env = HexBatch(N, G, variant=VARIANT_B, device=local, seed=args.seed + 1, game_offset=rank * G, agent_mode=AGENT_RANDOM,
                        auto_reset=True)
@@ -455,15 +457,15 @@ def run_gpu(args):
             env.set_host_transport(1.0 if mode == "dma" else 0.0)
         io = env.pinned_io()
         for t in range(Ew):
-            io["actions"].copy_(host_actions[t])
-            env.step_host(io["actions"], io)
+            env.step_host(host_actions[t], io)
         barrier()
         t0 = time.perf_counter()
         e0.record()
         checksum = 0.0
         for t in range(Ew, Ew + E):
-            io["actions"].copy_(host_actions[t])           # this step's inputs, host memory
-            env.step_host(io["actions"], io)               # H2D + kernel + D2H, returns with results in host memory
+            # this step's inputs are a row of pinned host memory; the call copies them to the device, steps, copies the results
+            # back and returns with them in host memory
+            env.step_host(host_actions[t], io)
             checksum += float(io["reward"][0]) + float(io["obs"][G - 1, N - 1, N - 1]) + float(io["mask"][G - 1, N * N - 1])   # host reads of the step's results
         e1.record()
         barrier()

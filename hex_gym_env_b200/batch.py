@@ -244,6 +244,17 @@ class HexBatch(object):
         check(self._lib.hexb_get_host_transport(self._h, ctypes.byref(f)))
         return f.value
 
+    def _host_actions(self, actions_host, io):
+        """Pointer to the step's host actions: a contiguous int32 CPU tensor (e.g. a row of a pinned trajectory) is used as it
+        is; anything else is staged through io["actions"]."""
+        if actions_host is None:
+            return None
+        if isinstance(actions_host, torch.Tensor) and actions_host.dtype == torch.int32 and not actions_host.is_cuda \
+                and actions_host.is_contiguous() and actions_host.numel() == self.G:
+            return _ptr(actions_host)
+        io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        return _ptr(io["actions"])
+
     def _host_ws(self):
         if self._ws is None:
             n = self._lib.hexb_host_workspace_bytes(ctypes.byref(self.cfg))
@@ -254,10 +265,9 @@ class HexBatch(object):
         """step_host split in two: enqueue H2D + step + D2H and return at once (a host-side policy can work meanwhile);
         step_host_end() waits until `io` holds the results. One step may be pending."""
         io = io or self.pinned_io()
-        if actions_host is not None and actions_host is not io["actions"]:
-            io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        ap = self._host_actions(actions_host, io)
         with torch.cuda.device(self.device):
-            check(self._lib.hexb_step_host_begin(self._h, self._host_ws(), _ptr(io["actions"]) if actions_host is not None else None,
+            check(self._lib.hexb_step_host_begin(self._h, self._host_ws(), ap,
                                                  _ptr(io["obs"]) if want_obs else None, _ptr(io["mask"]) if want_mask else None,
                                                  _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
         return io
@@ -274,11 +284,9 @@ class HexBatch(object):
             n = int(self._lib.hexb_host_packed_bytes(ctypes.byref(self.cfg)))
             self._packed = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
         ph = self._packed.data_ptr() + ((-self._packed.data_ptr()) % 64)
-        if actions_host is not None and actions_host is not io["actions"]:
-            io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        ap = self._host_actions(actions_host, io)
         with torch.cuda.device(self.device):
-            check(self._lib.hexb_step_host_packed(self._h, self._host_ws(), ctypes.c_void_p(ph),
-                                                  _ptr(io["actions"]) if actions_host is not None else None, _ptr(io["obs"]),
+            check(self._lib.hexb_step_host_packed(self._h, self._host_ws(), ctypes.c_void_p(ph), ap, _ptr(io["obs"]),
                                                   _ptr(io["mask"]), _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
         return io
 
@@ -287,10 +295,9 @@ class HexBatch(object):
         (one call, copies inside, returns when the results are in host memory). `io` = pinned_io() or compatible CPU
         tensors. actions_host=None: fused agent sampling on the device (no H2D)."""
         io = io or self.pinned_io()
-        if actions_host is not None and actions_host is not io["actions"]:
-            io["actions"].copy_(torch.as_tensor(actions_host, dtype=torch.int32))
+        ap = self._host_actions(actions_host, io)
         with torch.cuda.device(self.device):
-            check(self._lib.hexb_step_host(self._h, self._host_ws(), _ptr(io["actions"]) if actions_host is not None else None,
+            check(self._lib.hexb_step_host(self._h, self._host_ws(), ap,
                                            _ptr(io["obs"]) if want_obs else None, _ptr(io["mask"]) if want_mask else None,
                                            _ptr(io["reward"]), _ptr(io["done"]), self._stream()))
         return io

@@ -21,7 +21,9 @@ struct hexb_env {
     int host_pending, host_adapt, host_frac_fixed;
     double host_dma_frac;          // share of the games whose obs / mask rows travel as plain bytes by DMA
     double host_dma_bytes;
-    double host_t0_ms, host_hc_last_ms, host_hc_dir, host_hc_stride;   // hill climb on the call's duration (host_step_finish)
+    double host_t0_ms;                                   // start of the running synchronous call
+    int host_tune_calls;                                 // position in the split search (tune_next in hexb_kernels.cu)
+    double host_tune_ms[7][3], host_tune_best, host_tune_best_ms;
     long long host_plan_words, host_plan_first, host_slice_lo[4], host_slice_hi[4];
     uint32_t *host_packed;         // pinned staging of the packed words (cudaHostAlloc, owned by the handle)
     const uint32_t *host_packed_src;

@@ -303,8 +303,6 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     {   // host-buffer step: adaptive DMA / packed split unless HEXB_HOST_DMA_FRACTION pins it (1 = plain DMA only)
         const char *hf = getenv("HEXB_HOST_DMA_FRACTION");
         e->host_dma_frac = 0.5;
-        e->host_hc_dir = -1.0;
-        e->host_hc_stride = 0.2;
         if (hf) {
             const double f = atof(hf);
             if (f >= 0.0 && f <= 1.0) { e->host_dma_frac = f; e->host_frac_fixed = 1; }
@@ -542,12 +540,61 @@ static double now_ms() {
     return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
 }
 
-// Finish the pending step: expand the packed slices as they arrive, wait for the DMA part, and (adaptive mode) move the split.
-// The two paths are not independent - on a box where several GPUs copy at once they share the host's memory system, and plain
-// DMA bytes turned out more expensive there than host-written ones (8 GPUs: all-packed 15.1 ms, 34 % DMA 18.4 ms, all-DMA 22 ms;
-// one GPU: 6.3 / 4.3 (56 % DMA) / 5.1 ms) - so balancing two measured rates finds the wrong split. The controller is a plain
-// hill climb on the call's own duration instead: keep moving the split in the direction that made the last call faster,
-// reverse and shorten the stride when it got slower.
+// Adaptive split of the host transport. The two paths are not independent - on a box where several GPUs copy at once they
+// share the host's memory system, and plain DMA bytes turned out more expensive there than host-written ones (8 GPUs: all packed
+// 15.1 ms, 34 % DMA 18.4 ms, all DMA 22 ms per step; one GPU: 6.3 / 4.2 (60 % DMA) / 5.1 ms) - so balancing two measured rates
+// finds the wrong split, and a hill climb on single call durations random-walks on their noise (both were tried, profiles/README).
+// What is robust is a small tournament: after one throw-away call (it allocates the staging), five coarse splits are timed three
+// times each in rotation, the best median wins, its two neighbours at +-0.125 are timed the same way, and the winner stays.
+// 22 calls in all; the search restarts every 8,192 calls in case the box's load has changed.
+static const double kCoarse[5] = {0.0, 0.25, 0.5, 0.75, 0.97};
+static double median3(const double *v) {
+    const double a = v[0], b = v[1], c = v[2];
+    return a > b ? (b > c ? b : (a > c ? c : a)) : (a > c ? a : (b > c ? c : b));
+}
+static double tune_candidate(const hexb_env *env, int k) {   // k-th split of the running search (0..4 coarse, 5..6 fine)
+    if (k < 5) return kCoarse[k];
+    const double f = env->host_tune_best + (k == 5 ? -0.125 : 0.125);
+    return f < 0.0 ? 0.0 : (f > 0.97 ? 0.97 : f);
+}
+static void tune_next(hexb_env *env, double ms) {
+    int &n = env->host_tune_calls;
+    if (n == 0) {                       // throw-away call done: start the coarse round
+        n = 1;
+        env->host_dma_frac = kCoarse[0];
+        return;
+    }
+    if (n <= 15) {                      // coarse: call n measured candidate (n-1) % 5, sample (n-1) / 5
+        env->host_tune_ms[(n - 1) % 5][(n - 1) / 5] = ms;
+        if (n == 15) {
+            int best = 0;
+            for (int k = 1; k < 5; ++k)
+                if (median3(env->host_tune_ms[k]) < median3(env->host_tune_ms[best])) best = k;
+            env->host_tune_best = kCoarse[best];
+            env->host_tune_best_ms = median3(env->host_tune_ms[best]);
+        }
+        ++n;
+        env->host_dma_frac = n <= 15 ? kCoarse[(n - 1) % 5] : tune_candidate(env, 5);
+        return;
+    }
+    if (n <= 21) {                      // fine: call n measured candidate 5 + (n-16) % 2, sample (n-16) / 2
+        env->host_tune_ms[5 + (n - 16) % 2][(n - 16) / 2] = ms;
+        if (n == 21) {
+            double f = env->host_tune_best, t = env->host_tune_best_ms;
+            for (int k = 5; k < 7; ++k)
+                if (median3(env->host_tune_ms[k]) < t) { t = median3(env->host_tune_ms[k]); f = tune_candidate(env, k); }
+            env->host_dma_frac = f;     // settled
+            ++n;
+            return;
+        }
+        ++n;
+        env->host_dma_frac = tune_candidate(env, 5 + (n - 16) % 2);
+        return;
+    }
+    if (++n > 22 + 8192) n = 1, env->host_dma_frac = kCoarse[0];   // search again after a while
+}
+
+// Finish the pending step: expand the packed slices as they arrive, wait for the DMA part, and (adaptive mode) feed the search.
 static int host_step_finish(hexb_env *env, bool adapt) {
     env->host_pending = 0;
     CK(cudaSetDevice(env->cfg.device));
@@ -560,20 +607,7 @@ static int host_step_finish(hexb_env *env, bool adapt) {
         }
     }
     CK(cudaEventSynchronize(env->host_ev));
-    if (adapt) {
-        const double ms = now_ms() - env->host_t0_ms;
-        if (env->host_hc_last_ms > 0.0) {
-            if (ms > env->host_hc_last_ms * 0.995) {      // not faster: turn round, shorter stride
-                env->host_hc_dir = -env->host_hc_dir;
-                env->host_hc_stride = env->host_hc_stride * 0.6 < 0.03 ? 0.03 : env->host_hc_stride * 0.6;
-            }
-        }
-        env->host_hc_last_ms = ms;
-        double f = env->host_dma_frac + env->host_hc_dir * env->host_hc_stride;
-        if (f <= 0.0) { f = 0.0; env->host_hc_dir = 1.0; }      // at an end of the range the next probe goes inwards
-        if (f >= 0.97) { f = 0.97; env->host_hc_dir = -1.0; }
-        env->host_dma_frac = f;
-    }
+    if (adapt) tune_next(env, now_ms() - env->host_t0_ms);
     return HEXB_OK;
 }
 
@@ -617,9 +651,7 @@ int32_t hexb_set_host_transport(hexb_env *env, double dma_fraction) {
     if (dma_fraction < 0.0) {            // adaptive (the default)
         env->host_frac_fixed = 0;
         env->host_dma_frac = 0.5;
-        env->host_hc_dir = -1.0;
-        env->host_hc_stride = 0.2;
-        env->host_hc_last_ms = 0.0;
+        env->host_tune_calls = 0;
     } else {
         if (dma_fraction > 1.0) return HEXB_ERR_ARG;
         env->host_frac_fixed = 1;

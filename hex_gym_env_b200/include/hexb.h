@@ -142,8 +142,9 @@ int32_t hexb_step_host(hexb_env *env, void *workspace, const int32_t *actions_ho
 
 /* Transport of the observation + mask bytes inside hexb_step_host (they are 2*N*N of the 2*N*N + 5 bytes per game): by default
  * the games of a step are split between plain DMA copies and a 2-bit-per-cell transport that host threads expand into the same
- * arrays while the DMA runs (see hexb_step_host_packed); the split adapts from call to call (a hill climb on the call's own
- * duration: which mix is fastest depends on how many GPUs share the host's memory system). The bytes that arrive do not depend on it. dma_fraction in [0,1] pins the share of games copied as plain bytes (1 = no host threads,
+ * arrays while the DMA runs (see hexb_step_host_packed); the split is searched during the first 22 calls (five coarse splits and
+ * two neighbours of the best, three timed calls each - which mix is fastest depends on how many GPUs share the host's memory
+ * system) and then kept. The bytes that arrive do not depend on it. dma_fraction in [0,1] pins the share of games copied as plain bytes (1 = no host threads,
  * plain DMA only, the behaviour of library version 1.2), a negative value selects the adaptive default again. Environment:
  * HEXB_HOST_DMA_FRACTION, HEXB_HOST_THREADS. Applies when obs_host and mask_host are both given, obs_dtype is HEXB_OBS_I8
  * and the shard has at least 4,096 games. */
