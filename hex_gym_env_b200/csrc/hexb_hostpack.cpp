@@ -209,10 +209,10 @@ void pool_start() {   // called with g_submit held
 
 }  // namespace
 
+// Size of the pool (as it is, or as it will be: the threads are only created by the first expansion)
 extern "C" __attribute__((visibility("hidden"))) int hexb_hostpack_threads(void) {
     pthread_mutex_lock(&g_submit);
-    pool_start();
-    const int n = g_pool.nthreads;
+    const int n = g_pool.started ? g_pool.nthreads : pool_threads();
     pthread_mutex_unlock(&g_submit);
     return n;
 }

@@ -152,3 +152,36 @@ def test_sharding_invariance_full_size():
     for r, sh in enumerate(shards):
         assert torch.equal(sh.state_dict()["state"][:per_shard], ws[r * per_shard:(r + 1) * per_shard]), r
     assert properties.checksum(torch.cat([sh._out["obs"] for sh in shards])) == properties.checksum(whole._out["obs"])
+
+
+def test_fullsize_host_transports_and_float32_observations():
+    """1 Mi games of 11x11 (BASELINE config 3's size): the host-buffer step with every transport (plain DMA, all packed, the
+    library's own search) and the float32 observation dtype return the device step's bytes, whole arrays compared."""
+    from hex_gym_env_b200 import HexBatch
+    N, G, T = 11, 1 << 20, 26
+    dev = HexBatch(N, G, variant=1, device=0, seed=3, agent_mode=2)
+    f32 = HexBatch(N, G, variant=1, device=0, seed=3, agent_mode=2, obs_dtype=torch.float32)
+    hosts = []
+    for frac in (1.0, 0.0, -1.0):
+        h = HexBatch(N, G, variant=1, device=0, seed=3, agent_mode=2)
+        h.set_host_transport(frac)
+        h.reset()
+        hosts.append((frac, h, h.pinned_io()))
+    dev.reset(); f32.reset()
+    for t in range(T):
+        o = dev.step()
+        of = f32.step()
+        check = t in (0, 1, 12, T - 1)      # (the adaptive handle walks through all its candidate splits over these 26 calls)
+        if check:
+            assert torch.equal(of["obs"], o["obs"].float()) and torch.equal(of["mask"], o["mask"]), ("f32", t)
+            want = {k: o[k].cpu().numpy() for k in ("obs", "mask", "reward", "done")}
+        for frac, h, io in hosts:
+            if check:
+                io["obs"].fill_(77); io["mask"].fill_(77)
+            h.step_host(None, io)
+            if check:
+                for k in ("obs", "mask", "reward", "done"):
+                    assert np.array_equal(io[k].numpy(), want[k]), (k, t, frac)
+    assert 0.0 <= hosts[2][1].host_transport() <= 1.0
+    for _, h, _ in hosts:
+        assert torch.equal(h.stats(), dev.stats())
