@@ -20,7 +20,7 @@ steps / max over ranks of [e0, e1] (`ms_per_rank` lists every rank's figure).
 
 roofline: achieved = bytes this design must move per launch / the step kernel's average duration in that same bracket (it
 holds nothing else), B'(N) = 2*(C + 4*(W+2)) + 2*C + 5 bytes per env step (packed state in and out, obs, mask, reward, done;
-537 B at 11x11; DESIGN.md section 6). `frac_contract` is the same time against SURVEY.md 8(d)'s B(N) = 831 B, which assumes a
+537 B at 11x11; DESIGN.md section 3). `frac_contract` is the same time against SURVEY.md 8(d)'s B(N) = 831 B, which assumes a
 state twice as large as this design's and therefore exceeds 1.
 
 e2e: the same step through hexb_step_host with pinned HOST buffers (actions H2D, obs/mask/reward/done D2H inside the timed
@@ -417,7 +417,7 @@ def run_gpu(args):
                 "kernel_ms": kern_ms, "bytes_per_env_step": Bm, "bytes_per_launch": G * Bm,
                 "bytes_formula": "B'(N) = 2*(C + 4*(W+2)) [packed state in + out] + 2*C [obs + mask] + 5 [reward + done] (+4 with external actions); C = N*N, W = ceil(C/32)",
                 "frac_contract": G * Bc / (kern_ms * 1e-3) / 1e9 / peak, "bytes_per_env_step_contract": Bc,
-                "note": "achieved/frac count the bytes this design must move per env step (DESIGN.md section 6); frac_contract uses SURVEY "
+                "note": "achieved/frac count the bytes this design must move per env step (DESIGN.md section 3); frac_contract uses SURVEY "
                         "8(d)'s B(N), whose state term (290 B per game each way) is twice this design's 145 B and therefore exceeds 1. "
                         "20 MiB of the state stay L2-resident across steps, so HBM sees slightly less than bytes_per_launch "
                         "(traffic = ncu dram bytes per launch)",

@@ -11,6 +11,10 @@
 
 using namespace hexb;
 
+#ifndef HEXB_PDL_EARLY
+#define HEXB_PDL_EARLY 1
+#endif
+
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -362,7 +366,13 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         if (KIND == KIND_ROLLOUT) __syncwarp();
     }
 
-    // ---- chunk out
+    // ---- chunk out. The next grid on the stream (the next env step) may start launching now: it still waits at its
+    //      griddepcontrol.wait for this whole grid to complete and flush, but its CTAs are dispatched and set up while this grid's
+    //      chunks drain to global memory: about 1 % on every batch size measured (profiles/r2n_pdl_ab.jsonl; HEXB_PDL_EARLY=0
+    //      compiles the trigger out). Triggering at the TOP of the kernel was measured and rejected in round 1.
+#if HEXB_PDL_EARLY
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     fence_async_smem();  // generic-proxy writes to shared memory -> visible to the async proxy
     __syncwarp();
     if (lane == 0) {
@@ -546,7 +556,7 @@ __global__ void __launch_bounds__(WPC * 32) hexb_coop_kernel(const Params P) {
         if (KIND == KIND_ROLLOUT && tt + 1 < steps) __syncthreads();   // the next step reads what this one wrote
     }
 
-    // ---- chunk out
+    // ---- chunk out (no early launch trigger here: with at most one chunk per SM it measured 2 % slower, profiles/r2n_pdl_ab.jsonl)
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
