@@ -103,7 +103,7 @@ def build(force=False, verbose=False, jobs=None):
                     logs = list(ex.map(_run, todo))
                 tmp = "%s.%d.tmp" % (LIB_PATH, os.getpid())
                 try:
-                    _run([_nvcc(), "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + [u[0] for u in units] + ["-lpthread"])
+                    _run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", tmp] + [u[0] for u in units] + ["-lpthread"])
                 except RuntimeError:
                     if os.path.exists(tmp):
                         os.remove(tmp)

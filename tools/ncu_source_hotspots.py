@@ -6,7 +6,11 @@
 Joins `ncu -i <rep> --page source --csv` (per-SASS-instruction executed-instruction counts and warp-stall samples; the report
 must come from `ncu --set full --import-source on`) with the line table `nvdisasm -g` prints for the same kernel of the same
 library build (-lineinfo), and aggregates by source line and by enclosing function. source_dir holds the .cu/.cuh files the
-library was built from (default hex_gym_env_b200/csrc)."""
+library was built from (default hex_gym_env_b200/csrc).
+
+Since the step kernels are compiled one object per board size from the SAME source file (hexb_step_inst.cu), `cuobjdump -xelf all`
+on libhexb.so writes every per-size cubin under one name; pass the object of the size profiled instead of the library
+(hex_gym_env_b200/build/step_11.o: same build, same code)."""
 import collections
 import csv
 import glob
