@@ -117,6 +117,8 @@ struct Params {
     int8_t *info_winner;  // [G] nullable, MODE_STEP out: env.winner after the step: -1 None, 0 BLACK, 1 WHITE, 3 illegal move
     int out_hint;           // 1 = the obs / mask stores also carry an explicit L2 evict_first policy (off; HEXB_L2_OUT_HINT=1 turns it on)
     long long keep_chunks;  // chunks [0, keep_chunks) are kept in L2 between steps (evict_last), the others streamed (evict_first)
+    int early;     // 1: the record-only half of the env step (game_step_pre) runs on record words fetched with plain loads while
+                   // the chunk's bulk copy is still in flight (set per launch: pays for launches of at most one wave)
     uint32_t one;  // always 1, but opaque to the compiler: a * one + b is issued as IMAD on the FMA pipe (see fma_add)
     int obs_f32;   // 1: obs / term_obs point to float32 buffers (hexb_config.obs_dtype = HEXB_OBS_F32: the reference's observation
                    // is a float array, HexSingleGame.py:175, and SB3's policies take float32), 0: int8

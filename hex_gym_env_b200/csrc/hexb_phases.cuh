@@ -87,10 +87,38 @@ HEXB_HD void pre_draws(const Params &P, uint32_t meta, uint32_t draws, unsigned 
 // episode counters. With actions == null the agent is BaseRandomPolicy / random_policy itself and takes one draw from the
 // game's stream first, exactly like the reference loop  a = BaseRandomPolicy().choose_action(obs); env.step(a).
 // L = this game's C label bytes. prmA / prmB = relabel requests of the two plies, flg = row job for the warp.
+// game_step comes in two parts so that the device can run the first one while the chunk's label bytes are still in flight:
+//   game_step_pre   needs the game's RECORD only (occupancy, meta): the agent's action (given, or the k-th empty cell of its
+//                   draw), its validity, and - speculatively, from the occupancy as it will be - the cell of the opponent's reply
+//                   (the reply depends on the agent's ply only through one occupancy bit, not on its labels; it is used only if
+//                   the reply really happens, i.e. after a legal agent move that does not end the game)
+//   game_step_post  the two place_stone calls on the label bytes, reward / done, accounting, auto-reset
+struct Pre {
+    int a, n_reply, x_reply, cell_reply;
+    bool valid;
+};
 template <int N>
-HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &rec, double u_agent, double u_opp, Loc &loc,
-                       uint32_t &prmA, uint32_t &prmB, uint32_t &flg) {
+HEXB_HD void game_step_pre(const Params &P, long long g, const Rec<N> &rec, double u_agent, double u_opp, Pre &q) {
     constexpr int C = Geo<N>::C;
+    q.a = -1; q.n_reply = 0; q.x_reply = 0; q.cell_reply = 0; q.valid = false;
+    if (g >= P.G || !(rec.meta & M_LIVE) || (rec.meta & M_DONE)) return;
+    int a;
+    if (P.actions) a = P.actions[g];
+    else a = select_kth_zero<N>(rec.occ_rm, choice_of(u_agent, count_empty<N>(rec.occ_rm)));
+    q.a = a;
+    q.valid = (unsigned)a < (unsigned)C && !test_bit<N>(rec.occ_rm, a);
+    if (q.valid) {
+        uint32_t occ2[Geo<N>::W];
+#pragma unroll
+        for (int w = 0; w < Geo<N>::W; ++w) occ2[w] = rec.occ_rm[w] | ((w == (a >> 5)) ? (1u << (a & 31)) : 0u);
+        const double u = P.opp_u ? P.opp_u[2 * g] : u_opp;
+        q.n_reply = count_empty<N>(occ2);
+        q.cell_reply = select_kth_zero_colmajor<N>(occ2, choice_of(u, q.n_reply), q.x_reply);  // k-th empty cell of the opponent's view
+    }
+}
+template <int N>
+HEXB_HD void game_step_post(uint8_t *L, const Params &P, long long g, int t, Rec<N> &rec, const Pre &q, Loc &loc,
+                            uint32_t &prmA, uint32_t &prmB, uint32_t &flg) {
     const long long o = g + (long long)t * P.G;  // output slot: step t of a multi-step launch (hexb_rollout) writes row t of [T,G]
     loc.reward = 0.f;
     loc.action = -1;
@@ -111,45 +139,31 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &
         loc.reward = P.variant == VARIANT_A ? stale_reward_A(rec.meta) : 0.f;
     } else {
         // ---- agent ply
-        int a;
-        if (P.actions) a = P.actions[g];
-        else {
-            rec.draws++;
-            a = select_kth_zero<N>(rec.occ_rm, choice_of(u_agent, count_empty<N>(rec.occ_rm)));
-        }
+        if (!P.actions) rec.draws++;
+        const int a = q.a;
         loc.action = a;
         loc.st[6] = 1;
-        const bool valid = (unsigned)a < (unsigned)C && !test_bit<N>(rec.occ_rm, a);
-        // The opponent's reply depends on the agent's ply only through the occupancy (one more bit) - not on its labels - so its
-        // k-th-empty selection is computed HERE, beside the agent's place_stone, from the occupancy as it will be: two independent
-        // dependent chains in one basic block instead of one after the other (the step is bound by one warp's instruction latency
-        // for sub-wave launches and co-limited by issue slots for deep ones). The result is used only if the reply really happens
-        // (a legal agent move that does not end the game); otherwise it is dropped, nothing else was touched.
-        int n_reply = 0, x_reply = 0, cell_reply = 0;
-        if (!valid) {  // fast_move returns 3, state untouched; the env ends the episode (HexGame.py:252-253, HexSingleGame.py:240-241)
+        if (!q.valid) {  // fast_move returns 3, state untouched; the env ends the episode (HexGame.py:252-253, HexSingleGame.py:240-241)
             rec.meta |= M_DONE | M_INVALID | M_AGENT_ENDED;
             loc.reward = P.variant == VARIANT_A ? -100.f : 0.f;
         } else {
-            uint32_t occ2[Geo<N>::W];
-#pragma unroll
-            for (int w = 0; w < Geo<N>::W; ++w) occ2[w] = rec.occ_rm[w] | ((w == (a >> 5)) ? (1u << (a & 31)) : 0u);
-            const double u = P.opp_u ? P.opp_u[2 * g] : u_opp;
-            n_reply = count_empty<N>(occ2);
-            cell_reply = select_kth_zero_colmajor<N>(occ2, choice_of(u, n_reply), x_reply);  // k-th empty cell of the opponent's view
             const bool won = place_stone<N>(L, rec, 0, a, prmA);
             loc.st[7]++;
             rec.meta ^= M_TOMOVE;
             if (won) {
                 rec.meta |= M_DONE | (1u << M_WIN_SHIFT) | M_AGENT_ENDED;
                 loc.reward = 1.f;
-            } else if (P.variant == VARIANT_B && n_reply == 0) {
+            } else if (P.variant == VARIANT_B && q.n_reply == 0) {
                 rec.meta |= M_DONE | M_AGENT_ENDED;  // HexSingleGame.py:117-119 (cannot happen from an empty start)
             }
         }
         // ---- opponent ply: continue_game (SelfplayWrapper.py:146-172) / opponent_move (HexGame.py:332-349), random policy
         if (!(rec.meta & M_DONE)) {
             if (!P.opp_u) rec.draws += (P.variant == VARIANT_B) ? 2u : 1u;  // variant B: rv = random.uniform(0,1), unused (:159), then the choice
-            const int n = n_reply, x = x_reply, cell = cell_reply;
+            const int n = q.n_reply, x = q.x_reply, cell = q.cell_reply;
+            // (Reading the reply's neighbourhood before the agent's stone is written - stone_merge for both plies side by side,
+            // stone_commit afterwards - was measured and rejected: 15.15 vs 15.00 us at 131,072 games of 11x11, 100.0 vs 98.8 at
+            // 1 Mi, profiles/r2p_merge2_ab.jsonl: the reply does not always happen, and the extra live registers cost more.)
             const bool won = place_stone<N>(L, rec, 1, cell, prmB);
             // A: the env transposes the move back to the true cell (HexGame.py:341-346); B: the index in the opponent's own view
             if (P.info_opp) opp_move = P.variant == VARIANT_A ? cell : x * N + (cell - x) / N;
@@ -193,6 +207,13 @@ HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &
         }
     }
     if (!(flg & F_RESET) && ((prmA | prmB) & P_NEED)) flg |= F_RELABEL;
+}
+template <int N>
+HEXB_HD void game_step(uint8_t *L, const Params &P, long long g, int t, Rec<N> &rec, double u_agent, double u_opp, Loc &loc,
+                       uint32_t &prmA, uint32_t &prmB, uint32_t &flg) {
+    Pre q;
+    game_step_pre<N>(P, g, rec, u_agent, u_opp, q);
+    game_step_post<N>(L, P, g, t, rec, q, loc, prmA, prmB, flg);
 }
 
 // ---------------------------------------------------------------------------------------------- half step (hexb_half_step)

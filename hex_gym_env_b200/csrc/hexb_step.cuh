@@ -248,15 +248,23 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     uint32_t *recw = reinterpret_cast<uint32_t *>(chunk + Geo<N>::CHUNK_LAB) + lane;   // this lane's record word 0 (shared memory)
     uint32_t *lab32 = reinterpret_cast<uint32_t *>(chunk);
     double u_agent = 0.0, u_opp = 0.0;
+    Rec<N> rec = {};
+    Pre pre = {-1, 0, 0, 0, false};
+    const bool early = STEP_ONLY && P.early;   // kernel-uniform: the record-only part of the step runs before the chunk has landed
     if (STEP_ONLY && g < P.G) {
         const uint32_t *grec = reinterpret_cast<const uint32_t *>(gl + Geo<N>::CHUNK_LAB) + lane;
-        pre_draws(P, grec[Geo<N>::W * kRecStride], grec[(Geo<N>::W + 1) * kRecStride],
-                  (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+        if (early) {
+            load_rec<N>(grec, rec);
+            pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+            game_step_pre<N>(P, g, rec, u_agent, u_opp, pre);
+        } else {
+            pre_draws(P, grec[Geo<N>::W * kRecStride], grec[(Geo<N>::W + 1) * kRecStride],
+                      (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+        }
     }
     __syncwarp();  // the barrier's initialisation is visible to the other lanes
     mbar_wait(bar, 0);
-    Rec<N> rec;
-    load_rec<N>(recw, rec);
+    if (!early) load_rec<N>(recw, rec);
     uint8_t *L = chunk + lane * C;
 
     // One env step per iteration. hexb_step launches with steps == 1; hexb_rollout runs T steps with the chunk staying in
@@ -269,7 +277,8 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         if (STEP_ONLY) {
             if (t > 0 && g < P.G) pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
             Loc loc;
-            game_step<N>(L, P, g, t, rec, u_agent, u_opp, loc, prmA, prmB, flg);
+            if (!(early && tt == 0)) game_step_pre<N>(P, g, rec, u_agent, u_opp, pre);
+            game_step_post<N>(L, P, g, t, rec, pre, loc, prmA, prmB, flg);
             // K7: episode statistics - the eight per-game increments are packed into two words (fields wide enough for the
             // sum over 32 lanes), reduced with two redux.sync, and lane 0 adds the non-zero counters to this warp's stripe
             const uint32_t pa = (uint32_t)loc.st[0] | ((uint32_t)loc.st[1] << 6) | ((uint32_t)loc.st[2] << 12) |
@@ -630,7 +639,15 @@ static int launch_tile(const hexb_env *e, const Params &P, cudaStream_t s) {
     lc.attrs = la;
     lc.numAttrs = pdl ? 1 : 0;
     const long long chunks = P.Gpad / kWarp;
-    const Params &Q = P;
+    // The record-only half of the step before the chunk has landed (Params::early): while a launch is at most one wave of warps
+    // every warp waits for its bulk copy at the same time, and the copy of a whole wave's chunks takes longer than the Philox
+    // rounds that used to cover it. Measured on one box (profiles/r2p_early_ab.jsonl, us per step off / on): 11x11 32,768 games
+    // 8.01 / 7.88, 65,536 10.29 / 10.14, 131,072 15.43 / 15.14; 7x7 65,536 8.23 / 8.11, 131,072 12.49 / 12.35; 19x19 65,536
+    // 17.1 / 16.9; no change at 4,096 games; 1 Mi games of 11x11 99.7 / 101.3 (deep launches hide the wait behind other warps and
+    // pay for the second fetch of the record words), hence by launch depth. HEXB_EARLY=0 / 1 forces it (experiments).
+    static const int force_early = getenv("HEXB_EARLY") ? atoi(getenv("HEXB_EARLY")) : -1;
+    Params Q = P;
+    Q.early = (force_early >= 0 ? force_early != 0 : chunks <= wave_warps(e->cfg.device)) ? 1 : 0;
     int form = 1;
     if (P.mode == MODE_STEP) form = e->launch_form ? e->launch_form : auto_form(chunks, e->cfg.device);
     if (form > 1) {   // cooperative form: one CTA of `form` warps per chunk
