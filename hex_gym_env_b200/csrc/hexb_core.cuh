@@ -115,7 +115,7 @@ struct Params {
     uint8_t *to_move;     // [G] MODE_HALF / MODE_RESET out: 0 agent to move, 1 opponent to move, 2 finished
     int32_t *info_opp;    // [G] nullable, MODE_STEP out: the opponent's move of this step (info["last_move_opponent"]), -1 = none
     int8_t *info_winner;  // [G] nullable, MODE_STEP out: env.winner after the step: -1 None, 0 BLACK, 1 WHITE, 3 illegal move
-    int out_hint;           // 1 = the obs / mask stores also carry an explicit L2 evict_first policy (off; HEXB_L2_OUT_HINT=1 turns it on)
+    uint32_t enc_ka, enc_kb, enc_kc;   // observation bytes of a label word: obs = mask * ka + C-stones * kb + kc (enc_consts; per variant)
     long long keep_chunks;  // chunks [0, keep_chunks) are kept in L2 between steps (evict_last), the others streamed (evict_first)
     int early;     // 1: the record-only half of the env step (game_step_pre) runs on record words fetched with plain loads while
                    // the chunk's bulk copy is still in flight (set per launch: pays for launches of at most one wave)
@@ -179,6 +179,17 @@ HEXB_HD double draw01(unsigned long long seed, unsigned long long game, uint32_t
     philox4x32_10(idx, (uint32_t)game, (uint32_t)(game >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), a, b);
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
+
+// The same draw as a real function call, for the restart path (reset_game: up to four draws, taken by one or two lanes of a
+// warp in a step): inlined there, every draw is another copy of the ten Philox rounds in the step kernel, whose
+// instruction-cache footprint is worth more than the call (ncu: 18 % of the stall samples at 1 Mi games were 'no_instructions').
+#if defined(__CUDACC__) && !defined(HEXB_HOST_EMU)
+static __host__ __device__ __noinline__ double draw01_cold(unsigned long long seed, unsigned long long game, uint32_t idx) {
+    return draw01(seed, game, idx);
+}
+#else
+static inline double draw01_cold(unsigned long long seed, unsigned long long game, uint32_t idx) { return draw01(seed, game, idx); }
+#endif
 
 // choice = int(random.random() * n)   (SelfplayWrapper.py:20, minihex/__init__.py:11): one fp64 multiply, truncation.
 HEXB_HD int choice_of(double u, int n) {
@@ -418,19 +429,23 @@ HEXB_HD uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) { return a * one 
 // pipe, which is the busy one in the step kernel (ncu: sm__pipe_alu_cycles_active is the top pipe)
 HEXB_HD uint32_t flags_to_ones(uint32_t f) { return mulhi32(f, 1u << 25); }
 
-template <int VARIANT>
-HEXB_HD void encode_word_v(uint32_t x, uint32_t one, uint32_t &obs, uint32_t &msk) {
-    // 4 ALU-pipe ops (three LOP3 for t's operand, z, c and one for r1) + 4 FMA-pipe ops (the add, two multiply-highs, one IMAD)
+// One label word (4 cells) -> observation bytes + mask bytes, the same code for both variants: with msk = 0x01 per empty cell and
+// c1 = 0x01 per C stone (at most one of them per byte),
+//   variant B   R -> 0xff, C -> 0x01, empty -> 0x00:  obs = 0xffffffff - 0xff * msk - 0xfe * c1   (no byte ever borrows)
+//   variant A   BLACK (= R) 0, WHITE (= C) 1, EMPTY 2: obs = 2 * msk + c1
+// i.e. obs = msk * ka + (c1 * kb + kc) with per-variant constants (Params::enc_k*, filled by enc_consts): two multiply-adds on the
+// FMA pipe and no logic op for the observation itself. Per word: 3 ALU-pipe ops (LOP3: t's operand, z, c1's operand) + 5
+// FMA-pipe ops (one add issued as IMAD, two multiply-highs, two IMAD) - the ALU pipe is the busy one in the step kernel.
+HEXB_HD void enc_consts(int variant, uint32_t &ka, uint32_t &kb, uint32_t &kc) {
+    if (variant == VARIANT_B) { ka = 0u - 0xffu; kb = 0u - 0xfeu; kc = 0xffffffffu; }
+    else { ka = 2u; kb = 1u; kc = 0u; }
+}
+HEXB_HD void encode_word_k(uint32_t x, uint32_t one, uint32_t ka, uint32_t kb, uint32_t kc, uint32_t &obs, uint32_t &msk) {
     const uint32_t t = fma_add(x & 0x7f7f7f7fu, 0x7f7f7f7fu, one);
-    const uint32_t z = ~(t | x) & 0x80808080u;        // 0x80 per EMPTY cell
+    const uint32_t z = ~(t | x) & 0x80808080u;           // 0x80 per EMPTY cell
     const uint32_t c1 = flags_to_ones(x & 0x80808080u);  // 0x01 per C stone
-    msk = flags_to_ones(z);                           // legal == empty
-    if (VARIANT == VARIANT_B) {
-        const uint32_t r1 = (msk | c1) ^ 0x01010101u; // 0x01 per R stone
-        obs = r1 * 0xffu + c1;                        // R -> 0xff, C -> 0x01 (disjoint bytes: the multiply-add cannot carry)
-    } else {
-        obs = msk * 2u + c1;                          // BLACK 0 (= R), WHITE 1 (= C), EMPTY 2
-    }
+    msk = flags_to_ones(z);                              // legal == empty
+    obs = msk * ka + (c1 * kb + kc);
 }
 // one byte, optionally seen from the opponent's side (sign swap; the caller transposes the cell index)
 HEXB_HD uint32_t encode_byte(uint32_t b, int variant, bool opp_view, uint32_t &msk) {
@@ -466,15 +481,15 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
     } else if (P.variant == VARIANT_B) {
         if (!(meta & M_COLOUR_SET)) {  // random.randint(0,1) once per env (SelfplayWrapper.py:72-73)
             int colour = P.agent_mode;
-            if (P.agent_mode == 2) colour = (int)(draw01(P.seed, gid, rec.draws++) * 2.0);
+            if (P.agent_mode == 2) colour = (int)(draw01_cold(P.seed, gid, rec.draws++) * 2.0);
             meta |= M_COLOUR_SET | (colour ? M_TRANSPOSED : 0u);
         }
         if (!inj_u && !P.eval_state) {  // setup_opponents (:97-103): 80 % the best model, else a uniformly drawn pool entry
-            const double rv = draw01(P.seed, gid, rec.draws++);
+            const double rv = draw01_cold(P.seed, gid, rec.draws++);
             int pick = -1;
             if (!(rv < 0.8)) {   // random.random() for the pool index: the draw is always consumed, its value only matters to a caller-driven opponent
                 const uint32_t at = rec.draws++;
-                if (P.opp_index && P.pool_size > 0) pick = choice_of(draw01(P.seed, gid, at), P.pool_size);
+                if (P.opp_index && P.pool_size > 0) pick = choice_of(draw01_cold(P.seed, gid, at), P.pool_size);
             }
             if (P.opp_index) P.opp_index[gid - (unsigned long long)P.game_offset] = pick;
         }
@@ -489,7 +504,7 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
         if (inj_u) u = *inj_u;
         else {
             if (P.variant == VARIANT_B) rec.draws++;  // rv = random.uniform(0,1), unused (:159)
-            u = draw01(P.seed, gid, rec.draws++);
+            u = draw01_cold(P.seed, gid, rec.draws++);
         }
         const int k = choice_of(u, C);         // k-th empty cell of the opponent's view of an empty board
         const int x = k / N, y = k - x * N;    // stored column-major index -> stored (y, x)

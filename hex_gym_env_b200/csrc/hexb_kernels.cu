@@ -297,8 +297,7 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
         const char *kmb = getenv("HEXB_L2_KEEP_MB");
         if (kmb) keep_bytes = atoll(kmb) * (1ll << 20);
         P.keep_chunks = keep_bytes > 0 ? keep_bytes / cb : 0;
-        const char *oh = getenv("HEXB_L2_OUT_HINT");
-        P.out_hint = (P.keep_chunks > 0 && oh && atoi(oh) == 1) ? 1 : 0;
+        enc_consts(P.variant, P.enc_ka, P.enc_kb, P.enc_kc);
     }
     {   // host-buffer step: adaptive DMA / packed split unless HEXB_HOST_DMA_FRACTION pins it (1 = plain DMA only)
         const char *hf = getenv("HEXB_HOST_DMA_FRACTION");

@@ -602,17 +602,17 @@ HEXB_HD void store_tail(uint8_t *base, long long off, long long limit, const Vec
     for (int k = 0; k < 16; ++k)
         if (off + k < limit) base[off + k] = (uint8_t)(a[k >> 2] >> (8 * (k & 3)));
 }
-template <int VARIANT>
-HEXB_HD void encode_vec_v(const Vec4 &in, uint32_t one, Vec4 &o, Vec4 &m) {
-    encode_word_v<VARIANT>(in.x, one, o.x, m.x);
-    encode_word_v<VARIANT>(in.y, one, o.y, m.y);
-    encode_word_v<VARIANT>(in.z, one, o.z, m.z);
-    encode_word_v<VARIANT>(in.w, one, o.w, m.w);
+HEXB_HD void encode_vec_k(const Vec4 &in, uint32_t one, uint32_t ka, uint32_t kb, uint32_t kc, Vec4 &o, Vec4 &m) {
+    encode_word_k(in.x, one, ka, kb, kc, o.x, m.x);
+    encode_word_k(in.y, one, ka, kb, kc, o.y, m.y);
+    encode_word_k(in.z, one, ka, kb, kc, o.z, m.z);
+    encode_word_k(in.w, one, ka, kb, kc, o.w, m.w);
 }
 template <int N>
 HEXB_HD void encode_vec(const Vec4 &in, int variant, Vec4 &o, Vec4 &m) {
-    if (variant == VARIANT_B) encode_vec_v<VARIANT_B>(in, 1u, o, m);
-    else encode_vec_v<VARIANT_A>(in, 1u, o, m);
+    uint32_t ka, kb, kc;
+    enc_consts(variant, ka, kb, kc);
+    encode_vec_k(in, 1u, ka, kb, kc, o, m);
 }
 
 }  // namespace hexb

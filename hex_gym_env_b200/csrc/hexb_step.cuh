@@ -103,46 +103,72 @@ struct SmemLayout {
     static constexpr int BYTES = BAR + kWarpsPerCta * 8;
 };
 
-__device__ __forceinline__ void st_hint(uint4 *p, const uint4 &v, uint64_t policy) {
-    asm volatile("st.global.cs.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
-                 : "memory");
-}
-template <int N, int VARIANT, bool HINT>
-__device__ __forceinline__ void encode_loop(const uint4 *src, uint4 *po, uint4 *pm, int lane, int nthr, uint32_t one, uint64_t pol) {
+template <int N>
+__device__ __forceinline__ void encode_loop(const uint4 *src, uint4 *po, uint4 *pm, int lane, int nthr, const Params &P) {
 #pragma unroll 4
     for (int i = lane; i < Chunk<N>::VECS; i += nthr) {
         const uint4 x = src[i];
         Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
-        encode_vec_v<VARIANT>(in, one, o, m);
-        if (HINT) {
-            st_hint(po + i, make_uint4(o.x, o.y, o.z, o.w), pol);
-            st_hint(pm + i, make_uint4(m.x, m.y, m.z, m.w), pol);
-        } else {
-            __stcs(po + i, make_uint4(o.x, o.y, o.z, o.w));
-            __stcs(pm + i, make_uint4(m.x, m.y, m.z, m.w));
-        }
+        encode_vec_k(in, P.one, P.enc_ka, P.enc_kb, P.enc_kc, o, m);
+        __stcs(po + i, make_uint4(o.x, o.y, o.z, o.w));
+        __stcs(pm + i, make_uint4(m.x, m.y, m.z, m.w));
     }
 }
+// Everything a slow encode needs, by value: a noinline function must not take the kernel's Params by reference (that would copy the
+// whole struct from the constant bank to the stack of every thread).
+struct EncArgs {
+    void *obs;           // int8 or float32 [.., C]
+    uint8_t *mask;
+    int obs_f32;
+    uint32_t one, ka, kb, kc;
+    long long out0, limit;   // element offset of the chunk in the outputs, elements that exist
+};
 // float32 observations (hexb_config.obs_dtype = HEXB_OBS_F32): one label word = four cells = one 16-byte store per lane, so
 // that consecutive lanes write consecutive 16-byte pieces of the [G,N,N] float array
 template <int N>
-__device__ __forceinline__ void encode_obs_f32(const uint8_t *chunk, const Params &P, long long out0, long long limit, int lane, int nthr) {
+__device__ __forceinline__ void encode_obs_f32(const uint8_t *chunk, const EncArgs &A, int lane, int nthr) {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(chunk);
-    float *obs = reinterpret_cast<float *>(P.obs);
-    const bool vec_ok = ((((uintptr_t)obs) | (uintptr_t)(4 * out0)) & 15) == 0;
+    float *obs = reinterpret_cast<float *>(A.obs);
+    const bool vec_ok = ((((uintptr_t)obs) | (uintptr_t)(4 * A.out0)) & 15) == 0;
     for (int i = lane; i < Chunk<N>::WORDS; i += nthr) {
         uint32_t o, m;
-        if (P.variant == VARIANT_B) encode_word_v<VARIANT_B>(src[i], P.one, o, m);
-        else encode_word_v<VARIANT_A>(src[i], P.one, o, m);
+        encode_word_k(src[i], A.one, A.ka, A.kb, A.kc, o, m);
         const float4 f = make_float4((float)(int8_t)(o & 0xffu), (float)(int8_t)((o >> 8) & 0xffu), (float)(int8_t)((o >> 16) & 0xffu),
                                      (float)(int8_t)(o >> 24));
-        const long long off = out0 + 4ll * i;   // element index
-        if (vec_ok && off + 4 <= limit) {
+        const long long off = A.out0 + 4ll * i;   // element index
+        if (vec_ok && off + 4 <= A.limit) {
             __stcs(reinterpret_cast<float4 *>(obs + off), f);
         } else {
             const float a[4] = {f.x, f.y, f.z, f.w};
             for (int k = 0; k < 4; ++k)
-                if (off + k < limit) obs[off + k] = a[k];
+                if (off + k < A.limit) obs[off + k] = a[k];
+        }
+    }
+}
+// Every case but the common one (see encode_chunk): float32 observations, one of the two outputs missing, a ragged last chunk,
+// unaligned buffers. Out of line: it is a quarter of the step kernel's code and almost never runs.
+template <int N>
+__device__ __noinline__ void encode_chunk_slow(const uint8_t *chunk, EncArgs A, int lane, int nthr) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(chunk);
+    uint8_t *obs = reinterpret_cast<uint8_t *>(A.obs);
+    uint8_t *msk = A.mask;
+    if (A.obs_f32) {
+        if (obs) encode_obs_f32<N>(chunk, A, lane, nthr);
+        obs = nullptr;   // the byte loop below then writes the mask only
+    }
+    if (!obs && !msk) return;
+    const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)msk) | (uintptr_t)A.out0) & 15) == 0;
+    for (int i = lane; i < Chunk<N>::VECS; i += nthr) {
+        const uint4 x = src[i];
+        Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
+        encode_vec_k(in, A.one, A.ka, A.kb, A.kc, o, m);
+        const long long off = A.out0 + 16ll * i;
+        if (vec_ok && off + 16 <= A.limit) {
+            if (obs) __stcs(reinterpret_cast<uint4 *>(obs + off), make_uint4(o.x, o.y, o.z, o.w));
+            if (msk) __stcs(reinterpret_cast<uint4 *>(msk + off), make_uint4(m.x, m.y, m.z, m.w));
+        } else {
+            if (obs) store_tail(obs, off, A.limit, o);
+            if (msk) store_tail(msk, off, A.limit, m);
         }
     }
 }
@@ -153,42 +179,34 @@ __device__ __forceinline__ void encode_chunk(const uint8_t *chunk, const Params 
     constexpr int C = Geo<N>::C;
     const long long out0 = (g0 + (long long)t * P.G) * C;   // byte offset of the chunk in obs / mask (row t of [T,G,C])
     const long long limit = ((long long)t + 1) * P.G * C;   // bytes of that row that exist in the caller's buffers
-    const uint4 *src = reinterpret_cast<const uint4 *>(chunk);
     uint8_t *obs = reinterpret_cast<uint8_t *>(P.obs);
     uint8_t *msk = P.mask;
-    if (P.obs_f32) {   // kernel-uniform
-        if (obs) encode_obs_f32<N>(chunk, P, out0, limit, lane, nthr);
-        obs = nullptr;   // the byte loop below then writes the mask only
-    }
     const bool vec_ok = ((((uintptr_t)obs) | ((uintptr_t)msk) | (uintptr_t)out0) & 15) == 0;
-    if (vec_ok && obs && msk && out0 + Chunk<N>::BYTES <= limit) {
-        // the common case (warp-uniform): whole chunk inside the buffers, both outputs wanted, 16-byte aligned
-        uint4 *po = reinterpret_cast<uint4 *>(obs + out0), *pm = reinterpret_cast<uint4 *>(msk + out0);
-        // Optional (HEXB_L2_OUT_HINT=1): the streaming stores also carry an explicit L2 evict_first policy. Measured both ways
-        // with 20 MiB of state kept in L2: 95.5 -> 92.4 us per 1 Mi-game step in one process layout (tools/graph_probe.py) but
-        // 92.3 -> 96.3 us in bench.py on another box, so it stays off by default.
-        const uint64_t pol = l2_policy(false);
-        if (P.variant == VARIANT_B) {
-            if (P.out_hint) encode_loop<N, VARIANT_B, true>(src, po, pm, lane, nthr, P.one, pol);
-            else encode_loop<N, VARIANT_B, false>(src, po, pm, lane, nthr, P.one, pol);
-        } else {
-            if (P.out_hint) encode_loop<N, VARIANT_A, true>(src, po, pm, lane, nthr, P.one, pol);
-            else encode_loop<N, VARIANT_A, false>(src, po, pm, lane, nthr, P.one, pol);
-        }
+    if (!P.obs_f32 && vec_ok && obs && msk && out0 + Chunk<N>::BYTES <= limit) {
+        // the common case (warp-uniform): int8 observations, whole chunk inside the buffers, both outputs wanted, 16-byte aligned.
+        // (An explicit L2 evict_first policy on these streaming stores was measured both ways in round 1 - 95.5 -> 92.4 us per
+        // 1 Mi-game step in one process layout, 92.3 -> 96.3 us in bench.py on another box - and its code path removed in r2p: every
+        // instantiation of this loop that is compiled in but not run costs instruction-cache space in the step kernel.)
+        encode_loop<N>(reinterpret_cast<const uint4 *>(chunk), reinterpret_cast<uint4 *>(obs + out0), reinterpret_cast<uint4 *>(msk + out0),
+                       lane, nthr, P);
         return;
     }
-    for (int i = lane; i < Chunk<N>::VECS; i += nthr) {
-        const uint4 x = src[i];
-        Vec4 in = {x.x, x.y, x.z, x.w}, o, m;
-        encode_vec<N>(in, P.variant, o, m);
-        const long long off = out0 + 16ll * i;
-        if (vec_ok && off + 16 <= limit) {
-            if (obs) __stcs(reinterpret_cast<uint4 *>(obs + off), make_uint4(o.x, o.y, o.z, o.w));
-            if (msk) __stcs(reinterpret_cast<uint4 *>(msk + off), make_uint4(m.x, m.y, m.z, m.w));
-        } else {
-            if (obs) store_tail(obs, off, limit, o);
-            if (msk) store_tail(msk, off, limit, m);
-        }
+    const EncArgs A = {P.obs, P.mask, P.obs_f32, P.one, P.enc_ka, P.enc_kb, P.enc_kc, out0, limit};
+    encode_chunk_slow<N>(chunk, A, lane, nthr);
+}
+
+// The rare per-row views, out of line for the same reason: info["terminal_observation"] of a game that finished in this step
+// (term_row_lane) and the opponent's-side observation of a finished, not restarted game (view_row_lane). variant / dtype by value.
+template <int N>
+__device__ __noinline__ void rare_row_view(const uint8_t *chunk, int r, int8_t *obs, uint8_t *mask, int obs_f32, int variant, bool opp,
+                                           long long g, int lane) {
+    constexpr int C = Geo<N>::C;
+    const uint8_t *Lg = chunk + r * C;
+    for (int c = lane; c < C; c += kWarp) {
+        uint32_t mk;
+        const uint32_t ob = encode_byte(Lg[opp ? transpose_cell<N>(c) : c], variant, opp, mk);
+        if (obs) store_obs(obs, obs_f32, g * C + c, ob);
+        if (mask) mask[g * C + c] = (uint8_t)mk;
     }
 }
 
@@ -249,22 +267,21 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
     uint32_t *lab32 = reinterpret_cast<uint32_t *>(chunk);
     double u_agent = 0.0, u_opp = 0.0;
     Rec<N> rec = {};
-    Pre pre = {-1, 0, 0, 0, false};
-    const bool early = STEP_ONLY && P.early;   // kernel-uniform: the record-only part of the step runs before the chunk has landed
+    // Params::early (kernel-uniform, set per launch): the record-only half of the step (game_step_pre) runs BEFORE the chunk has
+    // landed, on record words fetched with plain coalesced loads - for launches of at most one wave, where every warp waits for
+    // its bulk copy at the same moment and the Philox rounds alone do not cover it. Deep launches fetch only meta / draws here.
+    const bool early = STEP_ONLY && P.early;
     if (STEP_ONLY && g < P.G) {
         const uint32_t *grec = reinterpret_cast<const uint32_t *>(gl + Geo<N>::CHUNK_LAB) + lane;
+        rec.meta = grec[Geo<N>::W * kRecStride];
+        rec.draws = grec[(Geo<N>::W + 1) * kRecStride];
         if (early) {
-            load_rec<N>(grec, rec);
-            pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
-            game_step_pre<N>(P, g, rec, u_agent, u_opp, pre);
-        } else {
-            pre_draws(P, grec[Geo<N>::W * kRecStride], grec[(Geo<N>::W + 1) * kRecStride],
-                      (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+#pragma unroll
+            for (int w = 0; w < Geo<N>::W; ++w) rec.occ_rm[w] = grec[w * kRecStride];
         }
+        pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
     }
     __syncwarp();  // the barrier's initialisation is visible to the other lanes
-    mbar_wait(bar, 0);
-    if (!early) load_rec<N>(recw, rec);
     uint8_t *L = chunk + lane * C;
 
     // One env step per iteration. hexb_step launches with steps == 1; hexb_rollout runs T steps with the chunk staying in
@@ -274,10 +291,20 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
         const int t = KIND == KIND_ROLLOUT ? tt : 0;   // a compile-time 0 on the single-step path
         // ---- thread-per-game phase
         uint32_t prmA = 0, prmB = 0, flg = 0;
+        if (!STEP_ONLY) {
+            mbar_wait(bar, 0);
+            load_rec<N>(recw, rec);
+        }
         if (STEP_ONLY) {
-            if (t > 0 && g < P.G) pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+            if (tt > 0 && g < P.G) pre_draws(P, rec.meta, rec.draws, (unsigned long long)(P.game_offset + g), u_agent, u_opp);
+            if (tt == 0 && !early) {
+                mbar_wait(bar, 0);
+                load_rec<N>(recw, rec);
+            }
+            Pre pre;
+            game_step_pre<N>(P, g, rec, u_agent, u_opp, pre);   // one copy of this code whichever side of the wait it runs on
+            if (tt == 0 && early) mbar_wait(bar, 0);
             Loc loc;
-            if (!(early && tt == 0)) game_step_pre<N>(P, g, rec, u_agent, u_opp, pre);
             game_step_post<N>(L, P, g, t, rec, pre, loc, prmA, prmB, flg);
             // K7: episode statistics - the eight per-game increments are packed into two words (fields wide enough for the
             // sum over 32 lanes), reduced with two redux.sync, and lane 0 adds the non-zero counters to this warp's stripe
@@ -306,7 +333,11 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
             const int r = __ffs(pending) - 1;
             pending &= pending - 1;
             const uint32_t rf = __shfl_sync(FULL, flg, r);
-            row_job_lane<N>(chunk, r, rf, P, g0 + r + (long long)t * P.G, lane, [] { __syncwarp(); });
+            if (rf & F_TERM) {   // terminal observation (reads the finished board), then the clear: different lanes touch the same words
+                rare_row_view<N>(chunk, r, P.term_obs, nullptr, P.obs_f32, P.variant, (rf & F_TERM_OPP) != 0u, g0 + r + (long long)t * P.G, lane);
+                __syncwarp();
+            }
+            if (rf & F_RESET) clear_row_lane<N>(lab32, r, rf, lane);
             __syncwarp();
         }
 
@@ -319,7 +350,7 @@ __global__ void __launch_bounds__(kCtaThreads, min_ctas(N)) hexb_step_kernel(con
             while (views) {
                 const int r = __ffs(views) - 1;
                 views &= views - 1;
-                view_row_lane<N>(chunk, r, P, g0 + r + (long long)t * P.G, lane);
+                rare_row_view<N>(chunk, r, P.obs, P.mask, P.obs_f32, P.variant, true, g0 + r + (long long)t * P.G, lane);
             }
         }
 
