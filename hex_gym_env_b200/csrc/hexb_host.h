@@ -12,19 +12,21 @@
 
 #define HEXB_LOCAL __attribute__((visibility("hidden")))
 
+#define HEXB_HOST_SLICES 6   // pieces the packed words of a host-buffer step travel in (host threads expand piece k while k+1 is in flight)
+
 struct hexb_env {
     hexb_config cfg;
     hexb::Params base;   // state pointers + config, I/O pointers null
     int launch_form;     // hexb_set_launch_form: 0 = chosen by launch depth, 1 / 2 / 4 / 8 = warps per 32-game chunk
     // ---- host-buffer step (hexb_step_host*): events, staging and the adaptive DMA / packed split
-    cudaEvent_t host_ev, host_ev_dma0, host_ev_slice[4];   // all copies done; start of the DMA part; each packed slice arrived
+    cudaEvent_t host_ev, host_ev_dma0, host_ev_slice[HEXB_HOST_SLICES];   // all copies done; start of the DMA part; each packed slice arrived
     int host_pending, host_adapt, host_frac_fixed;
     double host_dma_frac;          // share of the games whose obs / mask rows travel as plain bytes by DMA
     double host_dma_bytes;
     double host_t0_ms;                                   // start of the running synchronous call
     int host_tune_calls;                                 // position in the split search (tune_next in hexb_kernels.cu)
     double host_tune_ms[7][3], host_tune_best, host_tune_best_ms;
-    long long host_plan_words, host_plan_first, host_slice_lo[4], host_slice_hi[4];
+    long long host_plan_words, host_plan_first, host_slice_lo[HEXB_HOST_SLICES], host_slice_hi[HEXB_HOST_SLICES];
     uint32_t *host_packed;         // pinned staging of the packed words (cudaHostAlloc, owned by the handle)
     const uint32_t *host_packed_src;
     int8_t *host_obs;

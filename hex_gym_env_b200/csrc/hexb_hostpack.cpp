@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -144,11 +145,37 @@ void share(const Job &j, int k, int n, long long &w0, long long &w1) {
     if (w1 > end) w1 = end;
 }
 
+// The pieces of one host-buffer step reach the pool a few hundred microseconds apart, and a thread that sleeps on a condition
+// variable takes tens of microseconds to run again (more inside a VM), several times per step on every thread. So between jobs the
+// workers (and the submitting thread, waiting for them) first SPIN on the shared counters for a bounded time and only then sleep.
+double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e6 * (double)ts.tv_sec + 1e-3 * (double)ts.tv_nsec;
+}
+inline void cpu_relax() {
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
+}
+// HEXB_HOST_SPIN_US: how long a pool thread spins for the next piece before it sleeps (default 400; 0 = always sleep, e.g. when a
+// host policy needs the cores between steps)
+double spin_us() {
+    static const double v = [] {
+        const char *e = getenv("HEXB_HOST_SPIN_US");
+        const double x = e ? atof(e) : 400.0;
+        return x < 0.0 ? 0.0 : (x > 1e5 ? 1e5 : x);
+    }();
+    return v;
+}
+
 void *worker(void *arg) {
     const int k = (int)(intptr_t)arg;
     unsigned long long seen = 0;
-    pthread_mutex_lock(&g_pool.mu);
     for (;;) {
+        for (const double t_end = now_us() + spin_us(); __atomic_load_n(&g_pool.generation, __ATOMIC_ACQUIRE) == seen && now_us() < t_end;)
+            for (int i = 0; i < 64; ++i) cpu_relax();
+        pthread_mutex_lock(&g_pool.mu);
         while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv_work, &g_pool.mu);
         seen = g_pool.generation;
         const Job j = g_pool.job;
@@ -158,7 +185,9 @@ void *worker(void *arg) {
         share(j, k, n, w0, w1);
         if (w1 > w0) expand_range(j, w0, w1);
         pthread_mutex_lock(&g_pool.mu);
-        if (--g_pool.remaining == 0) pthread_cond_signal(&g_pool.cv_done);
+        const int left = __atomic_sub_fetch(&g_pool.remaining, 1, __ATOMIC_ACQ_REL);
+        if (left == 0) pthread_cond_signal(&g_pool.cv_done);
+        pthread_mutex_unlock(&g_pool.mu);
     }
     return nullptr;
 }
@@ -227,8 +256,8 @@ extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_expand(const
     if (n > 1) {
         pthread_mutex_lock(&g_pool.mu);
         g_pool.job = j;
-        g_pool.remaining = n - 1;
-        g_pool.generation++;
+        __atomic_store_n(&g_pool.remaining, n - 1, __ATOMIC_RELEASE);
+        __atomic_store_n(&g_pool.generation, g_pool.generation + 1, __ATOMIC_RELEASE);   // spinning workers see this without the lock
         pthread_cond_broadcast(&g_pool.cv_work);
         pthread_mutex_unlock(&g_pool.mu);
     }
@@ -236,6 +265,8 @@ extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_expand(const
     share(j, 0, n, w0, w1);
     if (w1 > w0) expand_range(j, w0, w1);
     if (n > 1) {
+        for (const double t_end = now_us() + spin_us(); __atomic_load_n(&g_pool.remaining, __ATOMIC_ACQUIRE) != 0 && now_us() < t_end;)
+            for (int i = 0; i < 64; ++i) cpu_relax();
         pthread_mutex_lock(&g_pool.mu);
         while (g_pool.remaining != 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
         pthread_mutex_unlock(&g_pool.mu);
