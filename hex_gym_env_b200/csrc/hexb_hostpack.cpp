@@ -112,12 +112,54 @@ __attribute__((target("avx2"))) void expand_avx2(const Job &j, long long w0, lon
     if (nt) _mm_sfence();
     if (w < w1) expand_scalar(j, w, w1);
 }
+
+// The same in 512-bit registers: 64 cells (four packed words) per iteration, and each result is ONE full cache line written by one
+// non-temporal store (two 32-byte halves of a line go through a write-combining buffer that can be flushed half full).
+__attribute__((target("avx512f,avx512bw"))) void expand_avx512(const Job &j, long long w0, long long w1) {
+    long long w = w0;
+    while ((w & 3) && w < w1) { expand_scalar(j, w, w + 1); ++w; }   // 64-cell groups are 64-byte aligned relative to cell 0
+    const bool nt = ((((uintptr_t)j.obs) | ((uintptr_t)j.mask)) & 63) == 0;
+    if (nt) {
+        // lane q of the 512-bit register takes packed bytes 4q .. 4q+3, each four times
+        const __m512i spread = _mm512_set_epi8(15, 15, 15, 15, 14, 14, 14, 14, 13, 13, 13, 13, 12, 12, 12, 12, 11, 11, 11, 11, 10, 10, 10, 10, 9, 9, 9, 9,
+                                               8, 8, 8, 8, 7, 7, 7, 7, 6, 6, 6, 6, 5, 5, 5, 5, 4, 4, 4, 4, 3, 3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1, 0, 0, 0, 0);
+        const __m512i three = _mm512_set1_epi8(3);
+        const __m512i sel0 = _mm512_set1_epi32(0x000000ff), sel1 = _mm512_set1_epi32(0x0000ff00), sel2 = _mm512_set1_epi32(0x00ff0000),
+                      sel3 = _mm512_set1_epi32((int)0xff000000u);
+        const __m128i t_obs = j.variant ? _mm_setr_epi8(0, 1, 2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) : _mm_setr_epi8(0, 1, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+        const __m128i t_msk = j.variant ? _mm_setr_epi8(1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) : _mm_setr_epi8(0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+        const __m512i tab_obs = _mm512_broadcast_i32x4(t_obs), tab_msk = _mm512_broadcast_i32x4(t_msk);
+        for (; w + 4 <= w1 && 16 * (w + 4) <= j.cells; w += 4) {
+            const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(j.packed + w));
+            const __m512i v = _mm512_shuffle_epi8(_mm512_broadcast_i32x4(x), spread);
+            const __m512i t0 = _mm512_and_si512(v, three);
+            const __m512i t1 = _mm512_and_si512(_mm512_srli_epi16(v, 2), three);
+            const __m512i t2 = _mm512_and_si512(_mm512_srli_epi16(v, 4), three);
+            const __m512i t3 = _mm512_and_si512(_mm512_srli_epi16(v, 6), three);
+            // byte position p of every 4-byte group takes t_p
+            const __m512i code = _mm512_or_si512(_mm512_or_si512(_mm512_and_si512(t0, sel0), _mm512_and_si512(t1, sel1)),
+                                                 _mm512_or_si512(_mm512_and_si512(t2, sel2), _mm512_and_si512(t3, sel3)));
+            const long long c0 = 16 * w;
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(j.obs + c0), _mm512_shuffle_epi8(tab_obs, code));
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(j.mask + c0), _mm512_shuffle_epi8(tab_msk, code));
+        }
+        _mm_sfence();
+    }
+    if (w < w1) expand_avx2(j, w, w1);
+}
 #endif
 
 void expand_range(const Job &j, long long w0, long long w1) {
 #if defined(__x86_64__)
-    static const int have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) { expand_avx2(j, w0, w1); return; }
+    static const int level = [] {   // HEXB_HOST_SIMD = 0 (scalar) / 2 (AVX2) / 512 caps what the CPU offers (experiments)
+        const char *e = getenv("HEXB_HOST_SIMD");
+        const int cap = e ? atoi(e) : 512;
+        if (cap >= 512 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) return 512;
+        if (cap >= 2 && __builtin_cpu_supports("avx2")) return 2;
+        return 0;
+    }();
+    if (level == 512) { expand_avx512(j, w0, w1); return; }
+    if (level == 2) { expand_avx2(j, w0, w1); return; }
 #endif
     expand_scalar(j, w0, w1);
 }
