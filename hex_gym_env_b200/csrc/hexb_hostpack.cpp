@@ -6,6 +6,9 @@
 // 8x fewer bytes cross PCIe and host cores write the API's arrays instead of the DMA engine. Whether that is faster depends on
 // the host (profiles/r2*_e2e_packed.json has the A/B at 1 and 8 GPUs).
 //
+// The packed words of a step arrive in pieces (csrc/hexb_kernels.cu: host_step_enqueue / host_step_finish); the pool below works on
+// them as they arrive: hexb_hostpack_begin / _publish / _finish.
+//
 // Plain C++ (g++), no CUDA: 16 cells per packed word, cell i of the flat [G*N*N] order in bits 2*(i%16).. of word i/16,
 // code = obs byte & 3 (variant B: -1/0/+1 -> 3/0/1; variant A: BLACK 0, WHITE 1, EMPTY 2).
 #include <pthread.h>
@@ -164,7 +167,11 @@ void expand_range(const Job &j, long long w0, long long w1) {
     expand_scalar(j, w0, w1);
 }
 
-// ---- a persistent pool: workers sleep on a condition variable between jobs
+// ---- a persistent pool. One job = the packed words of one host-buffer step, cut into blocks that the threads take from a shared
+// counter (so a thread that is late - it slept, or its core was taken - simply takes fewer blocks), and the words of the job become
+// AVAILABLE piece by piece while the threads are already at work: the submitting thread waits for each piece's device->host copy
+// and publishes how far the words have arrived; a thread whose block has not arrived yet spins for it. There is one join, at the
+// end of the step, instead of one per piece.
 struct Pool {
     pthread_mutex_t mu;
     pthread_cond_t cv_work, cv_done;
@@ -172,24 +179,19 @@ struct Pool {
     unsigned long long generation;
     int remaining;
     Job job;
+    long long blk, first_block, nblocks;   // block size in words; absolute index of the job's first block; number of blocks
+    long long next;                        // next block to hand out (atomic)
+    long long avail;                       // absolute word index up to which the packed words have arrived (atomic)
+    int abort;                             // the submitter gave up (a failed copy): threads drop the blocks they wait for
     pthread_t th[64];
 };
-Pool g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, 0, 0, {}, {}};
+Pool g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, 0, 0, {}, 0, 0, 0, 0, 0, 0, {}};
 pthread_mutex_t g_submit = PTHREAD_MUTEX_INITIALIZER;   // one job at a time (several handles / host threads may call in)
-
-void share(const Job &j, int k, int n, long long &w0, long long &w1) {
-    // contiguous shares, boundaries on even words so that every share starts 32-byte aligned in the outputs
-    const long long per = ((j.count + n - 1) / n + 1) & ~1ll;
-    w0 = j.first + per * k;
-    w1 = w0 + per;
-    const long long end = j.first + j.count;
-    if (w0 > end) w0 = end;
-    if (w1 > end) w1 = end;
-}
+const long long kBlockWords = 4096;   // 65,536 cells = 128 KB of obs + mask per block; a multiple of 4 (the AVX-512 loop's alignment)
 
 // The pieces of one host-buffer step reach the pool a few hundred microseconds apart, and a thread that sleeps on a condition
-// variable takes tens of microseconds to run again (more inside a VM), several times per step on every thread. So between jobs the
-// workers (and the submitting thread, waiting for them) first SPIN on the shared counters for a bounded time and only then sleep.
+// variable takes tens of microseconds to run again (more inside a VM). So between jobs the workers (and the submitting thread,
+// waiting for them) first SPIN on the shared counters for a bounded time and only then sleep.
 double now_us() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -200,7 +202,7 @@ inline void cpu_relax() {
     _mm_pause();
 #endif
 }
-// HEXB_HOST_SPIN_US: how long a pool thread spins for the next piece before it sleeps (default 400; 0 = always sleep, e.g. when a
+// HEXB_HOST_SPIN_US: how long a pool thread spins for the next job before it sleeps (default 400; 0 = always sleep, e.g. when a
 // host policy needs the cores between steps)
 double spin_us() {
     static const double v = [] {
@@ -211,8 +213,25 @@ double spin_us() {
     return v;
 }
 
-void *worker(void *arg) {
-    const int k = (int)(intptr_t)arg;
+// one thread's part of the running job: blocks from the shared counter, each as soon as its words have arrived
+void run_blocks() {
+    const Job j = g_pool.job;
+    const long long blk = g_pool.blk, b0 = g_pool.first_block, nb = g_pool.nblocks, end = j.first + j.count;
+    for (;;) {
+        const long long b = __atomic_fetch_add(&g_pool.next, 1, __ATOMIC_RELAXED);
+        if (b >= nb) break;
+        long long lo = (b0 + b) * blk, hi = lo + blk;
+        if (lo < j.first) lo = j.first;
+        if (hi > end) hi = end;
+        while (__atomic_load_n(&g_pool.avail, __ATOMIC_ACQUIRE) < hi) {
+            if (__atomic_load_n(&g_pool.abort, __ATOMIC_RELAXED)) return;
+            for (int i = 0; i < 16; ++i) cpu_relax();
+        }
+        if (hi > lo) expand_range(j, lo, hi);
+    }
+}
+
+void *worker(void *) {
     unsigned long long seen = 0;
     for (;;) {
         for (const double t_end = now_us() + spin_us(); __atomic_load_n(&g_pool.generation, __ATOMIC_ACQUIRE) == seen && now_us() < t_end;)
@@ -220,12 +239,8 @@ void *worker(void *arg) {
         pthread_mutex_lock(&g_pool.mu);
         while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv_work, &g_pool.mu);
         seen = g_pool.generation;
-        const Job j = g_pool.job;
-        const int n = g_pool.nthreads;
         pthread_mutex_unlock(&g_pool.mu);
-        long long w0, w1;
-        share(j, k, n, w0, w1);
-        if (w1 > w0) expand_range(j, w0, w1);
+        run_blocks();
         pthread_mutex_lock(&g_pool.mu);
         const int left = __atomic_sub_fetch(&g_pool.remaining, 1, __ATOMIC_ACQ_REL);
         if (left == 0) pthread_cond_signal(&g_pool.cv_done);
@@ -267,9 +282,9 @@ void pool_start() {   // called with g_submit held
         atfork_set = 1;
     }
     g_pool.nthreads = pool_threads();
-    // worker 0's share is run by the calling thread; the others are spawned once and live for the process
+    // the calling thread works too (after its last publish); the others are spawned once and live for the process
     for (int k = 1; k < g_pool.nthreads; ++k) {
-        if (pthread_create(&g_pool.th[k], nullptr, worker, (void *)(intptr_t)k) != 0) {
+        if (pthread_create(&g_pool.th[k], nullptr, worker, nullptr) != 0) {
             g_pool.nthreads = k;
             break;
         }
@@ -288,25 +303,38 @@ extern "C" __attribute__((visibility("hidden"))) int hexb_hostpack_threads(void)
     return n;
 }
 
-// Expand packed words [first_word, first_word + n_words) into obs / mask (whole arrays' base pointers; n_cells = G*N*N).
-extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_expand(const uint32_t *packed, long long first_word, long long n_words,
-                                                                            long long n_cells, int variant, int8_t *obs, uint8_t *mask) {
+// A job in three calls, all from ONE thread: _begin hands the whole range [first_word, first_word + n_words) to the pool (nothing
+// of it is available yet) and keeps the pool locked for this caller; _publish(w) says that the packed words below absolute index w
+// have arrived; _finish makes the caller work along, waits for the pool and unlocks it. abort != 0: the words will not arrive
+// (a failed copy) - threads drop what they wait for; the outputs are then incomplete and the caller reports the error.
+extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_begin(const uint32_t *packed, long long first_word, long long n_words,
+                                                                           long long n_cells, int variant, int8_t *obs, uint8_t *mask) {
     pthread_mutex_lock(&g_submit);
     pool_start();
-    Job j = {packed, first_word, n_words, n_cells, variant, obs, mask};
-    const int n = g_pool.nthreads;
-    if (n > 1) {
-        pthread_mutex_lock(&g_pool.mu);
-        g_pool.job = j;
-        __atomic_store_n(&g_pool.remaining, n - 1, __ATOMIC_RELEASE);
+    pthread_mutex_lock(&g_pool.mu);
+    g_pool.job = Job{packed, first_word, n_words, n_cells, variant, obs, mask};
+    g_pool.blk = kBlockWords;
+    g_pool.first_block = first_word / kBlockWords;
+    g_pool.nblocks = n_words > 0 ? (first_word + n_words + kBlockWords - 1) / kBlockWords - g_pool.first_block : 0;
+    __atomic_store_n(&g_pool.next, 0, __ATOMIC_RELAXED);
+    __atomic_store_n(&g_pool.avail, first_word, __ATOMIC_RELAXED);
+    __atomic_store_n(&g_pool.abort, 0, __ATOMIC_RELAXED);
+    __atomic_store_n(&g_pool.remaining, g_pool.nthreads - 1, __ATOMIC_RELEASE);
+    if (g_pool.nthreads > 1) {
         __atomic_store_n(&g_pool.generation, g_pool.generation + 1, __ATOMIC_RELEASE);   // spinning workers see this without the lock
         pthread_cond_broadcast(&g_pool.cv_work);
-        pthread_mutex_unlock(&g_pool.mu);
     }
-    long long w0, w1;
-    share(j, 0, n, w0, w1);
-    if (w1 > w0) expand_range(j, w0, w1);
-    if (n > 1) {
+    pthread_mutex_unlock(&g_pool.mu);
+}
+
+extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_publish(long long words_arrived_abs) {
+    __atomic_store_n(&g_pool.avail, words_arrived_abs, __ATOMIC_RELEASE);
+}
+
+extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_finish(int abort) {
+    if (abort) __atomic_store_n(&g_pool.abort, 1, __ATOMIC_RELEASE);
+    run_blocks();
+    if (g_pool.nthreads > 1) {
         for (const double t_end = now_us() + spin_us(); __atomic_load_n(&g_pool.remaining, __ATOMIC_ACQUIRE) != 0 && now_us() < t_end;)
             for (int i = 0; i < 64; ++i) cpu_relax();
         pthread_mutex_lock(&g_pool.mu);
@@ -314,4 +342,13 @@ extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_expand(const
         pthread_mutex_unlock(&g_pool.mu);
     }
     pthread_mutex_unlock(&g_submit);
+}
+
+// Expand packed words [first_word, first_word + n_words) into obs / mask (whole arrays' base pointers; n_cells = G*N*N), all of
+// them already in host memory.
+extern "C" __attribute__((visibility("hidden"))) void hexb_hostpack_expand(const uint32_t *packed, long long first_word, long long n_words,
+                                                                            long long n_cells, int variant, int8_t *obs, uint8_t *mask) {
+    hexb_hostpack_begin(packed, first_word, n_words, n_cells, variant, obs, mask);
+    hexb_hostpack_publish(first_word + n_words);
+    hexb_hostpack_finish(0);
 }

@@ -238,6 +238,10 @@ static View view_of(const hexb_env *e) {
 extern "C" HEXB_LOCAL void hexb_hostpack_expand(const uint32_t *packed, long long first_word, long long n_words, long long n_cells,
                                                 int variant, int8_t *obs, uint8_t *mask);
 extern "C" HEXB_LOCAL int hexb_hostpack_threads(void);
+extern "C" HEXB_LOCAL void hexb_hostpack_begin(const uint32_t *packed, long long first_word, long long n_words, long long n_cells, int variant,
+                                                int8_t *obs, uint8_t *mask);
+extern "C" HEXB_LOCAL void hexb_hostpack_publish(long long words_arrived_abs);
+extern "C" HEXB_LOCAL void hexb_hostpack_finish(int abort);
 
 extern "C" {
 
@@ -476,11 +480,12 @@ static HostPlan plan_host(const hexb_env *env, double frac) {
     return p;
 }
 
-// The packed words travel in kHostSlices pieces of growing size (cumulative sixteenths below): nothing can be expanded before the
-// first piece has arrived, so it is small (1/16 of the words, about 40 us of PCIe time for 1 Mi games of 11x11 instead of 170 us
-// for a quarter), and the later ones are large enough to keep the per-piece hand-over to the host threads negligible.
+// The packed words travel in kHostSlices pieces of growing size (cumulative 64ths below): nothing can be expanded before the
+// first piece has arrived, so it is small (1/64 of the words: about 10 us of PCIe time for 1 Mi games of 11x11), and since the
+// host pool works on one job per step (hexb_hostpack_begin / _publish / _finish) the pieces only set how early words become
+// available, not how often the threads have to meet.
 enum { kHostSlices = HEXB_HOST_SLICES };
-static const int kSliceCum[kHostSlices + 1] = {0, 1, 3, 6, 9, 12, 16};
+static const int kSliceCum[kHostSlices + 1] = {0, 1, 4, 12, 24, 40, 64};
 
 static int host_events(hexb_env *env) {
     if (env->host_ev) return HEXB_OK;
@@ -514,7 +519,7 @@ static int host_step_enqueue(hexb_env *env, void *workspace, uint32_t *packed_ho
                                                                             h.packed + p.first_word);
         CK(cudaGetLastError());
         for (int k = 0; k < kHostSlices; ++k) {
-            long long lo = p.first_word + ((p.words * kSliceCum[k] / 16) & ~15ll), hi = p.first_word + ((p.words * kSliceCum[k + 1] / 16) & ~15ll);
+            long long lo = p.first_word + ((p.words * kSliceCum[k] / 64) & ~15ll), hi = p.first_word + ((p.words * kSliceCum[k + 1] / 64) & ~15ll);
             if (k == kHostSlices - 1) hi = p.first_word + p.words;
             env->host_slice_lo[k] = lo;
             env->host_slice_hi[k] = hi;
@@ -608,11 +613,17 @@ static int host_step_finish(hexb_env *env, bool adapt) {
     CK(cudaSetDevice(env->cfg.device));
     const long long cells = (long long)env->cfg.num_games * env->cfg.board_size * env->cfg.board_size;
     if (env->host_plan_words > 0) {
-        for (int k = 0; k < kHostSlices; ++k) {
-            CK(cudaEventSynchronize(env->host_ev_slice[k]));
-            const long long lo = env->host_slice_lo[k], hi = env->host_slice_hi[k];
-            if (hi > lo) hexb_hostpack_expand(env->host_packed_src, lo, hi - lo, cells, env->cfg.variant, env->host_obs, env->host_mask);
+        // the pool gets the whole range at once and works on it while the pieces arrive: this thread waits for each piece's copy and
+        // publishes how far the words are there, then works along; one join per step (hexb_hostpack.cpp)
+        hexb_hostpack_begin(env->host_packed_src, env->host_plan_first, env->host_plan_words, cells, env->cfg.variant, env->host_obs,
+                            env->host_mask);
+        cudaError_t err = cudaSuccess;
+        for (int k = 0; k < kHostSlices && err == cudaSuccess; ++k) {
+            err = cudaEventSynchronize(env->host_ev_slice[k]);
+            if (err == cudaSuccess) hexb_hostpack_publish(env->host_slice_hi[k]);
         }
+        hexb_hostpack_finish(err != cudaSuccess);   // always: it releases the pool
+        if (err != cudaSuccess) return hexb_cuda_fail(err);
     }
     CK(cudaEventSynchronize(env->host_ev));
     if (adapt) tune_next(env, now_ms() - env->host_t0_ms);

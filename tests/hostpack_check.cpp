@@ -2,11 +2,10 @@
 // ragged word ranges against a plain per-cell loop. Built and run by tests/test_hostpack_cpu.py; test infrastructure.
 #include "../hex_gym_env_b200/csrc/hexb_hostpack.cpp"
 #include <stdio.h>
-extern "C" void hexb_hostpack_expand(const uint32_t *, long long, long long, long long, int, int8_t *, uint8_t *);
 int main() {
     int bad = 0;
     for (int variant = 0; variant < 2; ++variant) {
-        const long long cells = 7 * 361 * 33 + 5, words = (cells + 15) / 16;
+        const long long cells = 7 * 361 * 333 + 5, words = (cells + 15) / 16;
         uint32_t *packed; int8_t *obs, *ref_o; uint8_t *mask, *ref_m;
         if (posix_memalign((void **)&packed, 64, words * 4 + 64) || posix_memalign((void **)&obs, 64, cells + 128) ||
             posix_memalign((void **)&mask, 64, cells + 128) || posix_memalign((void **)&ref_o, 64, cells + 128) ||
@@ -39,6 +38,31 @@ int main() {
                     if ((c < c0 || c >= c1) && (obs[off + c] != 7 || mask[off + c] != 7)) ok = 0;
                 if (!ok) { printf("MISMATCH variant %d off %d range %lld+%lld\n", variant, off, r[0], r[1]); bad = 1; }
             }
+        // the streaming form hexb_step_host uses: the pool gets the whole range, the words are published piece by piece
+        for (int rep = 0; rep < 3; ++rep) {
+            memset(obs, 7, cells + 128); memset(mask, 7, cells + 128);
+            const long long first = rep == 0 ? 0 : 242 * rep, n = words - first;
+            hexb_hostpack_begin(packed, first, n, cells, variant, obs, mask);
+            const long long cuts[] = {first + 1, first + 17, first + n / 16, first + n / 3, first + n / 3, first + n - 1, first + n};
+            for (long long c : cuts) {
+                for (volatile int spin = 0; spin < 20000 * rep; ++spin) {}   // let the pool run ahead of the arrivals
+                hexb_hostpack_publish(c);
+            }
+            hexb_hostpack_finish(0);
+            const long long c0 = 16 * first;
+            int ok = memcmp(obs + c0, ref_o + c0, cells - c0) == 0 && memcmp(mask + c0, ref_m + c0, cells - c0) == 0;
+            for (long long c = 0; c < c0 && ok; ++c) ok = obs[c] == 7 && mask[c] == 7;
+            for (long long c = cells; c < cells + 64 && ok; ++c) ok = obs[c] == 7 && mask[c] == 7;
+            if (!ok) { printf("MISMATCH streaming variant %d rep %d\n", variant, rep); bad = 1; }
+        }
+        {   // an aborted job must return (threads drop the blocks they wait for) and leave the pool usable
+            hexb_hostpack_begin(packed, 0, words, cells, variant, obs, mask);
+            hexb_hostpack_publish(5000);
+            hexb_hostpack_finish(1);
+            memset(obs, 7, cells + 128); memset(mask, 7, cells + 128);
+            hexb_hostpack_expand(packed, 0, words, cells, variant, obs, mask);
+            if (memcmp(obs, ref_o, cells) || memcmp(mask, ref_m, cells)) { printf("MISMATCH after abort variant %d\n", variant); bad = 1; }
+        }
         free(packed); free(obs); free(mask); free(ref_o); free(ref_m);
     }
     printf(bad ? "FAILED\n" : "hostpack ok (%d threads)\n", hexb_hostpack_threads());
