@@ -171,6 +171,8 @@ def workload_config(args, world):
                          else "%dx%d SelfPlayEnv random self-play" % (N, N)),
             "board_size": N, "games_per_gpu": G, "global_games": world * G, "parallelism": "games sharded by index x%d" % world,
             "l2_policy": "working set %.0f MB per step > 126 MB L2" % (G * moved_bytes(N) / 1e6),
+            "device_memory": "packed state, obs and mask in compressible device memory (hexb_mem_alloc: cuMemCreate with "
+                             "CU_MEM_ALLOCATION_COMP_GENERIC) when the state is at least 64 MiB; roofline.memory_kind says what was granted",
             "agent": "random policy (BaseRandomPolicy) drawing from the game's own stream", "seed": args.seed,
             "preroll_steps": args.preroll + (K if use_graph else 0),
             "launch": ("ONE CUDA graph of the K = %d step launches" % K) if use_graph else "one launch per step"}
@@ -295,7 +297,7 @@ def extra_config(name, N, G, variant, agent_mode, K, preroll, dev, peak):
     mv = G * moved_bytes(N) / (us * 1e-6) / 1e9
     out = {"config": name, "board_size": N, "games": G, "steps": K, "preroll_steps": preroll, "us_per_step": us,
            "env_steps_per_sec": G / (us * 1e-6), "moved_GBps": mv, "frac_of_hbm_peak": mv / peak,
-           "bytes_per_env_step_moved": moved_bytes(N)}
+           "bytes_per_env_step_moved": moved_bytes(N), "memory_kind": env.memory_kind}
     env.close()
     del env
     torch.cuda.empty_cache()
@@ -419,9 +421,11 @@ def run_gpu(args):
                 "frac_contract": G * Bc / (kern_ms * 1e-3) / 1e9 / peak, "bytes_per_env_step_contract": Bc,
                 "note": "achieved/frac count the bytes this design must move per env step (DESIGN.md section 3); frac_contract uses SURVEY "
                         "8(d)'s B(N), whose state term (290 B per game each way) is twice this design's 145 B and therefore exceeds 1. "
-                        "20 MiB of the state stay L2-resident across steps, so HBM sees slightly less than bytes_per_launch "
-                        "(traffic = ncu dram bytes per launch)",
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+                        "20 MiB of the state stay L2-resident across steps and, in compressible memory (memory_kind), the L2's inline "
+                        "compression shrinks what reaches HBM further, so HBM sees less than bytes_per_launch (traffic = ncu dram bytes "
+                        "per launch)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "memory_kind": env.memory_kind}
     early = {"ms_per_step": early_ms / K, "value": world * G * K / (early_ms * 1e-3),
              "note": "the same K steps timed right after reset (3 warm-up steps): every game in its opening, no merges, no restarts"}
     env.close()

@@ -142,6 +142,8 @@ SYMBOLS = {
     "hexb_host_packed_bytes": (_sz, [_cfgp]),
     "hexb_step_host_packed": (_i32, [_vp] * 9),
     "hexb_host_threads": (_i32, []),
+    "hexb_mem_alloc": (_i32, [_i32, _sz, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_i32)]),
+    "hexb_mem_free": (_i32, [_vp]),
     "hexb_set_host_transport": (_i32, [_vp, ctypes.c_double]),
     "hexb_get_host_transport": (_i32, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "hexb_set_launch_form": (_i32, [_vp, _i32]),
@@ -192,3 +194,25 @@ def check(rc):
         if rc == -2:
             msg += " (cudaError %d)" % L.hexb_last_cuda_error()
         raise HexbError("libhexb: %s" % msg)
+
+
+class DeviceBuffer(object):
+    """`nbytes` of device memory from hexb_mem_alloc (compressible if asked and granted), exposed through
+    __cuda_array_interface__ so that torch.as_tensor(buf, device=...) aliases it; freed when the last tensor over it is gone."""
+
+    def __init__(self, nbytes, device, compressible=True):
+        L = lib()
+        p, got = ctypes.c_void_p(), ctypes.c_int32(0)
+        rc = L.hexb_mem_alloc(int(device), int(nbytes), 1 if compressible else 0, ctypes.byref(p), ctypes.byref(got))
+        if rc != 0 or not p.value:
+            raise RuntimeError("hexb_mem_alloc(%d bytes) failed: %s" % (nbytes, L.hexb_strerror(rc).decode()))
+        self.ptr, self.nbytes, self.compressed, self._lib = int(p.value), int(nbytes), bool(got.value), L
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", 0):
+                self._lib.hexb_mem_free(ctypes.c_void_p(self.ptr))
+                self.ptr = 0
+        except Exception:
+            pass

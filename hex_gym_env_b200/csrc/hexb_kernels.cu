@@ -13,6 +13,7 @@
 //   K8        hexb_masked_sample_kernel   masked categorical sampling (the rollout feed)
 //   K9        hexb_gae_kernel         GAE(lambda) advantages / returns over a [T,G] rollout (SB3 RolloutBuffer semantics)
 //   K10       hexb_pack_obs_kernel    2-bit observation transport for hexb_step_host_packed
+#include <cuda.h>   // types of the driver's virtual-memory API only (entry points come from cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -20,6 +21,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+
+#include <map>
+#include <mutex>
 
 #include "hexb_host.h"
 
@@ -245,7 +249,7 @@ extern "C" HEXB_LOCAL void hexb_hostpack_finish(int abort);
 
 extern "C" {
 
-int32_t hexb_version(void) { return (1 << 16) | 3; }   // 1.3: obs_dtype, launch forms, hexb_gae, packed / asynchronous host step
+int32_t hexb_version(void) { return (1 << 16) | 3; }   // 1.3: obs_dtype, launch forms, hexb_gae, packed / asynchronous host step (+ hexb_mem_alloc: additive)
 
 const char *hexb_strerror(int32_t code) {
     switch (code) {
@@ -702,6 +706,108 @@ size_t hexb_host_packed_bytes(const hexb_config *cfg) {
 }
 
 int32_t hexb_host_threads(void) { return hexb_hostpack_threads(); }
+
+// ---- hexb_mem_alloc / hexb_mem_free: virtual-memory-management allocations whose physical memory may be compressible. The
+// driver entry points are resolved at run time (cudaGetDriverEntryPoint), so libhexb.so has no link-time dependency on libcuda.
+namespace {
+struct DrvApi {
+    CUresult (*GetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags);
+    CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long);
+    CUresult (*GetProps)(CUmemAllocationProp *, CUmemGenericAllocationHandle);
+    CUresult (*Reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long);
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t);
+    CUresult (*Unmap)(CUdeviceptr, size_t);
+    CUresult (*AddressFree)(CUdeviceptr, size_t);
+    CUresult (*Release)(CUmemGenericAllocationHandle);
+    bool ok;
+};
+const DrvApi &drv() {
+    static const DrvApi api = [] {
+        DrvApi a = {};
+        const char *names[9] = {"cuMemGetAllocationGranularity", "cuMemCreate", "cuMemGetAllocationPropertiesFromHandle", "cuMemAddressReserve",
+                                "cuMemMap", "cuMemSetAccess", "cuMemUnmap", "cuMemAddressFree", "cuMemRelease"};
+        void **slots[9] = {(void **)&a.GetGranularity, (void **)&a.Create, (void **)&a.GetProps, (void **)&a.Reserve, (void **)&a.Map,
+                           (void **)&a.SetAccess, (void **)&a.Unmap, (void **)&a.AddressFree, (void **)&a.Release};
+        a.ok = true;
+        for (int i = 0; i < 9; ++i) {
+            cudaDriverEntryPointQueryResult st;
+            if (cudaGetDriverEntryPoint(names[i], slots[i], cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !*slots[i])
+                a.ok = false;
+        }
+        return a;
+    }();
+    return api;
+}
+struct MemRec {
+    CUmemGenericAllocationHandle handle;
+    size_t size;
+    int device;
+};
+std::map<CUdeviceptr, MemRec> g_mem;
+std::mutex g_mem_mu;
+}  // namespace
+
+int32_t hexb_mem_alloc(int32_t device, size_t bytes, int32_t compressible, void **ptr, int32_t *granted) {
+    if (!ptr || bytes == 0) return HEXB_ERR_ARG;
+    *ptr = nullptr;
+    if (granted) *granted = 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return HEXB_ERR_NOGPU;
+    CK(cudaSetDevice(device));
+    CK(cudaFree(nullptr));   // the device's primary context exists and is current: the driver calls below use it
+    const DrvApi &d = drv();
+    if (!d.ok) return HEXB_ERR_CUDA;
+    for (int attempt = compressible ? 0 : 1; attempt < 2; ++attempt) {   // compressible first, ordinary memory if the driver refuses
+        CUmemAllocationProp prop = {};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        prop.allocFlags.compressionType = attempt == 0 ? CU_MEM_ALLOCATION_COMP_GENERIC : CU_MEM_ALLOCATION_COMP_NONE;
+        size_t gran = 0;
+        if (d.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) continue;
+        const size_t size = (bytes + gran - 1) / gran * gran;
+        CUmemGenericAllocationHandle h;
+        if (d.Create(&h, size, &prop, 0) != CUDA_SUCCESS) continue;
+        CUmemAllocationProp got = {};
+        const bool comp = d.GetProps(&got, h) == CUDA_SUCCESS && got.allocFlags.compressionType == CU_MEM_ALLOCATION_COMP_GENERIC;
+        CUdeviceptr p = 0;
+        if (d.Reserve(&p, size, 0, 0, 0) != CUDA_SUCCESS) { d.Release(h); continue; }
+        if (d.Map(p, size, 0, h, 0) != CUDA_SUCCESS) { d.AddressFree(p, size); d.Release(h); continue; }
+        CUmemAccessDesc acc = {};
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (d.SetAccess(p, size, &acc, 1) != CUDA_SUCCESS) { d.Unmap(p, size); d.AddressFree(p, size); d.Release(h); continue; }
+        {
+            std::lock_guard<std::mutex> lock(g_mem_mu);
+            g_mem[p] = MemRec{h, size, device};
+        }
+        *ptr = (void *)p;
+        if (granted) *granted = comp ? 1 : 0;
+        return HEXB_OK;
+    }
+    return HEXB_ERR_CUDA;
+}
+
+int32_t hexb_mem_free(void *ptr) {
+    if (!ptr) return HEXB_OK;
+    MemRec r;
+    {
+        std::lock_guard<std::mutex> lock(g_mem_mu);
+        auto it = g_mem.find((CUdeviceptr)ptr);
+        if (it == g_mem.end()) return HEXB_ERR_ARG;
+        r = it->second;
+        g_mem.erase(it);
+    }
+    const DrvApi &d = drv();
+    if (!d.ok) return HEXB_ERR_CUDA;
+    cudaSetDevice(r.device);
+    cudaDeviceSynchronize();   // nothing may still be using the range
+    d.Unmap((CUdeviceptr)ptr, r.size);
+    d.AddressFree((CUdeviceptr)ptr, r.size);
+    d.Release(r.handle);
+    return HEXB_OK;
+}
 
 int32_t hexb_ply(hexb_env *env, const int32_t *actions, int8_t *ret, void *stream) {
     if (!env || !actions || !env->cfg.raw) return HEXB_ERR_ARG;
