@@ -754,6 +754,12 @@ int32_t hexb_mem_alloc(int32_t device, size_t bytes, int32_t compressible, void 
     if (granted) *granted = 0;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return HEXB_ERR_NOGPU;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct Restore {   // the caller's current device is left as it was
+        int dev;
+        ~Restore() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore{prev_dev};
     CK(cudaSetDevice(device));
     CK(cudaFree(nullptr));   // the device's primary context exists and is current: the driver calls below use it
     const DrvApi &d = drv();
@@ -801,11 +807,14 @@ int32_t hexb_mem_free(void *ptr) {
     }
     const DrvApi &d = drv();
     if (!d.ok) return HEXB_ERR_CUDA;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     cudaSetDevice(r.device);
     cudaDeviceSynchronize();   // nothing may still be using the range
     d.Unmap((CUdeviceptr)ptr, r.size);
     d.AddressFree((CUdeviceptr)ptr, r.size);
     d.Release(r.handle);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return HEXB_OK;
 }
 
