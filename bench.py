@@ -289,13 +289,16 @@ def extra_config(name, N, G, variant, agent_mode, K, preroll, dev, peak):
     from hex_gym_env_b200 import HexBatch
     env = HexBatch(N, G, variant=variant, device=dev.index, seed=0, agent_mode=agent_mode, auto_reset=True)
     env.reset()
-    env.rollout(preroll, outputs=False)
+    left = preroll
+    while left > 0:                      # untimed, in launches of at most 1,000 steps
+        env.rollout(min(left, 1000), outputs=False)
+        left -= 1000
     for _ in range(3):
         env.step()
-    ms, _ = time_steps(env, dev, K, True)
-    us = 1e3 * ms / K
+    ms, _ = time_steps(env, dev, K, True, reps=3)   # three replays of the K-step graph, timed as one bracket
+    us = 1e3 * ms / (3 * K)
     mv = G * moved_bytes(N) / (us * 1e-6) / 1e9
-    out = {"config": name, "board_size": N, "games": G, "steps": K, "preroll_steps": preroll, "us_per_step": us,
+    out = {"config": name, "board_size": N, "games": G, "steps": 3 * K, "preroll_steps": preroll, "us_per_step": us,
            "env_steps_per_sec": G / (us * 1e-6), "moved_GBps": mv, "frac_of_hbm_peak": mv / peak,
            "bytes_per_env_step_moved": moved_bytes(N), "memory_kind": env.memory_kind}
     env.close()
@@ -511,7 +514,8 @@ def run_gpu(args):
             extra_config("config 2: 7x7 HexEnv (variant A) + random_policy opponent, 65,536 games", 7, 65536, VARIANT_A, AGENT_BLACK, 200, 100, dev, peak),
             extra_config("config 3 shard: 11x11 SelfPlayEnv, 131,072 games (1 Mi games / 8 GPUs)", 11, 131072, VARIANT_B, AGENT_RANDOM, 200, 300, dev, peak),
             extra_config("config 4 env side: 6x6 SelfPlayEnv, 4,096 games", 6, 4096, VARIANT_B, AGENT_RANDOM, 200, 100, dev, peak),
-            extra_config("config 5: 19x19 SelfPlayEnv, 4,194,304 games", 19, 4194304, VARIANT_B, AGENT_RANDOM, 30, 200, dev, peak),
+            extra_config("config 5: 19x19 SelfPlayEnv, 4,194,304 games", 19, 4194304, VARIANT_B, AGENT_RANDOM, 30, 6000, dev, peak),   # ~36 episodes: the games must be out of phase, in compressible
+            # memory the step time follows how full the boards are (726-891 us over a cohort that is still in step, profiles/r2v)
         ]
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

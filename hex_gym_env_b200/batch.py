@@ -71,8 +71,11 @@ class HexBatch(object):
             compressible = (env_c != "0") if env_c is not None else self.state_bytes >= (64 << 20)
         self.compressible = bool(compressible)
         self.memory_kind = "ordinary (torch allocator)"
+        parts = os.environ.get("HEXB_COMPRESSIBLE_PARTS", "state,outputs")   # experiments: which buffers ("state", "outputs")
+        self._comp_state, self._comp_out = "state" in parts, "outputs" in parts
         with torch.cuda.device(self.device):
-            self._state = self._alloc(self.state_bytes + 256)
+            self._state = self._alloc(self.state_bytes + 256) if self._comp_state else \
+                torch.empty(self.state_bytes + 256, dtype=torch.uint8, device=self.device)
             off = (-self._state.data_ptr()) % 256
             self._state_ptr = self._state.data_ptr() + off
             h = ctypes.c_void_p()
@@ -129,7 +132,7 @@ class HexBatch(object):
             for d in shape:
                 n *= int(d)
             nbytes = n * torch.empty((), dtype=dtype).element_size()
-            if self.compressible and nbytes >= (8 << 20):
+            if self.compressible and self._comp_out and nbytes >= (8 << 20):
                 t = self._alloc(nbytes)[:nbytes].view(dtype).reshape(shape)
             else:
                 t = torch.empty(shape, dtype=dtype, device=self.device)
