@@ -73,6 +73,7 @@ class HexBatch(object):
         self.memory_kind = "ordinary (torch allocator)"
         parts = os.environ.get("HEXB_COMPRESSIBLE_PARTS", "state,outputs")   # experiments: which buffers ("state", "outputs")
         self._comp_state, self._comp_out = "state" in parts, "outputs" in parts
+        self._comp_min = int(float(os.environ.get("HEXB_COMPRESSIBLE_MIN_MB", "8")) * (1 << 20))   # smaller buffers stay with torch
         with torch.cuda.device(self.device):
             self._state = self._alloc(self.state_bytes + 256) if self._comp_state else \
                 torch.empty(self.state_bytes + 256, dtype=torch.uint8, device=self.device)
@@ -114,7 +115,7 @@ class HexBatch(object):
 
     def _alloc(self, nbytes):
         """uint8[nbytes] on the device: compressible memory from the library for large buffers when enabled, else torch's allocator."""
-        if self.compressible and nbytes >= (8 << 20):
+        if self.compressible and nbytes >= self._comp_min:
             try:
                 buf = _native.DeviceBuffer(nbytes, self.device.index, True)
                 self.memory_kind = "compressible (cuMemCreate, CU_MEM_ALLOCATION_COMP_GENERIC)" if buf.compressed else \
@@ -132,7 +133,7 @@ class HexBatch(object):
             for d in shape:
                 n *= int(d)
             nbytes = n * torch.empty((), dtype=dtype).element_size()
-            if self.compressible and self._comp_out and nbytes >= (8 << 20):
+            if self.compressible and self._comp_out and nbytes >= self._comp_min:
                 t = self._alloc(nbytes)[:nbytes].view(dtype).reshape(shape)
             else:
                 t = torch.empty(shape, dtype=dtype, device=self.device)
