@@ -47,6 +47,8 @@ def lib():
         L.emu_philox4x32_10.argtypes = [vp] * 3
         L.emu_draw01.restype = ctypes.c_double
         L.emu_draw01.argtypes = [u64, u64, ctypes.c_uint32]
+        L.emu_encode_word.argtypes = [ctypes.c_uint32, i32, vp, vp]
+        L.emu_encode_byte.argtypes = [ctypes.c_uint32, i32, vp, vp]
         _LIB = L
     return _LIB
 

@@ -263,4 +263,19 @@ void emu_stats(void *h, int64_t *out8) {
     for (int i = 0; i < 8; ++i) out8[i] = e->base.stats[i];
 }
 
+// the step kernel's word-wise observation / mask encode (encode_word_k with the per-variant constants) and the per-byte
+// definition it must agree with (encode_byte, agent's view), for tests/test_emu_parity.py
+void emu_encode_word(unsigned int x, int variant, unsigned int *obs, unsigned int *msk) {
+    uint32_t ka, kb, kc, o, m;
+    enc_consts(variant, ka, kb, kc);
+    encode_word_k(x, 1u, ka, kb, kc, o, m);
+    *obs = o;
+    *msk = m;
+}
+void emu_encode_byte(unsigned int b, int variant, unsigned int *obs, unsigned int *msk) {
+    uint32_t m;
+    *obs = encode_byte(b, variant, false, m) & 0xffu;
+    *msk = m;
+}
+
 }  // extern "C"

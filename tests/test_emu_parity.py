@@ -150,3 +150,32 @@ def test_golden_label_saturation(name):
 @pytest.mark.parametrize("name", golden_files("presetreset_"))
 def test_golden_preset_resets(name):
     parity.golden_preset_resets(lambda kind, N, G: EmuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True), name)
+
+
+def test_word_encode_matches_byte_definition():
+    """encode_word_k (the step kernel's 4-cells-per-word observation / mask encode: obs = mask*ka + C*kb + kc, no carries between
+    bytes) against encode_byte for EVERY valid label byte in every byte position, both variants, random neighbours."""
+    import ctypes
+    import random
+    from emu import emu as emu_mod
+    L = emu_mod.lib()
+    rnd = random.Random(7)
+    valid = [0] + list(range(1, 128)) + list(range(0x81, 0x100))      # empty, R labels, C labels (0x80 = label 0 never occurs)
+
+    def byte_def(b, variant):
+        o, m = ctypes.c_uint32(), ctypes.c_uint32()
+        L.emu_encode_byte(b, variant, ctypes.byref(o), ctypes.byref(m))
+        return o.value, m.value
+
+    for variant in (0, 1):
+        table = {b: byte_def(b, variant) for b in valid}
+        for b in valid:
+            for pos in range(4):
+                for _ in range(6):
+                    bytes_ = [rnd.choice(valid) for _ in range(4)]
+                    bytes_[pos] = b
+                    x = sum(v << (8 * k) for k, v in enumerate(bytes_))
+                    o, m = ctypes.c_uint32(), ctypes.c_uint32()
+                    L.emu_encode_word(x, variant, ctypes.byref(o), ctypes.byref(m))
+                    for k, v in enumerate(bytes_):
+                        assert ((o.value >> (8 * k)) & 0xff, (m.value >> (8 * k)) & 0xff) == table[v], (variant, hex(x), k)
