@@ -57,6 +57,20 @@ def test_state_bytes_and_errors(L):
         assert getattr(L, fn)(*([None] * args)) == -1                                         # null handle -> HEXB_ERR_ARG
 
 
+def test_mem_alloc_argument_checks(L):
+    """hexb_mem_alloc / hexb_mem_free without a device: bad arguments and the missing GPU are reported, nothing is allocated."""
+    import torch
+    p, got = ctypes.c_void_p(0x1234), ctypes.c_int32(7)
+    assert L.hexb_mem_alloc(0, 1 << 20, 1, None, None) == -1                      # HEXB_ERR_ARG: nowhere to put the pointer
+    assert L.hexb_mem_alloc(0, 0, 1, ctypes.byref(p), ctypes.byref(got)) == -1    # zero bytes
+    assert L.hexb_mem_free(None) == 0                                             # freeing nothing is fine
+    if not torch.cuda.is_available():
+        assert L.hexb_mem_alloc(0, 1 << 20, 1, ctypes.byref(p), ctypes.byref(got)) == -4   # HEXB_ERR_NOGPU
+        assert p.value is None and got.value == 0
+        with pytest.raises(RuntimeError, match="hexb_mem_alloc"):
+            _native.DeviceBuffer(1 << 20, 0, True)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
