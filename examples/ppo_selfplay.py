@@ -42,10 +42,15 @@ def main():
     ap.add_argument("--minibatch", type=int, default=16384)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--opponent", choices=["random", "self"], default="random",
+    ap.add_argument("--opponent", choices=["random", "self", "pool"], default="random",
                     help="random: BaseRandomPolicy inside the fused step kernel; self: a frozen copy of the policy, refreshed every "
-                         "--refresh iterations, played through the split step (hexb_half_step), like the reference's OpponentPolicy pool")
+                         "--refresh iterations, played through the split step (hexb_half_step); pool: the reference's opponent buffer "
+                         "(SelfplayWrapper.py:39-67,91-104 + SelfPlayCallback, EvaluationCallback.py:31-50): --pool-size frozen "
+                         "snapshots, per-episode choice on the device (80 %% the best one), every --eval-every iterations an "
+                         "evaluation against every entry and, if the learner scores, the worst entry replaced by it")
     ap.add_argument("--refresh", type=int, default=4)
+    ap.add_argument("--pool-size", type=int, default=8)
+    ap.add_argument("--eval-every", type=int, default=4)
     ap.add_argument("--obs-dtype", choices=["f32", "i8"], default="f32",
                     help="f32: the step kernel writes float32 observations straight into the rollout buffer (hexb_config.obs_dtype); "
                          "i8: int8 observations, converted for the network at every use")
@@ -54,7 +59,7 @@ def main():
     torch.manual_seed(args.seed)
     dev = torch.device("cuda", 0)
     env = HexBatch(args.board, args.games, variant=VARIANT_B, device=0, seed=args.seed, agent_mode=AGENT_RANDOM, auto_reset=True,
-                   manual_opponent=(args.opponent == "self"), pool_size=0,
+                   manual_opponent=(args.opponent != "random"), pool_size=args.pool_size if args.opponent == "pool" else 0,
                    obs_dtype=torch.float32 if args.obs_dtype == "f32" else torch.int8)
     policy = MlpPolicy(env.C).to(dev)
     frozen = MlpPolicy(env.C).to(dev)
@@ -66,6 +71,34 @@ def main():
         with torch.no_grad():
             logits, _ = frozen(obs.float())
             return masked_sample(logits, mask, generator=ogen)[0]
+
+    pool = None
+    if args.opponent == "pool":
+        from hex_gym_env_b200.opponents import OpponentPool, evaluate_pool
+
+        class Snapshot(object):
+            """A pool entry: a frozen network as a batched policy (OpponentPolicy.choose_action for n games). Replacing an entry
+            loads the learner's weights INTO its network, so a CUDA graph that captured the entry keeps reading the right tensors."""
+
+            def __init__(self):
+                self.net = MlpPolicy(env.C).to(dev)
+                self.net.load_state_dict(policy.state_dict())
+
+            def __call__(self, obs, mask):
+                with torch.no_grad():
+                    return masked_sample(self.net(obs.float())[0], mask, generator=ogen)[0]
+
+        entries = [Snapshot() for _ in range(args.pool_size)]
+        pool = OpponentPool(entries[0], buffer_size=args.pool_size, batch=env, dense=True)
+        for k in range(1, args.pool_size):
+            pool.set_opponent_model(k, entries[k], 0.0)
+        opponent_fn = pool
+        egen = torch.Generator(device=dev)
+        egen.manual_seed(args.seed + 5)
+
+        def greedy_agent(obs, mask):                       # the evaluation plays the learner's sampled policy, like training
+            with torch.no_grad():
+                return masked_sample(policy(obs.float())[0], mask, generator=egen)[0]
 
     opt = torch.optim.Adam(policy.parameters(), lr=args.lr, eps=1e-5, capturable=args.graph)
     col = RolloutCollector(env, args.n_steps, gamma=0.99, gae_lambda=0.95, seed=args.seed, extra_generators=[ogen])
@@ -105,7 +138,17 @@ def main():
         t0 = time.perf_counter()
         if args.opponent == "self" and it and it % args.refresh == 0:
             frozen.load_state_dict(policy.state_dict())
-        col.collect(policy, opponent_fn if args.opponent == "self" else None, use_graph=args.graph)
+        if pool is not None and it and it % args.eval_every == 0:
+            ev = evaluate_pool(env, pool, greedy_agent)      # set_eval(True): every game meets every entry once; set_eval(False)
+            def into_slot(i):                                # the learner replaces the worst entry: its weights go into that slot
+                entries[i].net.load_state_dict(policy.state_dict())
+                return entries[i]
+
+            score, idx_rep = pool.consider(policy, ev["mean_reward"], place=into_slot)
+            print(json.dumps({"iter": it, "eval_mean_reward": ev["mean_reward"], "eval_episodes": ev["episodes"], "score": score,
+                              "replaced_entry": idx_rep, "pool_scores": [round(float(x), 4) for x in pool.get_scores()]}))
+            col.restart()                                    # the evaluation reset the games: the next rollout starts from a reset
+        col.collect(policy, opponent_fn if args.opponent != "random" else None, use_graph=args.graph)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if args.graph and it == 1 and n % idx.numel() == 0:

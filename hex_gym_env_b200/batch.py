@@ -83,11 +83,13 @@ class HexBatch(object):
             check(self._lib.hexb_create(ctypes.byref(self.cfg), ctypes.c_void_p(self._state_ptr), self.state_bytes,
                                         self._stream(), ctypes.byref(h)))
         self._h = h
-        self.opp_index = self.to_move = None
+        self.opp_index = self.to_move = self.eval_episode = None
         if manual_opponent:  # per-game opponent bookkeeping, written by every reset / half step
             self.opp_index = torch.full((self.G,), -1, dtype=torch.int32, device=self.device)
             self.to_move = torch.full((self.G,), 2, dtype=torch.uint8, device=self.device)
             check(self._lib.hexb_set_opponent_buffers(self._h, _ptr(self.opp_index), _ptr(self.to_move)))
+            if eval_state:   # the evaluation cycle through the pool needs its per-game episode counter
+                self.set_eval(True)
         self._out = {}
         self._ws = None
         self._pinned = None
@@ -355,6 +357,22 @@ class HexBatch(object):
             out["term_obs"] = term_obs
         return out
 
+    def set_eval(self, eval_state):
+        """SelfPlayEnv.set_eval (SelfplayWrapper.py:117-120) for every game of the batch, at run time: while it is on, a restart
+        draws nothing for the opponent choice and - on a manual_opponent batch - episode k of a game since this call meets pool
+        entry k (self.opp_index = k while k <= pool_size - 1, then it stays; setup_opponents :92-96). Episodes under way go on."""
+        if self.variant != VARIANT_B or self.raw:
+            raise ValueError("set_eval belongs to SelfPlayEnv (variant B env handles)")
+        if self.opp_index is not None and self.eval_episode is None:
+            self.eval_episode = torch.zeros(self.G, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.hexb_set_eval(self._h, int(bool(eval_state)), _ptr(self.eval_episode), self._stream()))
+        self.cfg.eval_state = int(bool(eval_state))
+
+    @property
+    def eval_state(self):
+        return bool(self.cfg.eval_state)
+
     def opponent_opening(self, opponent_fn):
         """After reset(): let the caller's opponent open the games in which it moves first (agent is WHITE)."""
         o1, m1 = self._buf("opp_obs", (self.G, self.N, self.N), self.obs_dtype), self._buf("opp_mask", (self.G, self.C), torch.uint8)
@@ -463,7 +481,7 @@ class HexBatch(object):
         sd = {"config": cfg, "layout_version": int(self._lib.hexb_version()), "state": self._state[off:off + self.state_bytes].clone()}
         # per-game bookkeeping that lives outside the packed blob: the pool opponent drawn at reset for the running episode, whose
         # turn it is, and (when enabled) the info-dict tensors
-        for name in ("opp_index", "to_move", "last_move_opponent", "winner"):
+        for name in ("opp_index", "to_move", "eval_episode", "last_move_opponent", "winner"):
             t = getattr(self, name, None)
             if t is not None:
                 sd[name] = t.clone()
@@ -471,16 +489,21 @@ class HexBatch(object):
 
     def load_state_dict(self, sd):
         cfg = {f[0]: getattr(self.cfg, f[0]) for f in self.cfg._fields_ if f[0] != "device"}
-        if sd["config"] != cfg:
+        if {k: v for k, v in sd["config"].items() if k != "eval_state"} != {k: v for k, v in cfg.items() if k != "eval_state"}:
             raise ValueError("checkpoint belongs to a different configuration: %r vs %r" % (sd["config"], cfg))
         if sd.get("layout_version") != int(self._lib.hexb_version()) or sd["state"].numel() != self.state_bytes:
             raise ValueError("checkpoint was written by another version of the packed state layout (%r, library %r)"
                              % (sd.get("layout_version"), int(self._lib.hexb_version())))
         off = self._state_ptr - self._state.data_ptr()
         self._state[off:off + self.state_bytes].copy_(sd["state"].to(self.device))
-        for name in ("opp_index", "to_move", "last_move_opponent", "winner"):
+        if "eval_episode" in sd or bool(sd["config"].get("eval_state", 0)) != self.eval_state:   # set_eval is a run-time switch
+            self.set_eval(bool(sd["config"].get("eval_state", 0)))
+        for name in ("opp_index", "to_move", "eval_episode", "last_move_opponent", "winner"):
             t = getattr(self, name, None)
             if t is not None:
+                if name not in sd and name == "eval_episode":   # written before any set_eval call: no evaluation episode yet
+                    t.zero_()
+                    continue
                 if name not in sd:
                     raise ValueError("checkpoint lacks %r, which this batch tracks" % name)
                 t.copy_(sd[name].to(self.device))

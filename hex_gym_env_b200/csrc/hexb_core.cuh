@@ -112,6 +112,7 @@ struct Params {
     int half_side;        // MODE_HALF: 0 = the agent's ply, 1 = the opponent's ply
     int pool_size;        // setup_opponents: size of the opponent pool the index is drawn from
     int32_t *opp_index;   // [G] nullable: opponent chosen at reset, -1 = best model, k = pool entry (SelfplayWrapper.py:97-103)
+    int32_t *eval_episode;  // [G] nullable: episodes started since SelfPlayEnv.set_eval (hexb_set_eval; SelfplayWrapper.py:93-95)
     uint8_t *to_move;     // [G] MODE_HALF / MODE_RESET out: 0 agent to move, 1 opponent to move, 2 finished
     int32_t *info_opp;    // [G] nullable, MODE_STEP out: the opponent's move of this step (info["last_move_opponent"]), -1 = none
     int8_t *info_winner;  // [G] nullable, MODE_STEP out: env.winner after the step: -1 None, 0 BLACK, 1 WHITE, 3 illegal move
@@ -484,7 +485,16 @@ HEXB_HD void reset_game(Rec<N> &rec, const Params &P, unsigned long long gid, co
             if (P.agent_mode == 2) colour = (int)(draw01_cold(P.seed, gid, rec.draws++) * 2.0);
             meta |= M_COLOUR_SET | (colour ? M_TRANSPOSED : 0u);
         }
-        if (!inj_u && !P.eval_state) {  // setup_opponents (:97-103): 80 % the best model, else a uniformly drawn pool entry
+        if (P.eval_state) {  // setup_opponents while evaluating (:92-96): episode k since set_eval meets pool entry k, nothing is drawn
+            if (P.opp_index && P.eval_episode) {
+                const unsigned long long i = gid - (unsigned long long)P.game_offset;
+                const int ep = P.eval_episode[i];
+                if (ep <= P.pool_size - 1) {   // past the end of the pool the game keeps the opponent it has
+                    P.opp_index[i] = ep;
+                    P.eval_episode[i] = ep + 1;
+                }
+            }
+        } else if (!inj_u) {  // setup_opponents (:97-103): 80 % the best model, else a uniformly drawn pool entry
             const double rv = draw01_cold(P.seed, gid, rec.draws++);
             int pick = -1;
             if (!(rv < 0.8)) {   // random.random() for the pool index: the draw is always consumed, its value only matters to a caller-driven opponent

@@ -249,7 +249,7 @@ extern "C" HEXB_LOCAL void hexb_hostpack_finish(int abort);
 
 extern "C" {
 
-int32_t hexb_version(void) { return (1 << 16) | 3; }   // 1.3: obs_dtype, launch forms, hexb_gae, packed / asynchronous host step (+ hexb_mem_alloc: additive)
+int32_t hexb_version(void) { return (1 << 16) | 4; }   // 1.3: obs_dtype, launch forms, hexb_gae, packed / asynchronous host step (+ hexb_mem_alloc: additive); 1.4: hexb_set_eval
 
 const char *hexb_strerror(int32_t code) {
     switch (code) {
@@ -362,6 +362,17 @@ int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to
     if (!env) return HEXB_ERR_ARG;
     env->base.opp_index = opp_index;
     env->base.to_move = to_move;
+    return HEXB_OK;
+}
+
+int32_t hexb_set_eval(hexb_env *env, int32_t eval_state, int32_t *eval_episode, void *stream) {
+    if (!env || env->cfg.variant != HEXB_VARIANT_B || env->cfg.raw) return HEXB_ERR_ARG;
+    if (eval_episode) {
+        CK(cudaSetDevice(env->cfg.device));
+        CK(cudaMemsetAsync(eval_episode, 0, sizeof(int32_t) * (size_t)env->base.G, (cudaStream_t)stream));
+    }
+    env->cfg.eval_state = env->base.eval_state = eval_state ? 1 : 0;
+    env->base.eval_episode = eval_episode;
     return HEXB_OK;
 }
 

@@ -152,6 +152,12 @@ void op_set_launch_form(int64_t handle, int64_t warps_per_chunk) {
     check_rc(hexb_set_launch_form(env_of(handle), (int32_t)warps_per_chunk), "set_launch_form");
 }
 
+// SelfPlayEnv.set_eval at run time; eval_episode (int32[G], optional) becomes the handle's per-game evaluation-episode counter
+void op_set_eval(int64_t handle, bool eval_state, OptT eval_episode) {
+    Call k(handle);
+    check_rc(hexb_set_eval(k.e, eval_state ? 1 : 0, ptr<int32_t>(eval_episode, at::kInt, k.G, k.c.device, "eval_episode"), k.stream), "set_eval");
+}
+
 int64_t op_version() { return hexb_version(); }
 
 }  // namespace
@@ -171,6 +177,7 @@ TORCH_LIBRARY(hexb, m) {
     m.def("masked_sample(Tensor logits, Tensor mask, Tensor u, Tensor(a!)? actions, Tensor(b!)? logp, Tensor(c!)? entropy) -> ()");
     m.def("gae(Tensor rewards, Tensor values, Tensor dones, float gamma, float gae_lambda, Tensor(a!) advantages, Tensor(b!)? returns) -> ()");
     m.def("set_launch_form(int env, int warps_per_chunk) -> ()", &op_set_launch_form);
+    m.def("set_eval(int env, bool eval_state, Tensor(a!)? eval_episode) -> ()");
 }
 
 // The handle is an int, so these operators have no tensor argument to dispatch on when every optional is None: register them
@@ -186,4 +193,5 @@ TORCH_LIBRARY_IMPL(hexb, CompositeExplicitAutograd, m) {
     m.impl("stats", &op_stats);
     m.impl("masked_sample", &op_masked_sample);
     m.impl("gae", &op_gae);
+    m.impl("set_eval", &op_set_eval);
 }

@@ -243,6 +243,14 @@ int32_t hexb_stats(hexb_env *env, int64_t *out8, void *stream);
  * opp_index i32[G] (the opponent setup_opponents chose: -1 best model, k pool entry) and to_move u8[G] (0 agent, 1 opponent,
  * 2 finished). */
 int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to_move);
+
+/* SelfPlayEnv.set_eval(eval_state) (SelfplayWrapper.py:117-120; what SelfPlayCallback calls around its evaluation,
+ * EvaluationCallback.py:31-33) at run time: hexb_config.eval_state from now on. While it is set, a reset draws nothing for the
+ * opponent choice, and - when both opp_index (hexb_set_opponent_buffers) and eval_episode i32[G] (device, nullable, registered by
+ * this call and zeroed on `stream`, as set_eval zeroes self.eval_episode) are there - episode k of a game since this call meets
+ * pool entry k: opp_index = k while k <= pool_size - 1, later episodes keep the opponent they have (setup_opponents :92-96).
+ * The running episode is not touched. Variant B handles only. */
+int32_t hexb_set_eval(hexb_env *env, int32_t eval_state, int32_t *eval_episode, void *stream);
 int32_t hexb_half_step(hexb_env *env, int32_t side, const int32_t *actions, float *reward, uint8_t *done, void *term_obs,
                        void *stream);
 

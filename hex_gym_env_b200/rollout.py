@@ -126,6 +126,11 @@ class RolloutCollector(object):
         self._started = False
         self._graph, self._graph_key = None, None
 
+    def restart(self):
+        """The games were reset or stepped behind the collector's back (an evaluation pass, opponents.evaluate_pool): the next
+        collect() starts from a fresh reset instead of carrying the last observation over. A captured graph stays valid."""
+        self._started = False
+
     def collect(self, policy, opponent_fn=None, use_graph=False):
         """opponent_fn: only for manual_opponent batches - the learned opponent (see HexBatch.step_with_opponent).
 
@@ -149,7 +154,7 @@ class RolloutCollector(object):
         if not use_graph:
             self._rollout(policy, opponent_fn, carry=True)
             return buf
-        key = (id(policy), id(opponent_fn))
+        key = (id(policy), id(opponent_fn), getattr(opponent_fn, "version", 0))   # an OpponentPool counts its changes
         if self._graph is None or self._graph_key != key:
             g = torch.cuda.CUDAGraph()
             for gen in [self.gen] + self.extra_generators:

@@ -15,6 +15,8 @@ Fixture families
   envA_N*_of*.npz        variant-A HexEnv(opponent_policy=minihex.random_policy) rollouts, same two agent modes
   oppmodel_N*_a*.npz     SelfPlayEnv with OpponentPolicy opponents (scripted stand-ins for SB3 models, oracle/scripted.py): the
                          learned-opponent path incl. the 80/20 best/pool choice of setup_opponents and the opponent's observation
+  evalpool_N*_a*.npz     the same with SelfPlayEnv.set_eval switched on and off in mid-run: the evaluation cycle through the pool
+                         (setup_opponents in eval_state: episode k meets opponent_models[k], nothing is drawn)
   preset_N*.npz          HexGame.__init__ on preset boards (raster-order region rebuild), both variants
   kat.npz                the four hand-checked known-answer tests of SURVEY.md section 8c
 """
@@ -126,9 +128,12 @@ def rollout(kind, N, G, T, seed, agent_mode, fused, opponent_first=False, illega
     return out
 
 
-def rollout_scripted_opponent(N, G, T, seed, agent_mode, pool, illegal_rate=0.04):
+def rollout_scripted_opponent(N, G, T, seed, agent_mode, pool, illegal_rate=0.04, eval_schedule=None):
     """SelfPlayEnv whose opponents are OpponentPolicy objects (SelfplayWrapper.py:26-35) around scripted models: the
-    learned-opponent path (setup_opponents' 80/20 choice, continue_game with action masks). One env per game."""
+    learned-opponent path (setup_opponents' 80/20 choice, continue_game with action masks). One env per game.
+    eval_schedule {t: flag}: env.set_eval(flag) right before step t (SelfplayWrapper.py:117-120, what SelfPlayCallback does around
+    its evaluation, EvaluationCallback.py:31-33): while it is on, setup_opponents hands episode k since the call
+    opponent_models[k] (:92-96) and draws nothing; recorded as eval_at[t] (-1 = no call)."""
     from oracle.scripted import ScriptedModel
     minihex, A, B, S = rh.load()
     rs = np.random.RandomState(seed ^ 0xBEEF)
@@ -140,6 +145,10 @@ def rollout_scripted_opponent(N, G, T, seed, agent_mode, pool, illegal_rate=0.04
                regions=np.zeros((T, G, 2, N + 2, N + 2), np.uint8), counter=np.zeros((T, G, 2), np.int16),
                sim_cur=np.zeros((T, G), np.int8), draws=np.zeros((T, G), np.uint32), obs0=np.zeros((G, N, N), np.int8),
                mask0=np.zeros((G, C), np.uint8), agent=np.zeros(G, np.int8), draws0=np.zeros(G, np.uint32))
+    if eval_schedule:
+        out["eval_at"] = -np.ones(T, np.int8)
+        for t, flag in eval_schedule.items():
+            out["eval_at"][t] = int(bool(flag))
     for gi in range(G):
         stream = GameStream(seed, gi)
         rh.set_rng(stream)
@@ -154,6 +163,8 @@ def rollout_scripted_opponent(N, G, T, seed, agent_mode, pool, illegal_rate=0.04
         del log[:]
         out["obs0"][gi], out["mask0"][gi], out["agent"][gi], out["draws0"][gi] = obs, env.legal_actions(), env.agent_player_num, stream.idx
         for t in range(T):
+            if eval_schedule and t in eval_schedule:
+                env.set_eval(bool(eval_schedule[t]))
             legal = np.flatnonzero(env.legal_actions())
             a = int(rs.randint(C)) if rs.rand() < illegal_rate else int(legal[rs.randint(len(legal))])
             obs, r, done, _, _ = env.step(a)
@@ -442,6 +453,12 @@ def main():
         for agent_mode in (0, 1, 2):
             o = rollout_scripted_opponent(N, G, T, seed=3000 + N, agent_mode=agent_mode, pool=pool)
             np.savez_compressed(os.path.join(OUT, "oppmodel_N%d_a%d.npz" % (N, agent_mode)), N=N, seed=3000 + N, agent_mode=agent_mode,
+                                pool=pool, **o)
+    # evaluation mode switched on and off in mid-run; long enough for every game to outlast the pool (the index then stays put)
+    for N, G, T, pool, sched in [(4, 16, 90, 3, {20: True, 65: False}), (5, 12, 150, 6, {0: True, 100: False, 120: True})]:
+        for agent_mode in (0, 2):
+            o = rollout_scripted_opponent(N, G, T, seed=3500 + N, agent_mode=agent_mode, pool=pool, eval_schedule=sched)
+            np.savez_compressed(os.path.join(OUT, "evalpool_N%d_a%d.npz" % (N, agent_mode)), N=N, seed=3500 + N, agent_mode=agent_mode,
                                 pool=pool, **o)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden fixtures: %d files, %.1f KiB" % (len(os.listdir(OUT)), total / 1024.0))

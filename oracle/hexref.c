@@ -256,6 +256,7 @@ typedef struct {
     int env_cur;        /* B: HexEnv.current_player_num (HexSingleGame.py:209,259) */
     int env_winner;     /* self.winner at env level */
     int eval_state;     /* SelfplayWrapper.py:92 */
+    int eval_episode;   /* SelfplayWrapper.py:66,94-95: episodes started since set_eval */
     int64_t st[8];      /* episodes, black wins, white wins, agent wins, plies of finished episodes, invalid ends, env steps, plies */
     int plies;          /* plies in the running episode */
     int manual;         /* the opponent's moves come from the caller (an OpponentPolicy, SelfplayWrapper.py:26-35): resets do not open */
@@ -326,9 +327,17 @@ static void B_continue_game(env_t *e, const double *u_in, int reward[2]) {
     B_base_step(e, a, reward);
 }
 
-/* SelfPlayEnv.setup_opponents SelfplayWrapper.py:91-104 (every pool entry is a BaseRandomPolicy: only the draws matter) */
+/* SelfPlayEnv.setup_opponents SelfplayWrapper.py:91-104 (with BaseRandomPolicy entries only the draws matter; with a caller-driven
+ * opponent opp_index names the entry that plays). Evaluation (:92-96): episode k since set_eval meets opponent_models[k] while
+ * k <= len - 1, later episodes keep the opponent they have; nothing is drawn. */
 static void B_setup_opponents(env_t *e) {
-    if (e->eval_state) return;
+    if (e->eval_state) {
+        if (e->eval_episode <= e->pool_size - 1) {
+            e->opp_index = e->eval_episode;
+            e->eval_episode += 1;
+        }
+        return;
+    }
     double rv = rng_uniform01(&e->rng);
     e->opp_index = -1;                       /* self.opponent_model = self.best_model */
     if (!(rv < 0.8)) {
@@ -490,6 +499,12 @@ void hexref_batch_step(void *h, const int32_t *actions, const double *opp_u, int
 void hexref_batch_set_manual(void *h, int pool_size) {
     batch_t *b = (batch_t *)h;
     for (int64_t i = 0; i < b->G; ++i) { b->envs[i].manual = 1; b->envs[i].pool_size = pool_size; b->envs[i].opp_index = -1; }
+}
+
+/* SelfPlayEnv.set_eval SelfplayWrapper.py:117-120: eval_episode = 0, eval_state = the argument; the running episode goes on */
+void hexref_batch_set_eval(void *h, int eval_state) {
+    batch_t *b = (batch_t *)h;
+    for (int64_t i = 0; i < b->G; ++i) { b->envs[i].eval_episode = 0; b->envs[i].eval_state = eval_state ? 1 : 0; }
 }
 
 static int agent_to_move(const env_t *e) { return e->kind == 0 ? (e->g.cur == e->agent) : (e->env_cur == e->agent); }

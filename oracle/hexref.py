@@ -44,6 +44,7 @@ def lib():
         L.hexref_philox4x32_10.argtypes = [vp, vp, vp]
         L.hexref_set_threads.argtypes = [i32]
         L.hexref_batch_set_manual.argtypes = [vp, i32]
+        L.hexref_batch_set_eval.argtypes = [vp, i32]
         L.hexref_batch_half_step.argtypes = [vp, i32, vp, i32] + [vp] * 5
         L.hexref_batch_observe.argtypes = [vp, vp, vp]
         L.hexref_batch_opp_state.argtypes = [vp, vp, vp]
@@ -107,6 +108,9 @@ class RefBatch(object):
 
     def set_manual_opponent(self, pool_size=0):
         lib().hexref_batch_set_manual(self._h, pool_size)
+
+    def set_eval(self, eval_state):
+        lib().hexref_batch_set_eval(self._h, int(bool(eval_state)))
 
     def half_step(self, side, actions, auto_reset=True, want_term=False):
         reward = np.empty(self.G, np.float32)

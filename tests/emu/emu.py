@@ -40,6 +40,7 @@ def lib():
         L.emu_stats.argtypes = [vp, vp]
         L.emu_set_manual_opponent.argtypes = [vp, i32, vp, vp]
         L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.emu_set_eval.argtypes = [vp, i32, vp, i64]
         L.emu_set_info.argtypes = [vp, vp, vp]
         L.emu_rollout.argtypes = [vp, i32] + [vp] * 6
         L.emu_force_sweep.argtypes = [i32]
@@ -74,6 +75,11 @@ class EmuBatch(object):
             self.opp_index = np.full(num_games, -1, np.int32)
             self.to_move = np.full(num_games, 9, np.uint8)
             lib().emu_set_manual_opponent(self._h, pool_size, _p(self.opp_index), _p(self.to_move))
+
+    def set_eval(self, eval_state):
+        if getattr(self, "eval_episode", None) is None:
+            self.eval_episode = np.zeros(self.G, np.int32)
+        lib().emu_set_eval(self._h, int(bool(eval_state)), _p(self.eval_episode), self.G)
 
     def __del__(self):
         if getattr(self, "_h", None):

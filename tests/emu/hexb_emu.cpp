@@ -180,6 +180,12 @@ void emu_set_manual_opponent(void *h, int pool_size, int32_t *opp_index, uint8_t
     emu_env *e = (emu_env *)h;
     e->base.manual_opponent = 1; e->base.pool_size = pool_size; e->base.opp_index = opp_index; e->base.to_move = to_move;
 }
+void emu_set_eval(void *h, int eval_state, int32_t *eval_episode, long long G) {   // what hexb_set_eval does (SelfPlayEnv.set_eval)
+    emu_env *e = (emu_env *)h;
+    e->base.eval_state = eval_state ? 1 : 0;
+    e->base.eval_episode = eval_episode;
+    if (eval_episode) memset(eval_episode, 0, sizeof(int32_t) * (size_t)G);
+}
 void emu_set_info(void *h, int32_t *opp, int8_t *winner) {
     emu_env *e = (emu_env *)h;
     e->base.info_opp = opp; e->base.info_winner = winner;

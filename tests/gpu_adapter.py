@@ -57,6 +57,9 @@ class GpuBatch(object):
     def opp_state(self):
         return self._np(self.b.to_move), self._np(self.b.opp_index)
 
+    def set_eval(self, eval_state):
+        self.b.set_eval(eval_state)
+
     def view1(self):
         return self.encode(1)
 

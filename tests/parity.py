@@ -162,11 +162,14 @@ def snake_chain(make, N):
 def golden_oppmodel(make, name):
     """Caller-driven opponent (hexb_half_step) against the reference run with OpponentPolicy opponents (scripted models).
     The opponent's actions are re-derived here from the implementation's OWN side-to-move observation with the same scripted
-    rule the reference's models used, so the opponent view, the 80/20 opponent choice and the half steps are all pinned."""
+    rule the reference's models used, so the opponent view, the 80/20 opponent choice and the half steps are all pinned.
+    evalpool_* fixtures also switch SelfPlayEnv.set_eval on and off in mid-run (eval_at[t]: the call right before step t): the
+    evaluation cycle through the pool (SelfplayWrapper.py:92-96) must hand every episode the same pool entry."""
     from oracle.scripted import scripted_choice
     z = np.load(os.path.join(GOLDEN, name))
     N, seed, am, pool = int(z["N"]), int(z["seed"]), int(z["agent_mode"]), int(z["pool"])
     T, G = z["actions"].shape
+    eval_at = z["eval_at"] if "eval_at" in z.files else None
     env = make(hexref.KIND_SELFPLAY_B, N, G, seed=seed, agent_mode=am, manual_opponent=True, pool_size=pool)
     env.reset()
 
@@ -190,6 +193,8 @@ def golden_oppmodel(make, name):
     eq(e["draws"], z["draws0"], name + " draws0")
     for t in range(T):
         w = "%s t=%d " % (name, t)
+        if eval_at is not None and eval_at[t] >= 0:
+            env.set_eval(bool(eval_at[t]))
         h = env.half_step(0, z["actions"][t], want_term=True)
         reward, done, term = h["reward"].copy(), h["done"].astype(bool), h["term_obs"].copy()
         for j in (0, 1):

@@ -21,7 +21,7 @@ def make(kind, N, G, seed=0, game_offset=0, agent_mode=0, opponent_first=False, 
                     auto_reset=auto_reset, eval_state=eval_state, manual_opponent=manual_opponent, pool_size=pool_size)
 
 
-@pytest.mark.parametrize("name", golden_files("oppmodel_"))
+@pytest.mark.parametrize("name", golden_files("oppmodel_") + golden_files("evalpool_"))
 def test_golden_scripted_opponent(name):
     parity.golden_oppmodel(make, name)
 

@@ -1,0 +1,127 @@
+"""GPU (-m gpu): the opponent pool end to end - HexBatch.step_with_opponent driven by an OpponentPool of scripted models against
+the unmodified reference run with OpponentPolicy opponents (tests/golden/oppmodel_*.npz, evalpool_*.npz: the latter switch
+SelfPlayEnv.set_eval on and off in mid-run), the evaluation pass over the pool, and the checkpoint of the evaluation counters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_files
+from oracle.scripted import scripted_choice
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+
+
+class Scripted(object):
+    """The rule of oracle/scripted.py::ScriptedModel as a batched policy (evaluated on the host: this is a test double)."""
+
+    def __init__(self):
+        self.games = 0
+
+    def __call__(self, obs, mask):
+        o, m = obs.cpu().numpy(), mask.cpu().numpy()
+        self.games += len(o)
+        a = [scripted_choice(o[g], m[g]) if m[g].any() else 0 for g in range(len(o))]
+        return torch.tensor(a, dtype=torch.int32, device=obs.device)
+
+
+def _pool_and_batch(N, G, seed, agent_mode, pool_size, dense):
+    from hex_gym_env_b200 import VARIANT_B, HexBatch
+    from hex_gym_env_b200.opponents import OpponentPool
+    b = HexBatch(N, G, variant=VARIANT_B, device=0, seed=seed, agent_mode=agent_mode, manual_opponent=True, pool_size=pool_size)
+    pool = OpponentPool(Scripted(), buffer_size=pool_size, batch=b, dense=dense)
+    for k in range(pool_size):
+        pool.set_opponent_model(k, Scripted(), 0.0)          # distinct objects: every entry is dispatched on its own
+    return b, pool
+
+
+@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("name", golden_files("evalpool_") + ["oppmodel_N7_a2.npz"])
+def test_step_with_opponent_pool_against_the_reference(name, dense):
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, am, K = int(z["N"]), int(z["seed"]), int(z["agent_mode"]), int(z["pool"])
+    T, G = z["actions"].shape
+    eval_at = z["eval_at"] if "eval_at" in z.files else None
+    b, pool = _pool_and_batch(N, G, seed, am, K, dense)
+    b.reset()
+    b.opponent_opening(pool)
+    obs, mask = b.encode(0)
+    assert np.array_equal(obs.cpu().numpy(), z["obs0"]) and np.array_equal(mask.cpu().numpy(), z["mask0"])
+    for t in range(T):
+        if eval_at is not None and eval_at[t] >= 0:
+            pool.set_eval(bool(eval_at[t]))
+            assert b.eval_state == bool(eval_at[t])
+        b._buf("sw_term", (G, N, N), b.obs_dtype).zero_()
+        out = b.step_with_opponent(torch.from_numpy(z["actions"][t]).cuda(), pool, want_term=True)
+        done = z["done"][t].astype(bool)
+        w = "%s t=%d" % (name, t)
+        assert np.array_equal(out["done"].cpu().numpy().astype(bool), done), w
+        assert np.array_equal(out["reward"].cpu().numpy(), z["reward"][t]), w
+        assert np.array_equal(out["obs"].cpu().numpy(), z["obs"][t]), w
+        assert np.array_equal(out["mask"].cpu().numpy(), z["mask"][t]), w
+        assert np.array_equal(out["term_obs"].cpu().numpy()[done], z["term_obs"][t][done]), w
+    if not dense:   # the gather form never shows a model a game that is not its own
+        shown = sum(m.games for m, _ in pool.groups())
+        asked = int((z["opp_model"] != -9).sum()) + int((z["opp0_model"] != -9).sum())
+        assert shown == asked, (shown, asked)
+
+
+def test_evaluate_pool_meets_every_entry_once_per_game():
+    from hex_gym_env_b200.opponents import evaluate_pool
+    from hex_gym_env_b200.rollout import masked_sample
+    N, G, K = 5, 300, 4
+    b, pool = _pool_and_batch(N, G, 11, 2, K, dense=True)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+
+    def random_agent(obs, mask):
+        return masked_sample(torch.zeros(mask.shape, dtype=torch.float32, device=mask.device), mask, generator=gen)[0]
+
+    before = b.stats().cpu().numpy().copy()
+    r = evaluate_pool(b, pool, random_agent)
+    assert r["episodes"] == G * K and list(r["per_entry_episodes"]) == [G] * K
+    assert -1.0 <= r["mean_reward"] <= 1.0 and r["per_entry"].shape == (K,)
+    assert abs(r["mean_reward"] - float(np.mean(r["per_entry"]))) < 1e-12      # equal counts: mean of means
+    assert not b.eval_state and not pool.eval_state
+    assert (b.stats().cpu().numpy() - before)[0] >= G * K                      # the device counted at least those episodes
+    assert int((b.to_move == 0).all())                                         # left reset, the agent to move everywhere
+
+
+def test_checkpoint_carries_the_evaluation_cycle():
+    N, G, K = 4, 64, 5
+    a, pool_a = _pool_and_batch(N, G, 3, 2, K, dense=True)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+
+    def play(batch, pool, steps, g):
+        outs = []
+        obs, mask = batch.encode(0)
+        for _ in range(steps):
+            u = torch.rand(G, generator=g, device="cuda", dtype=torch.float64)
+            acts = batch.sample_actions(u, 0)
+            o = batch.step_with_opponent(acts, pool)
+            outs.append((o["obs"].clone(), o["reward"].clone(), o["done"].clone(), batch.opp_index.clone()))
+        return outs
+
+    a.reset()
+    a.opponent_opening(pool_a)
+    pool_a.set_eval(True)
+    play(a, pool_a, 12, gen)
+    sd = a.state_dict()
+    assert "eval_episode" in sd and sd["config"]["eval_state"] == 1 and int(sd["eval_episode"].max()) >= 1
+    gstate = gen.get_state()
+    want = play(a, pool_a, 25, gen)
+    b, pool_b = _pool_and_batch(N, G, 3, 2, K, dense=True)     # a fresh object in training mode
+    b.load_state_dict(sd)
+    assert b.eval_state
+    pool_b.eval_state = True
+    gen.set_state(gstate)
+    got = play(b, pool_b, 25, gen)
+    for t, (w, g) in enumerate(zip(want, got)):
+        for x, y in zip(w, g):
+            assert torch.equal(x, y), t

@@ -139,7 +139,7 @@ def test_snake_chain_worst_case(make, N):
     parity.snake_chain(make, N)
 
 
-@pytest.mark.parametrize("name", golden_files("oppmodel_"))
+@pytest.mark.parametrize("name", golden_files("oppmodel_") + golden_files("evalpool_"))
 def test_golden_scripted_opponent(make, name):
     """hexb_half_step (learned opponent) against the reference run with OpponentPolicy opponents."""
     parity.golden_oppmodel(make, name)

@@ -75,7 +75,7 @@ def test_envA_rollouts(name):
     _check_rollout(name, hexref.KIND_ENV_A)
 
 
-@pytest.mark.parametrize("name", golden_files("oppmodel_"))
+@pytest.mark.parametrize("name", golden_files("oppmodel_") + golden_files("evalpool_"))
 def test_scripted_opponent_rollouts(name):
     """The caller-driven opponent path of the oracle against the reference run with OpponentPolicy opponents."""
     import parity

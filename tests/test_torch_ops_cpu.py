@@ -6,7 +6,7 @@ import torch
 
 from hex_gym_env_b200 import torch_ops
 
-OPS = ("version", "reset", "step", "rollout", "half_step", "ply", "encode", "sample_actions", "stats", "masked_sample")
+OPS = ("version", "reset", "step", "rollout", "half_step", "ply", "encode", "sample_actions", "stats", "masked_sample", "gae", "set_launch_form", "set_eval")
 
 
 @pytest.fixture(scope="module")
