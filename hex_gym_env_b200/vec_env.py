@@ -12,6 +12,9 @@ this contract is duck-typed; if gymnasium / SB3 are importable the spaces are re
   auto-reset on done, with infos[i]["terminal_observation"] for the finished games
   env_method("action_masks") / action_masks() -> bool[G,C]      (what sb3_contrib's get_action_masks() calls)
   get_attr / set_attr / env_is_wrapped / seed / close
+Learned opponents: base_model= / buffer_size= / scores= as in selfplay_wrapper(HexEnv)(...) give every game the reference's opponent
+buffer (one OpponentPool, opponents.py); its API (set_eval, get_scores, set_opponent_model, ...) is reachable on the env and
+through env_method, which is what SelfPlayCallback (minihex/EvaluationCallback.py) calls on its gym_env.
 
 `output="numpy"` (default, what SB3 expects) copies results to host arrays; `output="torch"` returns device tensors and
 never touches the host (use it when the policy lives on the same GPU; `infos` is then a lazy object, not a list).
@@ -75,7 +78,8 @@ except Exception:  # pragma: no cover - SB3 is absent in the build image
 
 class HexVecEnv(_VecEnvBase):
     def __init__(self, board_size=5, num_envs=1024, variant="selfplay", agent_player_num=None, opponent_first=False,
-                 seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0, sample_board=False):
+                 seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0, sample_board=False,
+                 base_model=None, buffer_size=20, scores=None):
         if variant in ("selfplay", "B", VARIANT_B):
             v = VARIANT_B
             agent_mode = AGENT_RANDOM if agent_player_num is None else (AGENT_WHITE if int(agent_player_num) else AGENT_BLACK)
@@ -92,9 +96,18 @@ class HexVecEnv(_VecEnvBase):
             raise ValueError("sample_board is a SelfPlayEnv (variant B) option (HexSingleGame.py:171)")
         # sample_board: episodes start from random positions. The fused step kernel restarts games on the empty board, so this
         # mode runs the split step instead (agent ply / built-in random opponent ply as separate launches around the import).
+        # base_model: learned opponents - selfplay_wrapper(HexEnv)(base_model=..., scores=..., buffer_size=...) for every game
+        # (SelfplayWrapper.py:39-67): a batched policy (see opponents.py) fills the pool; the split step plays its entries.
+        if base_model is not None and (v != VARIANT_B or sample_board):
+            raise ValueError("base_model (an opponent pool) belongs to the SelfPlayEnv variant without sample_board")
         self.batch = HexBatch(board_size, num_envs, variant=v, device=device, seed=seed, game_offset=game_offset,
                               agent_mode=agent_mode, opponent_first=opponent_first, auto_reset=True,
-                              manual_opponent=self.sample_board)
+                              manual_opponent=self.sample_board or base_model is not None,
+                              pool_size=int(buffer_size) if base_model is not None else 0)
+        self.pool = None
+        if base_model is not None:
+            from .opponents import OpponentPool
+            self.pool = OpponentPool(base_model, buffer_size=int(buffer_size), scores=scores, batch=self.batch)
         self.device = self.batch.device
         self._bgen = torch.Generator(device=self.device)
         self._bgen.manual_seed(int(seed) + 0x5EED)
@@ -146,6 +159,9 @@ class HexVecEnv(_VecEnvBase):
             self._restart_on_sampled_boards()
             self.batch.opponent_catch_up()      # SelfPlayEnv.reset -> continue_game where the opponent moves first
             obs, mask = self.batch.encode(0)
+        elif self.pool is not None:
+            self.batch.opponent_opening(self.pool)   # the chosen pool entry opens where the agent is WHITE (:79-80)
+            obs, mask = self.batch.encode(0)
         self._mask = mask
         return self._obs_out(obs)
 
@@ -171,7 +187,13 @@ class HexVecEnv(_VecEnvBase):
         self._actions = actions
 
     def step_wait(self):
-        o = self._step_sampled(self._actions) if self.sample_board else self.batch.step(self._actions, want_term=True)
+        if self.sample_board:
+            o = self._step_sampled(self._actions)
+        elif self.pool is not None:
+            self.batch._buf("sw_term", (self.batch.G, self.batch.N, self.batch.N), self.batch.obs_dtype)
+            o = self.batch.step_with_opponent(self._actions, self.pool, want_term=True)
+        else:
+            o = self.batch.step(self._actions, want_term=True)
         self._mask = o["mask"]
         if self.output == "torch":
             infos = _LazyInfos(o["done"], o["term_obs"], self.num_envs)
@@ -199,11 +221,28 @@ class HexVecEnv(_VecEnvBase):
         torch.cuda.current_stream(self.device).synchronize()
         return h.numpy().astype(bool)
 
+    # the opponent buffer of SelfPlayEnv (SelfplayWrapper.py:106-144), one pool for all games: what SelfPlayCallback calls on its
+    # gym_env (EvaluationCallback.py:31-50). Also reachable through env_method, which answers once per env like SB3 does.
+    _POOL_API = ("set_eval", "get_scores", "get_opponent_models", "set_opponent_model", "append_opponent_model",
+                 "get_best_mean_reward", "save_best_model")
+    _POOL_ATTRS = ("opponent_models", "opponent_scores", "best_model", "best_score", "best_mean_reward", "eval_state")
+
+    def __getattr__(self, name):
+        if name in HexVecEnv._POOL_API or name in HexVecEnv._POOL_ATTRS:
+            pool = self.__dict__.get("pool")
+            if pool is None:
+                raise AttributeError("%r needs an opponent pool: create the HexVecEnv with base_model=..." % (name,))
+            return getattr(pool, name)
+        raise AttributeError(name)
+
     def env_method(self, method_name, *args, indices=None, **kwargs):
+        idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
         if method_name in ("action_masks", "legal_actions", "get_action_mask"):
             m = self.action_masks()
-            idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
             return [m[i] for i in idx]
+        if method_name in HexVecEnv._POOL_API and self.pool is not None:
+            r = getattr(self.pool, method_name)(*args, **kwargs)     # one pool for all games: called once
+            return [r for _ in idx]
         raise AttributeError("HexVecEnv has no per-env method %r" % (method_name,))
 
     def get_attr(self, attr_name, indices=None):

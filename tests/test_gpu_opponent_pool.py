@@ -125,3 +125,37 @@ def test_checkpoint_carries_the_evaluation_cycle():
     for t, (w, g) in enumerate(zip(want, got)):
         for x, y in zip(w, g):
             assert torch.equal(x, y), t
+
+
+@pytest.mark.parametrize("name", ["evalpool_N5_a2.npz", "oppmodel_N4_a1.npz"])
+def test_vec_env_with_an_opponent_pool_against_the_reference(name):
+    """HexVecEnv(base_model=..., buffer_size=...) = selfplay_wrapper(HexEnv)(base_model=..., buffer_size=...) for every game: the
+    SB3-shaped surface on top of the pool, set_eval through env_method like SelfPlayCallback reaches it."""
+    from hex_gym_env_b200.vec_env import HexVecEnv
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, am, K = int(z["N"]), int(z["seed"]), int(z["agent_mode"]), int(z["pool"])
+    T, G = z["actions"].shape
+    eval_at = z["eval_at"] if "eval_at" in z.files else None
+    env = HexVecEnv(board_size=N, num_envs=G, seed=seed, agent_player_num=None if am == 2 else am, base_model=Scripted(),
+                    buffer_size=K, scores=np.zeros(K), device=0)
+    assert len(env.get_opponent_models()) == K and list(env.get_scores()) == [0.0] * K and env.best_score == 0.0
+    for k in range(K):
+        env.set_opponent_model(k, Scripted(), 0.0)
+    obs = env.reset()
+    assert obs.dtype == np.float32 and np.array_equal(obs, z["obs0"].astype(np.float32))
+    assert np.array_equal(np.stack(env.env_method("action_masks")), z["mask0"].astype(bool))
+    for t in range(T):
+        if eval_at is not None and eval_at[t] >= 0:
+            r = env.env_method("set_eval", bool(eval_at[t]))
+            assert len(r) == G and env.eval_state == bool(eval_at[t]) and env.batch.eval_state == bool(eval_at[t])
+        obs, rew, done, infos = env.step(z["actions"][t])
+        w = "%s t=%d" % (name, t)
+        assert np.array_equal(done, z["done"][t].astype(bool)), w
+        assert np.array_equal(rew, z["reward"][t]), w
+        assert np.array_equal(obs, z["obs"][t].astype(np.float32)), w
+        assert np.array_equal(env.action_masks(), z["mask"][t].astype(bool)), w
+        for g in np.flatnonzero(done):
+            assert np.array_equal(infos[g]["terminal_observation"], z["term_obs"][t][g].astype(np.float32)), w
+    with pytest.raises(AttributeError):
+        HexVecEnv(board_size=4, num_envs=8, device=0).get_scores()      # no pool: the pool API is absent, not silently empty
+    env.close()
