@@ -74,24 +74,19 @@ def main():
 
     pool = None
     if args.opponent == "pool":
-        from hex_gym_env_b200.opponents import OpponentPool, evaluate_pool
+        from hex_gym_env_b200.opponents import OpponentPool, StackedMlpOpponents, evaluate_pool
 
-        class Snapshot(object):
-            """A pool entry: a frozen network as a batched policy (OpponentPolicy.choose_action for n games). Replacing an entry
-            loads the learner's weights INTO its network, so a CUDA graph that captured the entry keeps reading the right tensors."""
+        # every pool entry (and the best model) is a slot of ONE stack of weights: a batched matmul per layer evaluates all of them
+        # for all games; replacing an entry loads the learner's weights INTO its slot, so a captured CUDA graph stays valid
+        def pi_linears():
+            return [m for m in policy.pi if isinstance(m, nn.Linear)]
 
-            def __init__(self):
-                self.net = MlpPolicy(env.C).to(dev)
-                self.net.load_state_dict(policy.state_dict())
-
-            def __call__(self, obs, mask):
-                with torch.no_grad():
-                    return masked_sample(self.net(obs.float())[0], mask, generator=ogen)[0]
-
-        entries = [Snapshot() for _ in range(args.pool_size)]
-        pool = OpponentPool(entries[0], buffer_size=args.pool_size, batch=env, dense=True)
-        for k in range(1, args.pool_size):
-            pool.set_opponent_model(k, entries[k], 0.0)
+        stack = StackedMlpOpponents((env.C, 64, 64, env.C), args.pool_size + 1, device=dev, generator=ogen)
+        for sl in range(args.pool_size + 1):
+            stack.load(sl, pi_linears())
+        pool = OpponentPool(stack.entry(0), buffer_size=args.pool_size, batch=env)
+        for k in range(args.pool_size):
+            pool.set_opponent_model(k, stack.entry(k + 1), 0.0)
         opponent_fn = pool
         egen = torch.Generator(device=dev)
         egen.manual_seed(args.seed + 5)
@@ -141,8 +136,8 @@ def main():
         if pool is not None and it and it % args.eval_every == 0:
             ev = evaluate_pool(env, pool, greedy_agent)      # set_eval(True): every game meets every entry once; set_eval(False)
             def into_slot(i):                                # the learner replaces the worst entry: its weights go into that slot
-                entries[i].net.load_state_dict(policy.state_dict())
-                return entries[i]
+                stack.load(i + 1, pi_linears())
+                return stack.entry(i + 1)
 
             score, idx_rep = pool.consider(policy, ev["mean_reward"], place=into_slot)
             print(json.dumps({"iter": it, "eval_mean_reward": ev["mean_reward"], "eval_episodes": ev["episodes"], "score": score,

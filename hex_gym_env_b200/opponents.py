@@ -26,7 +26,7 @@ import random as _random
 import numpy as np
 import torch
 
-__all__ = ["OpponentPool", "evaluate_pool"]
+__all__ = ["OpponentPool", "StackedMlpOpponents", "evaluate_pool"]
 
 
 class OpponentPool(object):
@@ -72,7 +72,7 @@ class OpponentPool(object):
             self.best_model = opponent_model
             self.best_mean_reward = mean_reward
         self.opponent_models.append(opponent_model)
-        self.version += 1
+        self._changed()
 
     def get_best_mean_reward(self):
         return self.best_mean_reward
@@ -94,7 +94,7 @@ class OpponentPool(object):
         if score > self.best_score:
             self.best_model = model
             self.best_score = score
-        self.version += 1
+        self._changed()
 
     def get_opponent_models(self):
         return self.opponent_models
@@ -135,7 +135,30 @@ class OpponentPool(object):
                 out.append((m, [k]))
         return out
 
+    def _stack_slots(self, device):
+        """When every entry (and the best model) is a slot of one StackedMlpOpponents: (stack, long[pool + 1] slot of index k + 1)."""
+        models = [self.best_model] + list(self.opponent_models)
+        stack = getattr(models[0], "stack", None)
+        if stack is None or any(getattr(m, "stack", None) is not stack for m in models):
+            return None, None
+        cache = self.__dict__.setdefault("_slots", {})
+        hit = cache.get(str(device))
+        if hit is None or hit[0] != self.version:
+            hit = (self.version, torch.tensor([m.slot for m in models], dtype=torch.long, device=device))
+            cache[str(device)] = hit
+        return stack, hit[1]
+
+    def _changed(self):
+        """An entry or the best model changed: rebuild the slot table right away for the devices it is used on (a host-to-device
+        copy, which must not wait for the next __call__ - that one may run inside a CUDA-graph capture)."""
+        self.version += 1
+        for dev in list(self.__dict__.get("_slots", {})):
+            self._stack_slots(torch.device(dev))
+
     def __call__(self, obs, mask, to_move, opp_index):
+        stack, slot_of = self._stack_slots(opp_index.device)
+        if stack is not None:   # one batched evaluation of all entries, each game keeps its own (games not waiting are ignored anyway)
+            return stack.actions(obs, mask, slot_of[opp_index.long() + 1])
         actions = torch.zeros(opp_index.shape[0], dtype=torch.int32, device=opp_index.device)
         waiting = to_move == 1
         for model, entries in self.groups():
@@ -151,6 +174,69 @@ class OpponentPool(object):
                 if idx.numel():
                     actions[idx] = model(obs[idx], mask[idx]).to(torch.int32)
         return actions
+
+
+class StackedMlpOpponents(object):
+    """Every pool entry as ONE set of stacked weights: S policy networks of the same architecture (the reference's pool holds
+    MaskablePPO MlpPolicy snapshots, all `pi` = Linear-tanh-Linear-tanh-Linear, scripts/experiments/*.py:40) live in tensors
+    W_l[S, in_l, out_l], b_l[S, out_l], so one batched matmul per layer evaluates all of them for all games and a gather keeps
+    each game's own entry - a handful of launches per opponent pass whatever the pool size, instead of one forward per entry.
+    Replacing an entry copies the learner's weights INTO its slot, so a captured CUDA graph keeps reading the right memory.
+
+    entry(slot) is that slot as a pool entry (a batched policy on its own, and recognised by OpponentPool, which then asks the
+    stack once for all games). Actions are sampled with hexb_masked_sample (OpponentPolicy.choose_action calls
+    predict(deterministic=False)); deterministic=True takes the legal arg-max instead (pure torch, also what the CPU tests use)."""
+
+    class Entry(object):
+        def __init__(self, stack, slot):
+            self.stack, self.slot = stack, int(slot)
+
+        def __call__(self, obs, mask):
+            slots = torch.full((obs.shape[0],), self.slot, dtype=torch.long, device=obs.device)
+            return self.stack.actions(obs, mask, slots)
+
+    def __init__(self, layer_sizes, slots, device=None, deterministic=False, generator=None):
+        self.sizes, self.S = [int(x) for x in layer_sizes], int(slots)
+        self.deterministic, self.generator = bool(deterministic), generator
+        self.W = [torch.zeros(self.S, i, o, device=device) for i, o in zip(self.sizes[:-1], self.sizes[1:])]
+        self.b = [torch.zeros(self.S, o, device=device) for o in self.sizes[1:]]
+
+    def entry(self, slot):
+        if not 0 <= slot < self.S:
+            raise IndexError("slot %r of %d" % (slot, self.S))
+        return StackedMlpOpponents.Entry(self, slot)
+
+    def load(self, slot, linears):
+        """Copy a network into a slot, in place. linears: its torch.nn.Linear layers in order (e.g. [m for m in policy.pi if
+        isinstance(m, nn.Linear)]), or (weight[out,in], bias[out]) pairs."""
+        linears = list(linears)
+        if len(linears) != len(self.W):
+            raise ValueError("expected %d linear layers, got %d" % (len(self.W), len(linears)))
+        with torch.no_grad():
+            for l, lin in enumerate(linears):
+                w, b = (lin.weight, lin.bias) if hasattr(lin, "weight") else lin
+                if tuple(w.shape) != (self.sizes[l + 1], self.sizes[l]):
+                    raise ValueError("layer %d has shape %s, the stack holds %s" % (l, tuple(w.shape), (self.sizes[l + 1], self.sizes[l])))
+                self.W[l][slot].copy_(w.detach().t())
+                self.b[l][slot].copy_(b.detach())
+
+    def logits(self, obs, slots):
+        """f32[G, out]: the network of slot slots[g] applied to game g; every slot is evaluated for every game (dense)."""
+        G = obs.shape[0]
+        h = obs.reshape(G, -1).to(self.W[0].dtype).unsqueeze(0).expand(self.S, G, self.sizes[0])
+        for l in range(len(self.W)):
+            h = torch.baddbmm(self.b[l].unsqueeze(1), h, self.W[l])
+            if l + 1 < len(self.W):
+                h = torch.tanh(h)
+        return h[slots.long(), torch.arange(G, device=h.device)]
+
+    def actions(self, obs, mask, slots):
+        with torch.no_grad():
+            lg = self.logits(obs, slots)
+            if self.deterministic:
+                return lg.masked_fill(mask == 0, float("-inf")).argmax(dim=1).to(torch.int32)
+            from .rollout import masked_sample
+            return masked_sample(lg, mask, generator=self.generator)[0]
 
 
 def evaluate_pool(batch, pool, agent_fn, max_steps=None):

@@ -55,6 +55,8 @@ def test_state_bytes_and_errors(L):
     assert L.hexb_strerror(0) == b"ok" and b"argument" in L.hexb_strerror(-1) and b"unknown" in L.hexb_strerror(-99)
     for fn, args in (("hexb_step", 10), ("hexb_reset", 6), ("hexb_ply", 4), ("hexb_stats", 3), ("hexb_destroy", 1)):
         assert getattr(L, fn)(*([None] * args)) == -1                                         # null handle -> HEXB_ERR_ARG
+    assert L.hexb_set_eval(None, 1, None, None) == -1 and L.hexb_half_step(None, 0, None, None, None, None, None) == -1
+    assert L.hexb_version() & 0xffff >= 4                                                     # 1.4: hexb_set_eval
 
 
 def test_mem_alloc_argument_checks(L):

@@ -159,3 +159,66 @@ def test_vec_env_with_an_opponent_pool_against_the_reference(name):
     with pytest.raises(AttributeError):
         HexVecEnv(board_size=4, num_envs=8, device=0).get_scores()      # no pool: the pool API is absent, not silently empty
     env.close()
+
+
+def test_stacked_pool_samples_and_lives_in_the_rollout_graph():
+    """StackedMlpOpponents on the device: its sampled actions are hexb_masked_sample of its gathered logits with the same
+    uniforms, and a pool made of its slots runs inside RolloutCollector's CUDA graph, which is captured again when the pool changes."""
+    import torch.nn as nn
+    from hex_gym_env_b200 import VARIANT_B, HexBatch, OpponentPool, StackedMlpOpponents
+    from hex_gym_env_b200.rollout import RolloutCollector, masked_sample
+    N, G, K, T = 4, 512, 3, 8
+    C = N * N
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+
+    class Policy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pi = nn.Sequential(nn.Flatten(), nn.Linear(C, 32), nn.Tanh(), nn.Linear(32, 32), nn.Tanh(), nn.Linear(32, C))
+            self.vf = nn.Sequential(nn.Flatten(), nn.Linear(C, 32), nn.Tanh(), nn.Linear(32, 1))
+
+        def forward(self, obs):
+            return self.pi(obs), self.vf(obs).squeeze(-1)
+
+    policy = Policy().to(dev)
+    linears = lambda: [m for m in policy.pi if isinstance(m, nn.Linear)]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    stack = StackedMlpOpponents((C, 32, 32, C), K + 1, device=dev, generator=gen)
+    for sl in range(K + 1):
+        stack.load(sl, linears())
+    obs = torch.randint(-1, 2, (G, N, N), device=dev).to(torch.int8)
+    mask = (obs.reshape(G, C) == 0).to(torch.uint8)
+    mask[:, 3] = 1
+    slots = torch.randint(0, K + 1, (G,), device=dev)
+    with torch.no_grad():
+        assert torch.allclose(stack.logits(obs, slots), policy.pi(obs.float()), atol=1e-5)     # every slot holds the same network here
+    state = gen.get_state()
+    got = stack.actions(obs, mask, slots)
+    gen.set_state(state)
+    u = torch.rand(G, dtype=torch.float64, device=dev, generator=gen)
+    assert torch.equal(got, masked_sample(stack.logits(obs, slots), mask, u=u)[0])
+    assert bool((mask.gather(1, got.long().unsqueeze(1)) == 1).all())
+
+    env = HexBatch(N, G, variant=VARIANT_B, device=0, seed=2, agent_mode=2, manual_opponent=True, pool_size=K, obs_dtype=torch.float32)
+    pool = OpponentPool(stack.entry(0), buffer_size=K, batch=env)
+    for k in range(K):
+        pool.set_opponent_model(k, stack.entry(k + 1), 0.0)
+    col = RolloutCollector(env, T, seed=3, extra_generators=[gen])
+    col.collect(policy, pool, use_graph=True)        # the first rollout runs eagerly
+    col.collect(policy, pool, use_graph=True)        # captured and replayed
+    key = col._graph_key
+    col.collect(policy, pool, use_graph=True)        # replayed
+    assert col._graph_key == key
+    with torch.no_grad():
+        policy.pi[1].weight.mul_(1.5)
+    stack.load(2, linears())                         # the learner's weights into slot 2 (entry 1), which becomes the best model
+    pool.set_opponent_model(1, stack.entry(2), 0.5)
+    col.collect(policy, pool, use_graph=True)
+    assert col._graph_key != key and pool.best_model.slot == 2
+    torch.cuda.synchronize()
+    st = env.stats().cpu().numpy()
+    assert st[0] > 0 and st[5] == 0                  # episodes finished, none by an illegal agent move
+    buf = col.buf
+    assert bool(torch.isfinite(buf.advantages).all()) and bool((buf.action_masks[:-1].gather(2, buf.actions.long().unsqueeze(2)) == 1).all())

@@ -133,3 +133,64 @@ def test_binding_checks():
     fb.manual_opponent = False
     with pytest.raises(ValueError, match="manual_opponent"):
         OpponentPool(Tagged(0), buffer_size=3, batch=fb)
+
+
+def _mlp(sizes, seed):
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    layers = []
+    for i, (a, b) in enumerate(zip(sizes[:-1], sizes[1:])):
+        layers.append(nn.Linear(a, b))
+        if i + 2 < len(sizes):
+            layers.append(nn.Tanh())
+    return nn.Sequential(*layers)
+
+
+def test_stacked_mlp_opponents_equal_the_networks_one_by_one():
+    """One batched matmul per layer over all slots + a gather == each game's own network applied on its own."""
+    import torch.nn as nn
+    from hex_gym_env_b200.opponents import StackedMlpOpponents
+    N, K, G = 4, 5, 300
+    sizes = (N * N, 64, 64, N * N)
+    nets = [_mlp(sizes, 100 + k) for k in range(K + 1)]            # slot 0 = the best model, slot k + 1 = entry k
+    stack = StackedMlpOpponents(sizes, K + 1, deterministic=True)
+    for sl, net in enumerate(nets):
+        stack.load(sl, [m for m in net if isinstance(m, nn.Linear)])
+    g = torch.Generator().manual_seed(3)
+    obs = torch.randint(-1, 2, (G, N, N), generator=g).to(torch.int8)
+    mask = (obs.reshape(G, -1) == 0).to(torch.uint8)
+    mask[:, 0] = 1                                                   # never an empty mask
+    opp_index = torch.randint(-1, K, (G,), generator=g, dtype=torch.int32)
+    to_move = torch.ones(G, dtype=torch.uint8)
+    pool = OpponentPool(stack.entry(0), buffer_size=K)
+    for k in range(K):
+        pool.set_opponent_model(k, stack.entry(k + 1), 0.0)
+    assert pool._stack_slots(obs.device)[0] is stack
+    got = pool(obs, mask, to_move, opp_index)
+    lg = stack.logits(obs, (opp_index + 1).long())
+    x = obs.reshape(G, -1).float()
+    with torch.no_grad():
+        for gi in range(G):
+            want = nets[int(opp_index[gi]) + 1](x[gi:gi + 1])[0]
+            assert torch.allclose(lg[gi], want, atol=1e-5), gi
+            legal = want.masked_fill(mask[gi] == 0, float("-inf"))
+            top2 = legal.topk(2).values
+            if top2[0] - top2[1] > 1e-4:                             # (a tie within rounding may go either way)
+                assert int(got[gi]) == int(legal.argmax()), gi
+            assert mask[gi, int(got[gi])] == 1
+    # a slot as an entry on its own, and a pool with a foreign entry falls back to the per-model dispatch
+    one = stack.entry(2)(obs[:7], mask[:7])
+    assert torch.equal(one, stack.actions(obs[:7], mask[:7], torch.full((7,), 2)))
+    pool.set_opponent_model(1, Tagged(3), 0.0)
+    assert pool._stack_slots(obs.device)[0] is None
+    mixed = pool(obs, mask, to_move, opp_index)
+    assert bool((mixed[opp_index == 1] == 3).all()) and torch.equal(mixed[opp_index != 1], got[opp_index != 1])
+    # replacing an entry = loading into its slot: the very same tensors, new numbers; the pool's best slot follows its best model
+    before = stack.W[0].data_ptr()
+    stack.load(3, [m for m in _mlp(sizes, 999) if isinstance(m, nn.Linear)])
+    assert stack.W[0].data_ptr() == before
+    pool.set_opponent_model(1, stack.entry(2), 0.7)                  # new best score -> best_model = slot 2
+    _, slots = pool._stack_slots(obs.device)
+    assert slots.tolist() == [2, 1, 2, 3, 4, 5]
+    with pytest.raises(ValueError):
+        stack.load(0, [m for m in _mlp((16, 32, 16), 1) if isinstance(m, nn.Linear)])
