@@ -159,6 +159,7 @@ SYMBOLS = {
     "hexb_set_opponent_buffers": (_i32, [_vp, _vp, _vp]),
     "hexb_set_info_buffers": (_i32, [_vp, _vp, _vp]),
     "hexb_set_eval": (_i32, [_vp, _i32, _vp, _vp]),
+    "hexb_set_opponent_eps": (_i32, [_vp, ctypes.c_double]),
     "hexb_half_step": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "hexb_masked_sample": (_i32, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp, _vp, _vp, _i32, _vp]),
 }

@@ -369,6 +369,13 @@ class HexBatch(object):
             check(self._lib.hexb_set_eval(self._h, int(bool(eval_state)), _ptr(self.eval_episode), self._stream()))
         self.cfg.eval_state = int(bool(eval_state))
 
+    def set_opponent_eps(self, eps):
+        """Variant-A HexEnv(opponent_policy="opponent_predict", eps=...) (HexGame.py:354-359) on a manual_opponent batch: every
+        opponent half step first draws rv from the game's stream and lets random_policy move when rv < eps, else plays the
+        caller's action (the model's prediction on encode(1)). eps=None or negative: the caller's action always."""
+        check(self._lib.hexb_set_opponent_eps(self._h, -1.0 if eps is None else float(eps)))
+        self.opponent_eps = None if eps is None or eps < 0 else float(eps)
+
     @property
     def eval_state(self):
         return bool(self.cfg.eval_state)

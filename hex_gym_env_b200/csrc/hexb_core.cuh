@@ -113,6 +113,8 @@ struct Params {
     int pool_size;        // setup_opponents: size of the opponent pool the index is drawn from
     int32_t *opp_index;   // [G] nullable: opponent chosen at reset, -1 = best model, k = pool entry (SelfplayWrapper.py:97-103)
     int32_t *eval_episode;  // [G] nullable: episodes started since SelfPlayEnv.set_eval (hexb_set_eval; SelfplayWrapper.py:93-95)
+    double opp_eps;       // MODE_HALF, variant A, side 1 with caller actions: HexEnv.eps of opponent_predict (HexGame.py:354-359): one draw
+                          // rv per opponent ply, rv < eps -> random_policy moves instead of the caller's action; < 0 = off
     uint8_t *to_move;     // [G] MODE_HALF / MODE_RESET out: 0 agent to move, 1 opponent to move, 2 finished
     int32_t *info_opp;    // [G] nullable, MODE_STEP out: the opponent's move of this step (info["last_move_opponent"]), -1 = none
     int8_t *info_winner;  // [G] nullable, MODE_STEP out: env.winner after the step: -1 None, 0 BLACK, 1 WHITE, 3 illegal move

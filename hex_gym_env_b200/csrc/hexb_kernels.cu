@@ -249,7 +249,7 @@ extern "C" HEXB_LOCAL void hexb_hostpack_finish(int abort);
 
 extern "C" {
 
-int32_t hexb_version(void) { return (1 << 16) | 4; }   // 1.3: obs_dtype, launch forms, hexb_gae, packed / asynchronous host step (+ hexb_mem_alloc: additive); 1.4: hexb_set_eval
+int32_t hexb_version(void) { return (1 << 16) | 4; }   // 1.3: obs_dtype, launch forms, hexb_gae, packed / asynchronous host step (+ hexb_mem_alloc: additive); 1.4: hexb_set_eval, hexb_set_opponent_eps
 
 const char *hexb_strerror(int32_t code) {
     switch (code) {
@@ -293,6 +293,7 @@ int32_t hexb_create(const hexb_config *cfg, void *state, size_t state_bytes, voi
     P.manual_opponent = cfg->manual_opponent;
     P.pool_size = cfg->pool_size;
     P.obs_f32 = cfg->obs_dtype == HEXB_OBS_F32 ? 1 : 0;
+    P.opp_eps = -1.0;
     P.one = 1u;
     {   // L2 policy of the chunk copies (see l2_policy): when the packed state is too large to live in L2 anyway, keep a fixed
         // 20 MiB of it there across steps and stream the rest. Measured on 11x11: 1 Mi games 99.4 -> 93.0 us per step,
@@ -373,6 +374,12 @@ int32_t hexb_set_eval(hexb_env *env, int32_t eval_state, int32_t *eval_episode, 
     }
     env->cfg.eval_state = env->base.eval_state = eval_state ? 1 : 0;
     env->base.eval_episode = eval_episode;
+    return HEXB_OK;
+}
+
+int32_t hexb_set_opponent_eps(hexb_env *env, double eps) {
+    if (!env || env->cfg.variant != HEXB_VARIANT_A || !env->cfg.manual_opponent || !(eps == eps)) return HEXB_ERR_ARG;
+    env->base.opp_eps = eps < 0.0 ? -1.0 : eps;
     return HEXB_OK;
 }
 

@@ -244,7 +244,12 @@ HEXB_HD void game_half(uint8_t *L, const Params &P, long long g, Rec<N> &rec, Lo
     if (!was_done && my_turn) {
         if (side != 0 && P.variant == VARIANT_B) rec.draws++;           // rv = random.uniform(0,1), unused (SelfplayWrapper.py:159)
         int a;
-        if (P.actions) a = P.actions[g];
+        bool from_caller = P.actions != nullptr;
+        if (from_caller && side != 0 && P.variant == VARIANT_A && P.opp_eps >= 0.0) {
+            // HexEnv.opponent_predict (HexGame.py:354-359): rv = random.uniform(0,1); rv < eps -> random_policy(state), else the model
+            from_caller = !(draw01(P.seed, gid, rec.draws++) < P.opp_eps);
+        }
+        if (from_caller) a = P.actions[g];
         else {  // the built-in random opponent (BaseRandomPolicy / random_policy): k-th empty cell of ITS view
             const double u = draw01(P.seed, gid, rec.draws++);
             int x;

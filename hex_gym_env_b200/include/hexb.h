@@ -251,6 +251,13 @@ int32_t hexb_set_opponent_buffers(hexb_env *env, int32_t *opp_index, uint8_t *to
  * pool entry k: opp_index = k while k <= pool_size - 1, later episodes keep the opponent they have (setup_opponents :92-96).
  * The running episode is not touched. Variant B handles only. */
 int32_t hexb_set_eval(hexb_env *env, int32_t eval_state, int32_t *eval_episode, void *stream);
+
+/* Variant-A HexEnv(opponent_policy="opponent_predict", opponent_model=..., eps=...) (HexGame.py:165-167,180,354-359; what
+ * scripts/selfplay.py:38-44 creates through gym.make("hex-v0", ...)) for a manual_opponent=1 variant-A handle: from now on every
+ * opponent ply of hexb_half_step(side 1, actions) first takes one draw rv from the game's stream (random.uniform(0,1)); with
+ * rv < eps random_policy moves (one more draw, minihex/__init__.py:8-12), otherwise the caller's action - the model's prediction on
+ * the view hexb_encode(view 1) shows - is played. eps < 0 switches the mix off again (the caller's action always, no draw). */
+int32_t hexb_set_opponent_eps(hexb_env *env, double eps);
 int32_t hexb_half_step(hexb_env *env, int32_t side, const int32_t *actions, float *reward, uint8_t *done, void *term_obs,
                        void *stream);
 

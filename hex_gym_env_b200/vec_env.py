@@ -15,6 +15,8 @@ this contract is duck-typed; if gymnasium / SB3 are importable the spaces are re
 Learned opponents: base_model= / buffer_size= / scores= as in selfplay_wrapper(HexEnv)(...) give every game the reference's opponent
 buffer (one OpponentPool, opponents.py); its API (set_eval, get_scores, set_opponent_model, ...) is reachable on the env and
 through env_method, which is what SelfPlayCallback (minihex/EvaluationCallback.py) calls on its gym_env.
+variant="hex-v0" with opponent_model= / eps=: gym.make("hex-v0", opponent_policy="opponent_predict", opponent_model=..., eps=...)
+(scripts/selfplay.py:38-44) for every game - a batched policy on the opponent's view, random_policy with probability eps.
 
 `output="numpy"` (default, what SB3 expects) copies results to host arrays; `output="torch"` returns device tensors and
 never touches the host (use it when the policy lives on the same GPU; `infos` is then a lazy object, not a list).
@@ -79,7 +81,7 @@ except Exception:  # pragma: no cover - SB3 is absent in the build image
 class HexVecEnv(_VecEnvBase):
     def __init__(self, board_size=5, num_envs=1024, variant="selfplay", agent_player_num=None, opponent_first=False,
                  seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0, sample_board=False,
-                 base_model=None, buffer_size=20, scores=None):
+                 base_model=None, buffer_size=20, scores=None, opponent_model=None, eps=0.5):
         if variant in ("selfplay", "B", VARIANT_B):
             v = VARIANT_B
             agent_mode = AGENT_RANDOM if agent_player_num is None else (AGENT_WHITE if int(agent_player_num) else AGENT_BLACK)
@@ -100,14 +102,22 @@ class HexVecEnv(_VecEnvBase):
         # (SelfplayWrapper.py:39-67): a batched policy (see opponents.py) fills the pool; the split step plays its entries.
         if base_model is not None and (v != VARIANT_B or sample_board):
             raise ValueError("base_model (an opponent pool) belongs to the SelfPlayEnv variant without sample_board")
+        # opponent_model / eps: gym.make("hex-v0", opponent_policy="opponent_predict", opponent_model=..., eps=...) for every game
+        # (HexGame.py:165-167,354-359; scripts/selfplay.py:38-44): a batched policy answers on the opponent's view, and with
+        # probability eps - drawn from the game's own stream on the device - random_policy moves instead.
+        if opponent_model is not None and v != VARIANT_A:
+            raise ValueError("opponent_model / eps (opponent_predict) belong to the 'hex-v0' variant; SelfPlayEnv takes base_model")
         self.batch = HexBatch(board_size, num_envs, variant=v, device=device, seed=seed, game_offset=game_offset,
                               agent_mode=agent_mode, opponent_first=opponent_first, auto_reset=True,
-                              manual_opponent=self.sample_board or base_model is not None,
+                              manual_opponent=self.sample_board or base_model is not None or opponent_model is not None,
                               pool_size=int(buffer_size) if base_model is not None else 0)
         self.pool = None
         if base_model is not None:
             from .opponents import OpponentPool
             self.pool = OpponentPool(base_model, buffer_size=int(buffer_size), scores=scores, batch=self.batch)
+        self.opponent_model, self.eps = opponent_model, (float(eps) if opponent_model is not None else None)
+        if opponent_model is not None:
+            self.batch.set_opponent_eps(self.eps)
         self.device = self.batch.device
         self._bgen = torch.Generator(device=self.device)
         self._bgen.manual_seed(int(seed) + 0x5EED)
@@ -159,8 +169,8 @@ class HexVecEnv(_VecEnvBase):
             self._restart_on_sampled_boards()
             self.batch.opponent_catch_up()      # SelfPlayEnv.reset -> continue_game where the opponent moves first
             obs, mask = self.batch.encode(0)
-        elif self.pool is not None:
-            self.batch.opponent_opening(self.pool)   # the chosen pool entry opens where the agent is WHITE (:79-80)
+        elif self._opponent_fn() is not None:
+            self.batch.opponent_opening(self._opponent_fn())   # the opponent opens where it moves first (:79-80, HexGame.py:224-230)
             obs, mask = self.batch.encode(0)
         self._mask = mask
         return self._obs_out(obs)
@@ -189,9 +199,8 @@ class HexVecEnv(_VecEnvBase):
     def step_wait(self):
         if self.sample_board:
             o = self._step_sampled(self._actions)
-        elif self.pool is not None:
-            self.batch._buf("sw_term", (self.batch.G, self.batch.N, self.batch.N), self.batch.obs_dtype)
-            o = self.batch.step_with_opponent(self._actions, self.pool, want_term=True)
+        elif self._opponent_fn() is not None:
+            o = self.batch.step_with_opponent(self._actions, self._opponent_fn(), want_term=True)
         else:
             o = self.batch.step(self._actions, want_term=True)
         self._mask = o["mask"]
@@ -227,6 +236,26 @@ class HexVecEnv(_VecEnvBase):
                  "get_best_mean_reward", "save_best_model")
     _POOL_ATTRS = ("opponent_models", "opponent_scores", "best_model", "best_score", "best_mean_reward", "eval_state")
 
+    def _opponent_fn(self):
+        """The caller-driven opponent of the split step: the pool (variant B) or the one opponent_predict model (variant A)."""
+        if self.pool is not None:
+            return self.pool
+        if self.opponent_model is not None:
+            return self._single_opponent
+        return None
+
+    def _single_opponent(self, obs, mask, to_move, opp_index):
+        return self.opponent_model(obs, mask)
+
+    def set_opponent_model(self, *args, **kwargs):
+        """SelfPlayEnv.set_opponent_model(index, model, score) (SelfplayWrapper.py:125-136) with a pool; variant A:
+        HexEnv.set_opponent_model(model) (HexGame.py:351-352)."""
+        if self.pool is not None:
+            return self.pool.set_opponent_model(*args, **kwargs)
+        if self.opponent_model is None:
+            raise AttributeError("set_opponent_model needs learned opponents: create the HexVecEnv with base_model= or opponent_model=")
+        (self.opponent_model,) = args
+
     def __getattr__(self, name):
         if name in HexVecEnv._POOL_API or name in HexVecEnv._POOL_ATTRS:
             pool = self.__dict__.get("pool")
@@ -240,6 +269,9 @@ class HexVecEnv(_VecEnvBase):
         if method_name in ("action_masks", "legal_actions", "get_action_mask"):
             m = self.action_masks()
             return [m[i] for i in idx]
+        if method_name == "set_opponent_model" and (self.pool is not None or self.opponent_model is not None):
+            r = self.set_opponent_model(*args, **kwargs)
+            return [r for _ in idx]
         if method_name in HexVecEnv._POOL_API and self.pool is not None:
             r = getattr(self.pool, method_name)(*args, **kwargs)     # one pool for all games: called once
             return [r for _ in idx]

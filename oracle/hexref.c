@@ -262,6 +262,7 @@ typedef struct {
     int manual;         /* the opponent's moves come from the caller (an OpponentPolicy, SelfplayWrapper.py:26-35): resets do not open */
     int pool_size;      /* len(self.opponent_models) */
     int opp_index;      /* opponent chosen by setup_opponents: -1 = best_model, k = opponent_models[k] */
+    double opp_eps;     /* variant A, caller-driven opponent: HexEnv.eps of opponent_predict (HexGame.py:354-359); < 0 = plain caller moves */
     int last_opp;       /* the opponent's latest move as HexEnv reports it (A: true cell, HexGame.py:341-348; B: its own view) */
     int info_opp, info_winner; /* info["last_move_opponent"], env.winner at the end of the latest step() (before an auto-reset) */
 } env_t;
@@ -386,6 +387,7 @@ void *hexref_batch_create(int kind, int N, int64_t G, uint64_t seed, int64_t gam
         e->g.N = N;
         e->rng.seed = seed; e->rng.game = (uint64_t)(game_offset + i); e->rng.idx = 0; e->rng.inject = NULL;
         e->eval_state = eval_state;
+        e->opp_eps = -1.0;
         e->env_winner = NONE;
         if (kind == 0) { e->agent = BLACK; e->start_player = opponent_first ? WHITE : BLACK; }
         else if (kind == 1) { e->agent = agent_mode == 2 ? -1 : agent_mode; }
@@ -498,7 +500,13 @@ void hexref_batch_step(void *h, const int32_t *actions, const double *opp_u, int
 /* Caller-driven opponent: the env with an OpponentPolicy whose actions arrive from outside. */
 void hexref_batch_set_manual(void *h, int pool_size) {
     batch_t *b = (batch_t *)h;
-    for (int64_t i = 0; i < b->G; ++i) { b->envs[i].manual = 1; b->envs[i].pool_size = pool_size; b->envs[i].opp_index = -1; }
+    for (int64_t i = 0; i < b->G; ++i) { b->envs[i].manual = 1; b->envs[i].pool_size = pool_size; b->envs[i].opp_index = -1; b->envs[i].opp_eps = -1.0; }
+}
+
+/* HexEnv(opponent_policy="opponent_predict", eps=...) HexGame.py:165-167,180: the opponent's half steps mix random_policy in */
+void hexref_batch_set_opponent_eps(void *h, double eps) {
+    batch_t *b = (batch_t *)h;
+    for (int64_t i = 0; i < b->G; ++i) b->envs[i].opp_eps = eps;
 }
 
 /* SelfPlayEnv.set_eval SelfplayWrapper.py:117-120: eval_episode = 0, eval_state = the argument; the running episode goes on */
@@ -526,7 +534,13 @@ void hexref_batch_half_step(void *h, int side, const int32_t *actions, int auto_
             if (side == 0) e->st[6]++;
             if (side == 1 && e->kind == 1) (void)rng_uniform01(&e->rng);   /* continue_game's unused draw (:159) */
             int a;
-            if (actions) a = actions[i];
+            int from_caller = actions != NULL;
+            if (from_caller && side == 1 && e->kind == 0 && e->opp_eps >= 0.0) {
+                /* HexEnv.opponent_predict HexGame.py:354-359: rv = random.uniform(0,1); rv < eps -> random_policy(state), else the model */
+                double rv = rng_uniform01(&e->rng);
+                if (rv < e->opp_eps) from_caller = 0;
+            }
+            if (from_caller) a = actions[i];
             else if (e->kind == 1) a = random_choice(&e->g, rng_random(&e->rng));   /* BaseRandomPolicy on the mover's view */
             else {                                                                   /* random_policy on the inverted board */
                 invert_board(&e->g);
@@ -585,6 +599,21 @@ void hexref_batch_observe(void *h, int8_t *obs, uint8_t *mask) {
     batch_t *b = (batch_t *)h;
     const int C = b->N * b->N;
     for (int64_t i = 0; i < b->G; ++i) emit_obs_mask(&b->envs[i], obs ? obs + i * C : NULL, mask ? mask + i * C : NULL);
+}
+
+/* The board and mask the OPPONENT's policy is shown when it is to move (what hexb_encode(view 1) emits): variant B = the live board
+ * (already the mover's view); variant A = the board between the two invert_board calls of HexEnv.opponent_move (HexGame.py:333-339:
+ * transposed, colours swapped) and get_action_mask of that array (:358). Games with the agent to move: the live board. */
+void hexref_batch_observe_opponent(void *h, int8_t *obs, uint8_t *mask) {
+    batch_t *b = (batch_t *)h;
+    const int C = b->N * b->N;
+    for (int64_t i = 0; i < b->G; ++i) {
+        env_t *e = &b->envs[i];
+        const int inv = e->kind == 0 && !e->g.done && !agent_to_move(e);
+        if (inv) invert_board(&e->g);
+        emit_obs_mask(e, obs ? obs + i * C : NULL, mask ? mask + i * C : NULL);
+        if (inv) invert_board(&e->g);
+    }
 }
 
 /* Batched HexGame.make_move on raw games (kind 2 = A, kind 3 = B), or on the simulators inside envs. */

@@ -45,8 +45,10 @@ def lib():
         L.hexref_set_threads.argtypes = [i32]
         L.hexref_batch_set_manual.argtypes = [vp, i32]
         L.hexref_batch_set_eval.argtypes = [vp, i32]
+        L.hexref_batch_set_opponent_eps.argtypes = [vp, ctypes.c_double]
         L.hexref_batch_half_step.argtypes = [vp, i32, vp, i32] + [vp] * 5
         L.hexref_batch_observe.argtypes = [vp, vp, vp]
+        L.hexref_batch_observe_opponent.argtypes = [vp, vp, vp]
         L.hexref_batch_opp_state.argtypes = [vp, vp, vp]
         L.hexref_batch_info.argtypes = [vp, vp, vp]
         L.hexref_batch_env_set_board.argtypes = [vp, vp, vp]
@@ -109,6 +111,9 @@ class RefBatch(object):
     def set_manual_opponent(self, pool_size=0):
         lib().hexref_batch_set_manual(self._h, pool_size)
 
+    def set_opponent_eps(self, eps):
+        lib().hexref_batch_set_opponent_eps(self._h, float(eps))
+
     def set_eval(self, eval_state):
         lib().hexref_batch_set_eval(self._h, int(bool(eval_state)))
 
@@ -138,7 +143,10 @@ class RefBatch(object):
         return to_move, opp_index
 
     def view1(self):
-        return self.observe()
+        obs = np.empty((self.G, self.N, self.N), np.int8)
+        mask = np.empty((self.G, self.C), np.uint8)
+        lib().hexref_batch_observe_opponent(self._h, _p(obs), _p(mask))
+        return obs, mask
 
     def observe(self):
         obs = np.empty((self.G, self.N, self.N), np.int8)

@@ -41,6 +41,7 @@ def lib():
         L.emu_set_manual_opponent.argtypes = [vp, i32, vp, vp]
         L.emu_half_step.argtypes = [vp, i32, vp, vp, vp, vp]
         L.emu_set_eval.argtypes = [vp, i32, vp, i64]
+        L.emu_set_opponent_eps.argtypes = [vp, ctypes.c_double]
         L.emu_set_info.argtypes = [vp, vp, vp]
         L.emu_rollout.argtypes = [vp, i32] + [vp] * 6
         L.emu_force_sweep.argtypes = [i32]
@@ -75,6 +76,9 @@ class EmuBatch(object):
             self.opp_index = np.full(num_games, -1, np.int32)
             self.to_move = np.full(num_games, 9, np.uint8)
             lib().emu_set_manual_opponent(self._h, pool_size, _p(self.opp_index), _p(self.to_move))
+
+    def set_opponent_eps(self, eps):
+        lib().emu_set_opponent_eps(self._h, float(eps))
 
     def set_eval(self, eval_state):
         if getattr(self, "eval_episode", None) is None:

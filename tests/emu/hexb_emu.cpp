@@ -171,7 +171,7 @@ void *emu_create(int N, int variant, long long G, long long game_offset, unsigne
     P.stats = (long long *)(base + stats_off);
     P.G = G; P.Gpad = Gpad; P.game_offset = game_offset; P.seed = seed;
     P.variant = variant; P.auto_reset = auto_reset; P.eval_state = eval_state; P.opponent_first = opponent_first;
-    P.agent_mode = agent_mode; P.raw = raw; P.one = 1u;
+    P.agent_mode = agent_mode; P.raw = raw; P.one = 1u; P.opp_eps = -1.0;
     return e;
 }
 void emu_destroy(void *h) { delete (emu_env *)h; }
@@ -186,6 +186,7 @@ void emu_set_eval(void *h, int eval_state, int32_t *eval_episode, long long G) {
     e->base.eval_episode = eval_episode;
     if (eval_episode) memset(eval_episode, 0, sizeof(int32_t) * (size_t)G);
 }
+void emu_set_opponent_eps(void *h, double eps) { ((emu_env *)h)->base.opp_eps = eps < 0.0 ? -1.0 : eps; }   // hexb_set_opponent_eps
 void emu_set_info(void *h, int32_t *opp, int8_t *winner) {
     emu_env *e = (emu_env *)h;
     e->base.info_opp = opp; e->base.info_winner = winner;

@@ -60,6 +60,9 @@ class GpuBatch(object):
     def set_eval(self, eval_state):
         self.b.set_eval(eval_state)
 
+    def set_opponent_eps(self, eps):
+        self.b.set_opponent_eps(eps)
+
     def view1(self):
         return self.encode(1)
 

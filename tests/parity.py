@@ -465,3 +465,59 @@ def golden_preset_resets(make_raw, name):
         e = env.export()
         eq(e["regions"][ok], z["moved_regions_" + variant][ok].astype(np.float64), "%s %s regions after a move" % (name, variant))
         eq(e["region_counter"][ok], z["moved_counter_" + variant][ok].astype(np.float64), "%s %s counter after a move" % (name, variant))
+
+
+def golden_oppredict_batched(make, name):
+    """Variant-A HexEnv(opponent_policy="opponent_predict", opponent_model=..., eps=...) for a whole batch (hexb_set_opponent_eps +
+    hexb_half_step) against the reference run one env per game (oppredict_*.npz: HexGame.py:165-167,354-359; the batched form of
+    what scripts/selfplay.py:38-44 builds with gym.make("hex-v0", ...)). The scripted model answers for EVERY waiting game from the
+    implementation's own opponent view; the implementation's draw from the game's stream decides whether random_policy moves instead.
+    Pins: the draw order (rv, then random_policy's draw), the board and mask the model is shown, rewards, restarts with the opponent
+    opening, the region planes."""
+    from oracle.scripted import scripted_choice_a
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, eps, of = int(z["N"]), int(z["seed"]), float(z["eps"]), int(z["opponent_first"])
+    T, G = z["actions"].shape
+    env = make(hexref.KIND_ENV_A, N, G, seed=seed, opponent_first=bool(of), manual_opponent=True)
+    env.set_opponent_eps(eps)
+    env.reset()
+
+    def opponent_pass(model_calls=None, t=None):
+        tm, _ = env.opp_state()
+        obs1, mask1 = env.view1()
+        acts = np.zeros(G, np.int32)
+        for g in np.flatnonzero(tm == 1):
+            acts[g] = scripted_choice_a(obs1[g], mask1[g])
+            if model_calls is not None and model_calls[g]:   # the reference's model was asked in this step: same board, mask, answer
+                assert np.array_equal(obs1[g], z["model_board"][t, g]), (name, t, g, "board shown to the model")
+                assert np.array_equal(mask1[g], z["model_mask"][t, g]), (name, t, g, "mask shown to the model")
+                assert acts[g] == z["model_action"][t, g], (name, t, g)
+        return env.half_step(1, acts, want_term=True), tm == 1
+
+    _, opened = opponent_pass()
+    eq(opened, np.full(G, bool(of)), name + " who opens")
+    obs, _ = env.view1()                                         # (every game is back at the agent: its view)
+    eq(obs, z["obs0"], name + " obs0")
+    eq(env.export()["draws"], z["draws0"], name + " draws0")
+    for t in range(T):
+        w = "%s t=%d " % (name, t)
+        h = env.half_step(0, z["actions"][t], want_term=True)
+        reward, done = h["reward"].copy(), h["done"].astype(bool)
+        h, replied = opponent_pass(z["model_calls"][t], t)       # the reply to the agent's ply
+        assert not (z["model_calls"][t].astype(bool) & ~replied).any(), w + "a model call without a reply"
+        reward += h["reward"]
+        done |= h["done"].astype(bool)
+        h, _ = opponent_pass()                                   # the opening move of a game that restarted (opponent_first)
+        assert not h["done"].any(), w + "an opening move cannot end a game"
+        tm, _ = env.opp_state()
+        assert (tm == 0).all(), w + "every game back at the agent"
+        eq(reward, z["reward"][t], w + "reward")
+        eq(done, z["done"][t].astype(bool), w + "done")
+        obs, mask = env.view1()
+        eq(obs, z["obs"][t], w + "obs")
+        eq(mask, (z["obs"][t].reshape(G, -1) == 2).astype(np.uint8), w + "mask")
+        e = env.export()
+        eq(e["draws"], z["draws"][t], w + "draws")
+        live = ~done                                             # the fixture's planes are those before the restart
+        eq(e["regions"][live], z["regions"][t][live].astype(np.float64), w + "regions")
+        eq(e["region_counter"][live], z["counter"][t][live].astype(np.float64), w + "counter")

@@ -179,3 +179,9 @@ def test_word_encode_matches_byte_definition():
                     L.emu_encode_word(x, variant, ctypes.byref(o), ctypes.byref(m))
                     for k, v in enumerate(bytes_):
                         assert ((o.value >> (8 * k)) & 0xff, (m.value >> (8 * k)) & 0xff) == table[v], (variant, hex(x), k)
+
+
+@pytest.mark.parametrize("name", golden_files("oppredict_"))
+def test_opponent_predict_batched(name):
+    """hexb_set_opponent_eps + hexb_half_step (variant A, HexEnv.opponent_predict for a batch) in the device code."""
+    parity.golden_oppredict_batched(make, name)

@@ -222,3 +222,40 @@ def test_stacked_pool_samples_and_lives_in_the_rollout_graph():
     assert st[0] > 0 and st[5] == 0                  # episodes finished, none by an illegal agent move
     buf = col.buf
     assert bool(torch.isfinite(buf.advantages).all()) and bool((buf.action_masks[:-1].gather(2, buf.actions.long().unsqueeze(2)) == 1).all())
+
+
+class ScriptedA(object):
+    """oracle/scripted.py::ScriptedModelA's rule as a batched policy for the variant-A opponent view (a host-side test double)."""
+
+    def __call__(self, obs, mask):
+        from oracle.scripted import scripted_choice_a
+        o, m = obs.cpu().numpy(), mask.cpu().numpy()
+        return torch.tensor([scripted_choice_a(o[g], m[g]) if m[g].any() else 0 for g in range(len(o))], dtype=torch.int32, device=obs.device)
+
+
+@pytest.mark.parametrize("name", golden_files("oppredict_"))
+def test_vec_env_hex_v0_with_opponent_predict_against_the_reference(name):
+    """HexVecEnv(variant="hex-v0", opponent_model=..., eps=...) = gym.make("hex-v0", opponent_policy="opponent_predict", ...) for
+    every game (scripts/selfplay.py:38-44), against the unmodified reference run one env per game."""
+    from hex_gym_env_b200.vec_env import HexVecEnv
+    z = np.load(os.path.join(GOLDEN, name))
+    N, seed, eps, of = int(z["N"]), int(z["seed"]), float(z["eps"]), int(z["opponent_first"])
+    T, G = z["actions"].shape
+    env = HexVecEnv(board_size=N, num_envs=G, variant="hex-v0", seed=seed, opponent_first=bool(of), opponent_model=ScriptedA(),
+                    eps=eps, device=0)
+    obs = env.reset()
+    assert np.array_equal(obs, z["obs0"].astype(np.float32))
+    for t in range(T):
+        obs, rew, done, infos = env.step(z["actions"][t])
+        w = "%s t=%d" % (name, t)
+        assert np.array_equal(done, z["done"][t].astype(bool)), w
+        assert np.array_equal(rew, z["reward"][t]), w
+        assert np.array_equal(obs, z["obs"][t].astype(np.float32)), w
+        assert np.array_equal(env.action_masks(), z["obs"][t].reshape(G, -1) == 2), w
+    assert np.array_equal(env.batch.export_state()["draws"].cpu().numpy().astype(np.uint32), z["draws"][T - 1])
+    other = ScriptedA()
+    env.env_method("set_opponent_model", other)
+    assert env.opponent_model is other
+    with pytest.raises(ValueError):
+        HexVecEnv(board_size=4, num_envs=8, opponent_model=ScriptedA(), device=0)     # SelfPlayEnv takes base_model instead
+    env.close()

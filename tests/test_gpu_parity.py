@@ -162,19 +162,17 @@ def test_half_step_vs_oracle(make, N, variant_kind):
                 parity.eq(tm, rtm, "to_move t=%d" % t)
                 parity.eq(idx, ridx, "opp_index t=%d" % t)
                 obs1, mask1 = env.view1()
-                if variant_kind == hexref.KIND_SELFPLAY_B:
-                    robs1, rmask1 = ref.view1()
-                    live = tm != 2
-                    parity.eq(obs1[live], robs1[live], "side-to-move obs t=%d" % t)
-                    parity.eq(mask1[live], rmask1[live], "side-to-move mask t=%d" % t)
-                else:   # variant A: the oracle keeps the true board; the opponent sees it transposed with colours swapped
-                    robs1, rmask1 = ref.view1()
+                # (variant A: the opponent sees the board transposed with the colours swapped, HexGame.py:333-339 - the oracle's
+                # view1 applies the reference's own invert_board; checked here independently of it as well)
+                robs1, rmask1 = ref.view1()
+                live = tm != 2
+                parity.eq(obs1[live], robs1[live], "side-to-move obs t=%d" % t)
+                parity.eq(mask1[live], rmask1[live], "side-to-move mask t=%d" % t)
+                if variant_kind == hexref.KIND_ENV_A:
+                    true_board = ref.observe()[0]
                     oppv = tm == 1
-                    robs1[oppv] = np.where(robs1[oppv] == 2, 2, 1 - robs1[oppv]).transpose(0, 2, 1)
-                    rmask1[oppv] = rmask1[oppv].reshape(-1, N, N).transpose(0, 2, 1).reshape(-1, C)
-                    live = tm != 2
-                    parity.eq(obs1[live], robs1[live], "side-to-move obs (A) t=%d" % t)
-                    parity.eq(mask1[live], rmask1[live], "side-to-move mask (A) t=%d" % t)
+                    want = np.where(true_board[oppv] == 2, 2, 1 - true_board[oppv]).transpose(0, 2, 1)
+                    parity.eq(obs1[oppv], want, "opponent view (A) t=%d" % t)
                 cnt = np.maximum(mask1.sum(1), 1)
                 k = (rs.rand(G) * cnt).astype(np.int64)
                 acts = np.argsort(-mask1.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
@@ -418,3 +416,10 @@ def test_golden_preset_resets(name):
     """hexb_import_labels: HexGame.__init__ with connected_stones (the cached planes of HexEnv.reset's later calls)."""
     from gpu_adapter import GpuBatch
     parity.golden_preset_resets(lambda kind, N, G: GpuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True), name)
+
+
+@pytest.mark.parametrize("name", golden_files("oppredict_"))
+def test_opponent_predict_batched(make, name):
+    """hexb_set_opponent_eps + hexb_half_step: variant-A HexEnv(opponent_policy="opponent_predict", eps=...) for a batch against the
+    unmodified reference run one env per game."""
+    parity.golden_oppredict_batched(make, name)

@@ -167,3 +167,10 @@ def test_preset_resets(name):
         e = b.export()
         assert np.array_equal(e["regions"][ok], z["moved_regions_" + variant][ok].astype(np.float64))
         assert np.array_equal(e["region_counter"][ok], z["moved_counter_" + variant][ok].astype(np.float64))
+
+
+@pytest.mark.parametrize("name", golden_files("oppredict_"))
+def test_opponent_predict_batched(name):
+    """Variant A with a caller-driven, eps-mixed opponent (HexEnv.opponent_predict) in the oracle against the reference's run."""
+    import parity
+    parity.golden_oppredict_batched(lambda kind, N, G, **kw: hexref.RefBatch(kind, N, G, **kw), name)
