@@ -81,7 +81,7 @@ except Exception:  # pragma: no cover - SB3 is absent in the build image
 class HexVecEnv(_VecEnvBase):
     def __init__(self, board_size=5, num_envs=1024, variant="selfplay", agent_player_num=None, opponent_first=False,
                  seed=0, device=None, output="numpy", obs_dtype=None, game_offset=0, sample_board=False,
-                 base_model=None, buffer_size=20, scores=None, opponent_model=None, eps=0.5):
+                 base_model=None, buffer_size=20, scores=None, opponent_model=None, eps=0.5, info_fields=False):
         if variant in ("selfplay", "B", VARIANT_B):
             v = VARIANT_B
             agent_mode = AGENT_RANDOM if agent_player_num is None else (AGENT_WHITE if int(agent_player_num) else AGENT_BLACK)
@@ -115,6 +115,12 @@ class HexVecEnv(_VecEnvBase):
         if base_model is not None:
             from .opponents import OpponentPool
             self.pool = OpponentPool(base_model, buffer_size=int(buffer_size), scores=scores, batch=self.batch)
+        # info_fields: the info dict of variant-A HexEnv.step (HexGame.py:281-286) per env: last_move_opponent, last_move_player, winner
+        self.info_fields = bool(info_fields)
+        if self.info_fields:
+            if v != VARIANT_A or opponent_model is not None:
+                raise ValueError("info_fields is the info dict of the fused 'hex-v0' step (HexGame.py:281-286)")
+            self.batch.enable_info()
         self.opponent_model, self.eps = opponent_model, (float(eps) if opponent_model is not None else None)
         if opponent_model is not None:
             self.batch.set_opponent_eps(self.eps)
@@ -202,18 +208,29 @@ class HexVecEnv(_VecEnvBase):
         elif self._opponent_fn() is not None:
             o = self.batch.step_with_opponent(self._actions, self._opponent_fn(), want_term=True)
         else:
-            o = self.batch.step(self._actions, want_term=True)
+            o = self.batch.step(self._actions, want_term=True, want_actions=self.info_fields)
         self._mask = o["mask"]
         if self.output == "torch":
             infos = _LazyInfos(o["done"], o["term_obs"], self.num_envs)
+            if self.info_fields:   # device tensors, -1 = None (winner 3 = illegal move), overwritten by the next step
+                infos.last_move_opponent, infos.winner, infos.last_move_player = self.batch.last_move_opponent, self.batch.winner, o["actions"]
             return o["obs"].to(self.obs_dtype), o["reward"], o["done"].bool(), infos
-        h = {k: self._host(k, o[k]) for k in ("obs", "reward", "done", "term_obs")}
+        keys = ("obs", "reward", "done", "term_obs")
+        h = {k: self._host(k, o[k]) for k in keys}
+        if self.info_fields:
+            h.update(lmo=self._host("lmo", self.batch.last_move_opponent), win=self._host("win", self.batch.winner),
+                     lmp=self._host("lmp", o["actions"]))
         torch.cuda.current_stream(self.device).synchronize()
         done = h["done"].numpy().astype(bool)
         term = h["term_obs"].numpy()
-        infos = [{} for _ in range(self.num_envs)]
+        if self.info_fields:   # HexGame.py:281-286 ('state' is the observation itself)
+            lmo, win, lmp = h["lmo"].numpy(), h["win"].numpy(), h["lmp"].numpy()
+            infos = [{"last_move_opponent": None if lmo[i] < 0 else int(lmo[i]), "last_move_player": int(lmp[i]),
+                      "winner": None if win[i] < 0 else int(win[i])} for i in range(self.num_envs)]
+        else:
+            infos = [{} for _ in range(self.num_envs)]
         for i in np.flatnonzero(done):
-            infos[i] = {"terminal_observation": term[i].astype(self.obs_dtype), "TimeLimit.truncated": False}
+            infos[i].update({"terminal_observation": term[i].astype(self.obs_dtype), "TimeLimit.truncated": False})
         return h["obs"].numpy().astype(self.obs_dtype), h["reward"].numpy().copy(), done, infos
 
     def step(self, actions):

@@ -259,3 +259,42 @@ def test_vec_env_hex_v0_with_opponent_predict_against_the_reference(name):
     with pytest.raises(ValueError):
         HexVecEnv(board_size=4, num_envs=8, opponent_model=ScriptedA(), device=0)     # SelfPlayEnv takes base_model instead
     env.close()
+
+
+def test_vec_env_info_dict_of_hex_v0():
+    """HexVecEnv(variant="hex-v0", info_fields=True): infos carry last_move_opponent / last_move_player / winner of the reference's
+    info dict (HexGame.py:281-286), checked against the oracle's env-level bookkeeping on the same seeded run."""
+    from hex_gym_env_b200.vec_env import HexVecEnv
+    from oracle import hexref
+    N, G, T, seed = 5, 200, 40, 21
+    C = N * N
+    env = HexVecEnv(board_size=N, num_envs=G, variant="hex-v0", seed=seed, info_fields=True, device=0)
+    ref = hexref.RefBatch(hexref.KIND_ENV_A, N, G, seed=seed)
+    obs = env.reset()
+    robs, rmask = ref.reset()
+    assert np.array_equal(obs, robs.astype(np.float32))
+    rs = np.random.RandomState(4)
+    seen_win = seen_illegal = 0
+    for t in range(T):
+        mask = env.action_masks()
+        assert np.array_equal(mask, rmask.astype(bool))
+        k = (rs.rand(G) * np.maximum(mask.sum(1), 1)).astype(np.int64)
+        acts = np.argsort(-mask.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
+        bad = rs.rand(G) < 0.03
+        acts[bad] = rs.randint(0, C, size=int(bad.sum()))
+        obs, rew, done, infos = env.step(acts)
+        r = ref.step(acts, want_term=True)
+        fo, fw = ref.info()
+        assert np.array_equal(rew, r["reward"]) and np.array_equal(done, r["done"].astype(bool))
+        for i in range(G):
+            assert infos[i]["last_move_player"] == int(acts[i])
+            assert infos[i]["last_move_opponent"] == (None if fo[i] < 0 else int(fo[i])), (t, i)
+            assert infos[i]["winner"] == (None if fw[i] < 0 else int(fw[i])), (t, i)
+            assert ("terminal_observation" in infos[i]) == bool(done[i])
+        seen_win += int((fw >= 0).sum() - (fw == 3).sum())
+        seen_illegal += int((fw == 3).sum())
+        rmask = r["mask"]
+    assert seen_win > 0 and seen_illegal > 0
+    with pytest.raises(ValueError):
+        HexVecEnv(board_size=4, num_envs=8, info_fields=True, device=0)       # SelfPlayEnv's step returns an empty info dict
+    env.close()
