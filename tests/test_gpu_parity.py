@@ -154,8 +154,12 @@ def test_half_step_vs_oracle(make, N, variant_kind):
         env = make(variant_kind, N, G, seed=N, auto_reset=auto_reset, manual_opponent=True, pool_size=7, **kw)
         ref = hexref.RefBatch(variant_kind, N, G, seed=N, manual_opponent=True, pool_size=7, **kw)
         env.reset(); ref.reset()
+        if variant_kind == hexref.KIND_ENV_A:     # HexEnv.opponent_predict's eps mix: the draw decides who moves, on both sides alike
+            env.set_opponent_eps(0.35); ref.set_opponent_eps(0.35)
         rs = np.random.RandomState(N)
         for t in range(T):
+            if variant_kind == hexref.KIND_SELFPLAY_B and t in (T // 4, (2 * T) // 3):   # SelfPlayEnv.set_eval on, later off again
+                env.set_eval(t == T // 4); ref.set_eval(t == T // 4)
             for side in (1, 0, 1):
                 tm, idx = env.opp_state()
                 rtm, ridx = ref.opp_state()
