@@ -521,3 +521,51 @@ def golden_oppredict_batched(make, name):
         live = ~done                                             # the fixture's planes are those before the restart
         eq(e["regions"][live], z["regions"][t][live].astype(np.float64), w + "regions")
         eq(e["region_counter"][live], z["counter"][t][live].astype(np.float64), w + "counter")
+
+
+def opponent_modes_fuzz(make, kind, N, G, T, seed, pool=4):
+    """Split steps with random (mostly legal) moves of both sides against the oracle while the opponent modes change at random
+    moments: variant B - SelfPlayEnv.set_eval switched on / off (the evaluation cycle restarts from entry 0 at every call);
+    variant A - HexEnv.eps of opponent_predict re-set to a new value or switched off. Every half step: to_move, the pool entry,
+    reward, done, the terminal observation; the whole exported state every few steps."""
+    rs = np.random.RandomState(seed)
+    C = N * N
+    kw = dict(agent_mode=2) if kind == hexref.KIND_SELFPLAY_B else dict(opponent_first=bool(seed & 1))
+    env = make(kind, N, G, seed=seed, manual_opponent=True, pool_size=pool, **kw)
+    ref = hexref.RefBatch(kind, N, G, seed=seed, manual_opponent=True, pool_size=pool, **kw)
+    env.reset(); ref.reset()
+    switches = 0
+    for t in range(T):
+        if rs.rand() < 0.15:
+            switches += 1
+            if kind == hexref.KIND_SELFPLAY_B:
+                flag = bool(rs.randint(2))
+                env.set_eval(flag); ref.set_eval(flag)
+            else:
+                eps = -1.0 if rs.rand() < 0.3 else float(rs.choice([0.0, 0.25, 0.5, 1.0]))
+                env.set_opponent_eps(eps); ref.set_opponent_eps(eps)
+        for side in (1, 0, 1):
+            tm, idx = env.opp_state()
+            rtm, ridx = ref.opp_state()
+            eq(tm, rtm, "to_move t=%d side=%d" % (t, side))
+            eq(idx, ridx, "pool entry t=%d side=%d" % (t, side))
+            obs1, mask1 = env.view1()
+            robs1, rmask1 = ref.view1()
+            eq(obs1[tm != 2], robs1[tm != 2], "side-to-move obs t=%d side=%d" % (t, side))
+            cnt = np.maximum(mask1.sum(1), 1)
+            k = (rs.rand(G) * cnt).astype(np.int64)
+            acts = np.argsort(-mask1.astype(np.int8), axis=1, kind="stable")[np.arange(G), k].astype(np.int32)
+            bad = rs.rand(G) < 0.01
+            acts[bad] = rs.randint(-1, C + 1, size=int(bad.sum()))
+            o = env.half_step(side, acts, want_term=True)
+            r = ref.half_step(side, acts, want_term=True)
+            for key in ("reward", "done", "to_move", "opp_index"):
+                eq(o[key], r[key], "%s t=%d side=%d" % (key, t, side))
+            d = r["done"].astype(bool)
+            eq(o["term_obs"][d], r["term_obs"][d], "term_obs t=%d side=%d" % (t, side))
+        if t % 6 == 5 or t == T - 1:
+            e, re_ = env.export(), ref.export()
+            for key in ("regions", "region_counter", "cur", "done", "winner", "agent", "draws"):
+                eq(e[key], re_[key], "%s t=%d" % (key, t))
+    eq(env.stats(), ref.stats(), "stats")
+    assert switches > 0

@@ -185,3 +185,9 @@ def test_word_encode_matches_byte_definition():
 def test_opponent_predict_batched(name):
     """hexb_set_opponent_eps + hexb_half_step (variant A, HexEnv.opponent_predict for a batch) in the device code."""
     parity.golden_oppredict_batched(make, name)
+
+
+@pytest.mark.parametrize("kind,N,seed", [(hexref.KIND_SELFPLAY_B, 4, 1), (hexref.KIND_SELFPLAY_B, 5, 2), (hexref.KIND_SELFPLAY_B, 7, 3),
+                                         (hexref.KIND_ENV_A, 4, 4), (hexref.KIND_ENV_A, 5, 5), (hexref.KIND_ENV_A, 6, 6)])
+def test_opponent_modes_fuzz(kind, N, seed):
+    parity.opponent_modes_fuzz(make, kind, N, 200, 60, seed)

@@ -427,3 +427,10 @@ def test_opponent_predict_batched(make, name):
     """hexb_set_opponent_eps + hexb_half_step: variant-A HexEnv(opponent_policy="opponent_predict", eps=...) for a batch against the
     unmodified reference run one env per game."""
     parity.golden_oppredict_batched(make, name)
+
+
+@pytest.mark.parametrize("kind,N,seed", [(hexref.KIND_SELFPLAY_B, 5, 12), (hexref.KIND_SELFPLAY_B, 11, 13), (hexref.KIND_ENV_A, 4, 14),
+                                         (hexref.KIND_ENV_A, 7, 15)])
+def test_opponent_modes_fuzz(make, kind, N, seed):
+    """set_eval / the eps of opponent_predict switched at random moments of a random split-step run, GPU vs oracle."""
+    parity.opponent_modes_fuzz(make, kind, N, 600, 60, seed)
