@@ -34,26 +34,28 @@ struct Job {
 
 // ---- one worker's share: words [w0, w1) of the job
 void expand_scalar(const Job &j, long long w0, long long w1) {
-    // byte-wise LUT: 4 cells per packed byte
-    static uint32_t lut_obs[2][256], lut_msk[2][256];
-    static int ready = 0;
-    if (!__atomic_load_n(&ready, __ATOMIC_ACQUIRE)) {
-        for (int v = 0; v < 2; ++v)
-            for (int b = 0; b < 256; ++b) {
-                uint32_t o = 0, m = 0;
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t c = (b >> (2 * k)) & 3u;
-                    const uint32_t ob = v == 1 ? (c == 3u ? 0xffu : c) : c;          // variant B: code 3 is -1
-                    const uint32_t mk = v == 1 ? (c == 0u) : (c == 2u);              // legal == empty
-                    o |= ob << (8 * k);
-                    m |= mk << (8 * k);
+    // byte-wise LUT: 4 cells per packed byte; built once by whichever thread gets here first (a function-local static is
+    // initialised exactly once under the language's own guard, so no worker ever reads a table another one is still writing)
+    struct Lut {
+        uint32_t obs[2][256], msk[2][256];
+        Lut() {
+            for (int v = 0; v < 2; ++v)
+                for (int b = 0; b < 256; ++b) {
+                    uint32_t o = 0, m = 0;
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t c = (b >> (2 * k)) & 3u;
+                        const uint32_t ob = v == 1 ? (c == 3u ? 0xffu : c) : c;          // variant B: code 3 is -1
+                        const uint32_t mk = v == 1 ? (c == 0u) : (c == 2u);              // legal == empty
+                        o |= ob << (8 * k);
+                        m |= mk << (8 * k);
+                    }
+                    obs[v][b] = o;
+                    msk[v][b] = m;
                 }
-                lut_obs[v][b] = o;
-                lut_msk[v][b] = m;
-            }
-        __atomic_store_n(&ready, 1, __ATOMIC_RELEASE);   // racing initialisers write identical tables
-    }
-    const uint32_t *lo = lut_obs[j.variant ? 1 : 0], *lm = lut_msk[j.variant ? 1 : 0];
+        }
+    };
+    static const Lut lut;
+    const uint32_t *lo = lut.obs[j.variant ? 1 : 0], *lm = lut.msk[j.variant ? 1 : 0];
     for (long long w = w0; w < w1; ++w) {
         const uint32_t x = j.packed[w];
         const long long c0 = 16 * w;
