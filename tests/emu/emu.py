@@ -13,6 +13,8 @@ _LIB = None
 
 
 def build(force=False):
+    if os.environ.get("HEXB_EMU_LIB"):      # a prebuilt variant, e.g. the sanitizer build of tools/emu_sanitize.py
+        return os.environ["HEXB_EMU_LIB"]
     so = os.path.join(_HERE, "libhexb_emu.so")
     srcs = [os.path.join(_HERE, "hexb_emu.cpp")] + [os.path.join(_ROOT, "hex_gym_env_b200", "csrc", f)
                                                      for f in ("hexb_core.cuh", "hexb_phases.cuh", "hexb_views.cuh")]

