@@ -97,3 +97,17 @@ def test_missing_library_fails_loudly():
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, HEXB_LIB="/nonexistent/libhexb.so"),
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert out.returncode == 0 and "raised" in out.stdout, out.stderr
+
+
+def test_every_entry_point_rejects_a_null_handle(L):
+    """Every symbol of include/hexb.h that takes a hexb_env* answers HEXB_ERR_ARG for a null handle (no crash, nothing launched)."""
+    no_env = {"hexb_version", "hexb_strerror", "hexb_last_cuda_error", "hexb_state_bytes", "hexb_create", "hexb_host_workspace_bytes",
+              "hexb_host_packed_bytes", "hexb_host_threads", "hexb_mem_alloc", "hexb_mem_free", "hexb_masked_sample", "hexb_gae"}
+    called = 0
+    for name, (_res, args) in _native.SYMBOLS.items():
+        if name in no_env:
+            continue
+        vals = [0.0 if a is ctypes.c_double else (0 if a in (ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t) else None) for a in args]
+        assert getattr(L, name)(*vals) == -1, name
+        called += 1
+    assert called == len(_native.SYMBOLS) - len(no_env) and called >= 24
