@@ -111,3 +111,13 @@ def test_every_entry_point_rejects_a_null_handle(L):
         assert getattr(L, name)(*vals) == -1, name
         called += 1
     assert called == len(_native.SYMBOLS) - len(no_env) and called >= 24
+
+
+def test_handle_less_entry_points_check_their_arguments(L):
+    """hexb_masked_sample / hexb_gae without a handle: null buffers, empty or oversized shapes are HEXB_ERR_ARG before any launch."""
+    p = ctypes.c_void_p(8)
+    assert L.hexb_gae(None, None, None, 4, 10, 0.99, 0.95, None, None, 0, None) == -1
+    assert L.hexb_gae(p, p, p, 0, 10, 0.99, 0.95, p, None, 0, None) == -1 and L.hexb_gae(p, p, p, 4, 0, 0.99, 0.95, p, None, 0, None) == -1
+    assert L.hexb_masked_sample(None, None, None, 10, 9, None, None, None, 0, None) == -1
+    for G, C in ((10, 0), (10, 400), (0, 9)):
+        assert L.hexb_masked_sample(p, p, p, G, C, None, None, None, 0, None) == -1, (G, C)
