@@ -65,3 +65,17 @@ def test_batched_opponent_predict_on_fresh_seeds(gg, tmp_path, monkeypatch, make
     monkeypatch.setattr(gg, "OUT", str(tmp_path))
     gg.gen_opponent_predict(N, G, T, seed=seed, eps=eps, opponent_first=of)
     parity.golden_oppredict_batched(make, str(tmp_path / ("oppredict_N%d_of%d.npz" % (N, int(of)))))
+
+
+@pytest.mark.parametrize("variant,N,n,seed", [("A", 4, 6, 90041), ("A", 8, 3, 90042), ("B", 5, 5, 90043), ("B", 10, 2, 90044)])
+def test_raw_game_traces_on_fresh_seeds(gg, tmp_path, monkeypatch, variant, N, n, seed):
+    """Raw HexGame.make_move traces (random moves incl. occupied cells, played on past the win) of the live reference: the oracle
+    for both variants, the device logic for variant A (the raw handle of the C ABI is the variant-A game)."""
+    from test_oracle_golden import test_raw_game_traces as check_oracle
+    monkeypatch.setattr(gg, "OUT", str(tmp_path))
+    gg.gen_raw_games(variant, N, n, seed)
+    path = str(tmp_path / ("game_%s_N%d.npz" % (variant, N)))
+    monkeypatch.setattr("test_oracle_golden.load", lambda name: np.load(path))
+    check_oracle("game_%s_N%d.npz" % (variant, N))
+    if variant == "A":
+        parity.golden_raw_game(_emu, path)
