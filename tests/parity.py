@@ -44,7 +44,7 @@ def golden_rollout(make, name):
     z = np.load(os.path.join(GOLDEN, name))
     N, seed, fused = int(z["N"]), int(z["seed"]), int(z["fused"])
     T, G = z["actions"].shape
-    if name.startswith("selfplay"):
+    if os.path.basename(name).startswith("selfplay"):    # a fixture's file name, or the path of a trace written elsewhere
         env = make(hexref.KIND_SELFPLAY_B, N, G, seed=seed, agent_mode=int(z["agent_mode"]))
     else:
         env = make(hexref.KIND_ENV_A, N, G, seed=seed, opponent_first=bool(int(z["opponent_first"])))

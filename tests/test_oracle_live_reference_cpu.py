@@ -30,23 +30,27 @@ def _emu(kind, N, G, **kw):
     return make(kind, N, G, **kw)
 
 
-@pytest.mark.parametrize("N,G,T,seed,agent_mode,fused", [(4, 10, 40, 90001, 2, True), (6, 8, 60, 90002, 0, False), (9, 4, 90, 90003, 1, True)])
+@pytest.mark.parametrize("N,G,T,seed,agent_mode,fused", [(4, 10, 40, 90001, 2, True), (6, 8, 60, 90002, 0, False), (9, 4, 90, 90003, 1, True),
+                                                      (11, 4, 140, 90004, 2, True), (13, 2, 120, 90005, 2, False)])
 def test_selfplay_rollouts_on_fresh_seeds(gg, tmp_path, N, G, T, seed, agent_mode, fused):
     from test_oracle_golden import _check_rollout
     o = gg.rollout("B", N, G, T, seed=seed, agent_mode=agent_mode, fused=fused)
     path = str(tmp_path / "selfplay_live.npz")
     np.savez_compressed(path, N=N, seed=seed, agent_mode=agent_mode, fused=int(fused), **o)
     _check_rollout(path, hexref.KIND_SELFPLAY_B)
+    parity.golden_rollout(_emu, path)           # the device logic against the same live trace
     assert o["done"].sum() > 0
 
 
-@pytest.mark.parametrize("N,G,T,seed,of,fused", [(4, 10, 40, 90011, 0, True), (6, 8, 50, 90012, 1, False)])
+@pytest.mark.parametrize("N,G,T,seed,of,fused", [(4, 10, 40, 90011, 0, True), (6, 8, 50, 90012, 1, False), (7, 6, 70, 90013, 0, False),
+                                              (11, 3, 130, 90014, 1, True)])
 def test_envA_rollouts_on_fresh_seeds(gg, tmp_path, N, G, T, seed, of, fused):
     from test_oracle_golden import _check_rollout
     o = gg.rollout("A", N, G, T, seed=seed, agent_mode=0, fused=fused, opponent_first=bool(of))
     path = str(tmp_path / "envA_live.npz")
     np.savez_compressed(path, N=N, seed=seed, opponent_first=of, fused=int(fused), **o)
     _check_rollout(path, hexref.KIND_ENV_A)
+    parity.golden_rollout(_emu, path)
 
 
 @pytest.mark.parametrize("make", [_oracle, _emu], ids=["oracle", "emulator"])
@@ -67,7 +71,8 @@ def test_batched_opponent_predict_on_fresh_seeds(gg, tmp_path, monkeypatch, make
     parity.golden_oppredict_batched(make, str(tmp_path / ("oppredict_N%d_of%d.npz" % (N, int(of)))))
 
 
-@pytest.mark.parametrize("variant,N,n,seed", [("A", 4, 6, 90041), ("A", 8, 3, 90042), ("B", 5, 5, 90043), ("B", 10, 2, 90044)])
+@pytest.mark.parametrize("variant,N,n,seed", [("A", 4, 6, 90041), ("A", 8, 3, 90042), ("B", 5, 5, 90043), ("B", 10, 2, 90044),
+                                              ("A", 19, 1, 90045), ("B", 19, 1, 90046)])
 def test_raw_game_traces_on_fresh_seeds(gg, tmp_path, monkeypatch, variant, N, n, seed):
     """Raw HexGame.make_move traces (random moves incl. occupied cells, played on past the win) of the live reference: the oracle
     for both variants, the device logic for variant A (the raw handle of the C ABI is the variant-A game)."""
