@@ -369,6 +369,8 @@ class HexBatch(object):
             check(self._lib.hexb_set_eval(self._h, int(bool(eval_state)), _ptr(self.eval_episode), self._stream()))
         self.cfg.eval_state = int(bool(eval_state))
 
+    opponent_eps = None   # what set_opponent_eps last set (None: the caller's action always)
+
     def set_opponent_eps(self, eps):
         """Variant-A HexEnv(opponent_policy="opponent_predict", eps=...) (HexGame.py:354-359) on a manual_opponent batch: every
         opponent half step first draws rv from the game's stream and lets random_policy move when rv < eps, else plays the
@@ -492,6 +494,7 @@ class HexBatch(object):
             t = getattr(self, name, None)
             if t is not None:
                 sd[name] = t.clone()
+        sd["opponent_eps"] = self.opponent_eps    # run-time switch of the handle (set_opponent_eps), not part of hexb_config
         return sd
 
     def load_state_dict(self, sd):
@@ -505,6 +508,8 @@ class HexBatch(object):
         self._state[off:off + self.state_bytes].copy_(sd["state"].to(self.device))
         if "eval_episode" in sd or bool(sd["config"].get("eval_state", 0)) != self.eval_state:   # set_eval is a run-time switch
             self.set_eval(bool(sd["config"].get("eval_state", 0)))
+        if "opponent_eps" in sd and sd["opponent_eps"] != self.opponent_eps:   # HexEnv.eps of opponent_predict, a run-time switch too
+            self.set_opponent_eps(sd["opponent_eps"])
         for name in ("opp_index", "to_move", "eval_episode", "last_move_opponent", "winner"):
             t = getattr(self, name, None)
             if t is not None:
