@@ -77,16 +77,26 @@ class ShardedHexBatch(object):
     def step(self, *a, **k):
         return self.local.step(*a, **k)
 
-    def global_stats(self):
-        """Episode statistics summed over all ranks (device int64[8]). The all-reduce runs on a side stream that waits for
-        the statistics copy only, so step kernels issued afterwards are not held up by it."""
+    def global_stats_begin(self):
+        """Start the global sum: the statistics kernel on the caller's stream, the all-reduce on a side stream that waits for
+        that kernel only. Returns at once; step kernels issued on the caller's stream afterwards are NOT held up by the
+        collective (this is the form bench.py uses around its timed bracket). global_stats_end() joins."""
         main = torch.cuda.current_stream(self.local.device)
         self.local.stats(out=self._stats)
         self._side.wait_stream(main)
         with torch.cuda.stream(self._side):
             allreduce_stats(self._stats, self.group)
-        main.wait_stream(self._side)
+
+    def global_stats_end(self):
+        """Make the caller's stream wait for the all-reduce started by global_stats_begin(); returns the device int64[8] sums."""
+        torch.cuda.current_stream(self.local.device).wait_stream(self._side)
         return self._stats
+
+    def global_stats(self):
+        """Episode statistics summed over all ranks (device int64[8]): begin + end. The caller's stream waits for the 64-byte
+        all-reduce here, because the result is read on it; use the begin / end pair to keep it away from the step kernels."""
+        self.global_stats_begin()
+        return self.global_stats_end()
 
     def global_stats_dict(self):
         return dict(zip(STAT_NAMES, self.global_stats().cpu().tolist()))
