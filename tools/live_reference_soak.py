@@ -14,7 +14,7 @@ def one(seed):
     import numpy as np
     import parity
     from oracle import gen_golden as gg, hexref
-    from test_emu_parity import make as emu
+    from test_emu_parity import make as emu, EmuBatch
     from test_oracle_golden import _check_rollout
     import test_oracle_golden as tog
     rs = np.random.RandomState(seed)
@@ -60,6 +60,27 @@ def one(seed):
                 if variant == "A":
                     parity.golden_raw_game(emu, p)
                 done.append("raw %s N=%d" % (variant, N))
+            # preset boards: HexGame.__init__ rebuilding the planes in raster order, and HexEnv.reset adopting its cached planes
+            N = int(rs.randint(3, 14)); n = int(rs.randint(2, 7))
+            gg.gen_preset_boards(N, n, seed + 5)
+            p = os.path.join(tmp, "preset_N%d.npz" % N)
+            tc = np.load(p)["board_true"]
+
+            def oracle_raw(kind, N, G):
+                b = hexref.RefBatch(kind, N, G)
+                b.set_board(tc if kind == hexref.KIND_GAME_A else np.where(tc == 0, -1, np.where(tc == 1, 1, 0)).astype(np.int8), cur=0)
+                return b
+
+            def emu_raw(kind, N, G):
+                env = EmuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True)
+                env.reset()
+                env.import_boards(tc, np.zeros(G, np.int8))
+                return env
+            parity.golden_preset(oracle_raw, p); parity.golden_preset(emu_raw, p)
+            gg.gen_preset_resets(N, n, seed + 6)
+            parity.golden_preset_resets(lambda kind, N, G: EmuBatch(0 if kind == hexref.KIND_GAME_A else 1, N, G, raw=True),
+                                        os.path.join(tmp, "presetreset_N%d.npz" % N), need_merges=False)
+            done.append("presets N=%d" % N)
         except Exception as e:   # noqa: BLE001 - report the seed and go on
             return seed, "FAIL after %s: %s: %s" % (done, type(e).__name__, str(e)[:300])
         finally:
@@ -78,5 +99,5 @@ if __name__ == "__main__":
             if err:
                 bad += 1
                 print("seed %d: %s" % (seed, err), flush=True)
-    print("live-reference soak done: %d seeds x 6 traces (env rollouts of both variants, learned opponents + evaluation cycle, "
-          "batched opponent_predict, raw games of both variants), failures: %d" % (count, bad))
+    print("live-reference soak done: %d seeds x 7 traces (env rollouts of both variants, learned opponents + evaluation cycle, "
+          "batched opponent_predict, raw games of both variants, preset boards and repeated resets on them), failures: %d" % (count, bad))
