@@ -58,3 +58,28 @@ def test_product_never_touches_the_oracle_or_the_emulator():
     import sys
     code = "import sys, hex_gym_env_b200; bad = [m for m in sys.modules if m.split('.')[0] in ('oracle', 'emu')]; assert not bad, bad"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=os.path.dirname(root))
+
+
+def test_vec_env_rejects_option_mixes_before_touching_a_gpu():
+    """HexVecEnv's option checks (which reference env each option belongs to) fire before any device work."""
+    import pytest
+    from hex_gym_env_b200.vec_env import HexVecEnv
+    for kw in (dict(variant="hex-v1"), dict(output="jax"), dict(variant="hex-v0", sample_board=True),
+               dict(variant="hex-v0", base_model=lambda o, m: None), dict(variant="selfplay", sample_board=True, base_model=lambda o, m: None),
+               dict(variant="selfplay", opponent_model=lambda o, m: None)):
+        with pytest.raises(ValueError):
+            HexVecEnv(board_size=5, num_envs=4, **kw)
+
+
+def test_lazy_infos_follow_the_sb3_shape():
+    """output='torch': infos behaves like SB3's list of dicts - terminal_observation only for the finished games."""
+    from hex_gym_env_b200.vec_env import _LazyInfos
+    done = np.array([0, 1, 0], np.uint8)
+    term = np.arange(3 * 4, dtype=np.int8).reshape(3, 2, 2)
+    infos = _LazyInfos(done, term, 3)
+    assert len(infos) == 3 and infos[0] == {} and infos[2] == {}
+    assert set(infos[1]) == {"terminal_observation", "TimeLimit.truncated"} and infos[1]["TimeLimit.truncated"] is False
+    assert np.array_equal(infos[1]["terminal_observation"], term[1])
+    assert [bool(i) for i in infos] == [False, True, False]
+    t = _LazyInfos(torch.tensor([1, 0]), torch.ones(2, 2, 2), 2)[0]["terminal_observation"]
+    assert isinstance(t, torch.Tensor) and t.shape == (2, 2)
