@@ -83,3 +83,13 @@ def test_lazy_infos_follow_the_sb3_shape():
     assert [bool(i) for i in infos] == [False, True, False]
     t = _LazyInfos(torch.tensor([1, 0]), torch.ones(2, 2, 2), 2)[0]["terminal_observation"]
     assert isinstance(t, torch.Tensor) and t.shape == (2, 2)
+
+
+def test_rollout_helpers_have_no_cpu_path():
+    """masked_sample / gae are kernels of libhexb.so: CPU tensors are refused, nothing is computed in torch instead."""
+    import pytest
+    from hex_gym_env_b200.rollout import gae, masked_sample
+    with pytest.raises(RuntimeError):
+        masked_sample(torch.zeros(4, 9), torch.ones(4, 9, dtype=torch.uint8))
+    with pytest.raises(RuntimeError):
+        gae(torch.zeros(3, 4), torch.zeros(4, 4), torch.zeros(3, 4, dtype=torch.uint8))
