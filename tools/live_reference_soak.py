@@ -1,6 +1,7 @@
 """One-off CPU soak: the UNMODIFIED reference run live (oracle/gen_golden.py's drivers on /root/reference or oracle/_ref) on
 many fresh seeds, every trace replayed through the C oracle AND the device logic (the emulator build of csrc/*.cuh) with the
-checkers the committed fixtures go through. python tools/live_reference_soak.py [first_seed] [count] [processes]"""
+checkers the committed fixtures go through. python tools/live_reference_soak.py [first_seed] [count] [processes]
+SOAK_BIG=1: the two env rollouts on boards of 10x10 ... 19x19 (2-3 games, long enough to finish episodes)."""
 import os
 import sys
 import tempfile
@@ -24,14 +25,18 @@ def one(seed):
     with tempfile.TemporaryDirectory() as tmp:
         gg.OUT = tmp
         try:
-            N = int(rs.randint(3, 12)); G = int(rs.randint(2, 9)); T = int(rs.randint(20, 5 * N + 30))
+            big = os.environ.get("SOAK_BIG") == "1"     # large boards: few games, rollouts long enough to finish episodes
+            N = int(rs.randint(12, 20)) if big else int(rs.randint(3, 12))
+            G = int(rs.randint(2, 4)) if big else int(rs.randint(2, 9))
+            T = int(N * N // 2 + rs.randint(10, 60)) if big else int(rs.randint(20, 5 * N + 30))
             am, fused = int(rs.randint(3)), bool(rs.randint(2))
             o = gg.rollout("B", N, G, T, seed=seed, agent_mode=am, fused=fused)
             p = os.path.join(tmp, "selfplay_live.npz")
             np.savez_compressed(p, N=N, seed=seed, agent_mode=am, fused=int(fused), **o)
             _check_rollout(p, hexref.KIND_SELFPLAY_B); parity.golden_rollout(emu, p)
             done.append("selfplay N=%d" % N)
-            N = int(rs.randint(3, 10)); of = int(rs.randint(2))
+            N = int(rs.randint(10, 20)) if big else int(rs.randint(3, 10))
+            of = int(rs.randint(2))
             o = gg.rollout("A", N, G, T, seed=seed + 1, agent_mode=0, fused=fused, opponent_first=bool(of))
             p = os.path.join(tmp, "envA_live.npz")
             np.savez_compressed(p, N=N, seed=seed + 1, opponent_first=of, fused=int(fused), **o)
